@@ -1,0 +1,156 @@
+/*
+ * advhmm.h -- C-ABI of the B200 Viterbi / forward engine for adVNTR's profile HMMs.
+ *
+ * This is the drop-in boundary of the hot path.  The reference has no C-level plugin
+ * ABI: its engine is the private Cython methods of the vendored pomegranate
+ * (/root/reference/pomegranate/hmm.pyx).  Each entry point below names the reference
+ * interface it replaces; INTEGRATION.md shows the ctypes stub a reference maintainer
+ * would add to pomegranate's `HiddenMarkovModel` to bind them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer it passes;
+ *   - the library owns all device memory tied to a context / model handle; per-context
+ *     workspaces grow, they are never allocated per call;
+ *   - every function returns ADVHMM_OK (0) or a negative ADVHMM_E* code;
+ *     advhmm_last_error() gives the thread-local message of the last failure;
+ *   - a handle may be used from one host thread at a time; one CUDA stream per context;
+ *   - multi-GPU = one context (and one copy of each model) per device, no collective.
+ *   - symbols are small integer codes 0..n_symbols-1 (A,C,G,T = 0,1,2,3 for DNA), one
+ *     byte per base in host/device buffers; the engine packs them 2-bit internally.
+ */
+#ifndef ADVHMM_H_
+#define ADVHMM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADVHMM_ABI_VERSION 1
+
+/* error codes */
+#define ADVHMM_OK             0
+#define ADVHMM_EINVAL        -1  /* bad argument / malformed model                        */
+#define ADVHMM_ECUDA         -2  /* CUDA runtime failure (message has the CUDA error)     */
+#define ADVHMM_ENOMEM        -3  /* host or device allocation failed                      */
+#define ADVHMM_ESYMBOL       -4  /* a read contains a code >= n_symbols                   */
+#define ADVHMM_ECAPACITY     -5  /* caller's path buffer too small (see path_total)       */
+#define ADVHMM_EUNSUPPORTED  -6  /* feature not available for this model / precision      */
+
+/* flags for the decoding calls */
+#define ADVHMM_WANT_PATH      0x1u  /* backtrack on device and return state paths          */
+#define ADVHMM_BOTH_STRANDS   0x2u  /* also decode the reverse complement of every read;   */
+                                    /* results are interleaved: 2*i forward, 2*i+1 revcomp */
+#define ADVHMM_FP32           0x4u  /* fp32 DP arithmetic (tolerance documented in DESIGN) */
+#define ADVHMM_FORCE_GENERIC  0x8u  /* use the generic CSR kernel even if the model is     */
+                                    /* banded (testing / cross-checking)                   */
+
+/* kernel families a model can be compiled to (advhmm_model_info.kind) */
+#define ADVHMM_KIND_GENERIC   0     /* any baked model: row-synchronous CSR kernel         */
+#define ADVHMM_KIND_BANDED    1     /* profile-shaped model: register wavefront kernel     */
+
+typedef struct advhmm_context advhmm_context;
+typedef struct advhmm_model   advhmm_model;
+
+/*
+ * A baked model, exactly the arrays pomegranate's bake() produces
+ * (hmm.pyx:844-1123): states 0..silent_start-1 emit, silent_start..n_states-1 are
+ * silent and topologically ordered; in-edges of state l are
+ * in_src/in_logp[in_off[l] .. in_off[l+1]) in the reference's in-edge order (it
+ * decides Viterbi tie-breaking); emis[l*n_symbols + code] is the emission
+ * log-probability (+ log state weight) of emitting state l.
+ */
+typedef struct advhmm_model_desc {
+    int32_t        n_states;
+    int32_t        silent_start;
+    int32_t        start_index;
+    int32_t        end_index;
+    int32_t        finite;       /* 1: logp = v[n][end_index]; 0: best state (hmm.pyx:2089-2098) */
+    int32_t        n_symbols;    /* 1..16 */
+    const int32_t* in_off;       /* [n_states + 1] */
+    const int32_t* in_src;       /* [in_off[n_states]] */
+    const double*  in_logp;      /* [in_off[n_states]] */
+    const double*  emis;         /* [silent_start * n_symbols] */
+} advhmm_model_desc;
+
+typedef struct advhmm_model_info {
+    int32_t kind;            /* ADVHMM_KIND_*                                           */
+    int32_t n_states;
+    int32_t n_edges;         /* edges the DP evaluates (dead silent->silent edges dropped) */
+    int32_t n_columns;       /* banded: profile columns; generic: silent levels         */
+    int32_t n_final_states;  /* banded: silent states evaluated only on the last row    */
+    int32_t smem_bytes;      /* shared memory the model tables occupy per CTA           */
+    int32_t max_in_degree;
+    int32_t reserved;
+} advhmm_model_info;
+
+/* ---- contexts ------------------------------------------------------------------------- */
+
+/* Create an engine context on CUDA device `device`.  `stream` is a cudaStream_t to launch
+ * on (e.g. torch's current stream) or NULL to let the context create its own. */
+int  advhmm_context_create(int device, void* stream, advhmm_context** out);
+void advhmm_context_destroy(advhmm_context* ctx);
+/* Block until everything queued on the context's stream has finished. */
+int  advhmm_context_synchronize(advhmm_context* ctx);
+/* The cudaStream_t the context launches on (for CUDA-event timing by the caller). */
+void* advhmm_context_stream(advhmm_context* ctx);
+/* Number of kernels this context has launched since creation (bench `gpu_launches`). */
+int64_t advhmm_context_launch_count(advhmm_context* ctx);
+
+/* ---- models ---------------------------------------------------------------------------
+ * Replaces the tail of HiddenMarkovModel.bake() (hmm.pyx:932-1023: building the C arrays
+ * the DP kernels read) -- the host analyses the graph once (silent levels / profile
+ * columns, row-0 closure, first-row tables) and uploads the tables. */
+int  advhmm_model_create(advhmm_context* ctx, const advhmm_model_desc* desc, advhmm_model** out);
+void advhmm_model_destroy(advhmm_model* model);
+int  advhmm_model_info_get(const advhmm_model* model, advhmm_model_info* out);
+
+/* ---- decoding, host buffers -------------------------------------------------------------
+ * Replaces HiddenMarkovModel.viterbi / _viterbi (hmm.pyx:1911-2136) for a batch of reads
+ * of ONE model.  seqs holds the reads back to back, read r = seqs[seq_off[r] .. seq_off[r+1]).
+ * n_out = n_reads * (BOTH_STRANDS ? 2 : 1) results are produced:
+ *   logp[n_out]      Viterbi log-probability, -inf for an impossible read (hmm.pyx:1967)
+ *   path_len[n_out]  number of states on the path (silent ones included), -1 if impossible
+ *   path_off[n_out]  start of that read's path inside `path`
+ *   path[path_cap]   state indices in the baked order, concatenated (order unspecified)
+ *   *path_total      total entries written (or needed, with ADVHMM_ECAPACITY)
+ * path*, path_total may be NULL when ADVHMM_WANT_PATH is not set. */
+int advhmm_viterbi_batch(advhmm_model* model,
+                         const uint8_t* seqs, const int64_t* seq_off, int32_t n_reads,
+                         uint32_t flags,
+                         double* logp, int32_t* path_len, int64_t* path_off,
+                         int32_t* path, int64_t path_cap, int64_t* path_total);
+
+/* Replaces HiddenMarkovModel.log_probability / _forward (hmm.pyx:1258-1313, 1371-1484). */
+int advhmm_log_probability_batch(advhmm_model* model,
+                                 const uint8_t* seqs, const int64_t* seq_off, int32_t n_reads,
+                                 uint32_t flags, double* logp);
+
+/* ---- decoding, many loci in one launch ---------------------------------------------------
+ * The batched form of the per-locus loop (genome_analyzer.py:280 x vntr_finder.py:727-767):
+ * read r is decoded against models[read_model[r]].  All models must belong to one context.
+ * Buffers are HOST buffers unless ADVHMM_DEVICE_BUFFERS is set, in which case every pointer
+ * except `models` is a device pointer, nothing is copied, the call is asynchronous on the
+ * context's stream and *path_total is a device int64 (ECAPACITY is reported by path_len=-2). */
+#define ADVHMM_DEVICE_BUFFERS 0x100u
+int advhmm_viterbi_multi(advhmm_context* ctx,
+                         advhmm_model* const* models, int32_t n_models,
+                         const int32_t* read_model,
+                         const uint8_t* seqs, const int64_t* seq_off, int32_t n_reads,
+                         uint32_t flags,
+                         double* logp, int32_t* path_len, int64_t* path_off,
+                         int32_t* path, int64_t path_cap, int64_t* path_total);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+const char* advhmm_last_error(void);
+int         advhmm_abi_version(void);
+/* Encode ASCII DNA to codes A,C,G,T -> 0..3 (both cases).  Returns -1 on success or the index
+ * of the first byte that is not ACGT (the wrapper raises the reference's ValueError for it,
+ * hmm.pyx:72-79). */
+int64_t     advhmm_encode_acgt(const char* ascii, int64_t n, uint8_t* codes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADVHMM_H_ */
