@@ -1,0 +1,1435 @@
+// advhmm.cu -- B200 (sm_100a) Viterbi / forward engine for adVNTR's profile HMMs + its C-ABI.
+//
+// Replaces the vendored pomegranate's `_viterbi` / `_forward`
+// (/root/reference/pomegranate/hmm.pyx:1970-2136, 1371-1484) for batches of reads.
+// See DESIGN.md for the data layout and the roofline of each kernel.
+//
+// Kernels (all hand-written, no tensor cores -- this is max-plus DP, not a contraction):
+//   pack_reads_kernel        byte codes -> 2-bit packed reads (+ reverse complement, validation)
+//   banded_fill_kernel<RPL>  profile-shaped models: one warp per read, lanes own blocks of RPL
+//                            read positions, columns sweep as a register wavefront (skew 1
+//                            column per lane, 3 shuffles per step); model tables staged into
+//                            shared memory with one TMA bulk copy per CTA; 6-bit traceback per
+//                            (position, column) packed into one word per lane and step.
+//   banded_backtrack_kernel  device backtrack to the state path (one thread per read)
+//   generic_fill_kernel      any baked model: row-synchronous CSR kernel, silent states by level
+//   generic_backtrack_kernel
+//   generic_forward_kernel   log_probability (sum-product with the reference's pair_lse)
+//
+// Exactness: every DP value is produced by the same IEEE-754 double operations in the same
+// order as the reference ((v + t) + e per edge, strict '>' in candidate order), so paths and
+// log-probabilities are bit-identical; see model_compile.hpp for why the banded schedule may
+// skip / reorder the candidates it does.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "model_compile.hpp"
+
+using namespace advhmm;
+
+// =============================================================================================
+// error plumbing
+// =============================================================================================
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                          \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return set_error(e__ == cudaErrorMemoryAllocation ? ADVHMM_ENOMEM : ADVHMM_ECUDA, \
+                             "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),         \
+                             __FILE__, __LINE__);                                             \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, want = bytes); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// =============================================================================================
+// device-side model descriptors
+// =============================================================================================
+struct DevGeneric {
+    int m, S, K, start, end, finite, n_levels, max_in_degree;
+    const int32_t* in_off;
+    const int32_t* in_src;
+    const double* in_w;
+    const double* emis;
+    const double* v0;
+    const int32_t* tb0;
+    const int32_t* lvl_off;
+    const int32_t* lvl_state;
+};
+
+struct DevBanded {
+    int NC, P, S, m, NF, end_final, acc_col, n_acc;
+    int start, end, image_bytes, pad0;
+    double logp_empty;            // v0[end]: the answer for an empty read
+    const unsigned char* image;   // smem image: doubles w[9P] e[8P] v1[8P] accw[P], bytes cflag[P]
+    const int32_t* st;            // [3*NC] slot -> state
+    const int32_t* tb1;           // [4*S]
+    const int32_t* acc_src_col;   // [n_acc]
+    const int32_t* fin_state;     // [NF]
+    const int32_t* fin_off;       // [NF+1]
+    const int32_t* fin_src;
+    const double* fin_w;
+    const int32_t* tb0;           // [m]
+};
+
+struct Tile {
+    const void* model;   // DevBanded* or DevGeneric*
+    int32_t first;       // first index into order[]
+    int32_t cnt;         // reads in this tile (<= warps per block)
+};
+
+constexpr int kColFlagAccSrc = 1;
+constexpr int kColFlagAccDst = 2;
+constexpr int kMaxRPL = 10;             // read positions per lane: reads up to 320 bases on the banded path
+constexpr int kBandedWarps = 8;         // reads per CTA (banded)
+constexpr int kGenericWarpsMax = 8;
+
+}  // namespace
+
+struct advhmm_context {
+    int device = -1;             // < 0: host-only context (model analysis without a GPU)
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    size_t workspace_budget = 0;
+    DevBuf d_seqs, d_seq_off, d_pk, d_meta, d_work, d_out, d_paths, d_flags;
+    PinnedBuf h_meta, h_out;
+    cudaEvent_t meta_done = nullptr;
+    int banded_smem_set[kMaxRPL + 1] = {0};   // dynamic-smem opt-in already applied per RPL
+    int generic_smem_set = 0;
+    std::mutex mu;
+};
+
+struct advhmm_model {
+    advhmm_context* ctx = nullptr;
+    CompiledModel cm;
+    DevBuf blob;                 // all device tables of this model
+    DevGeneric* d_generic = nullptr;
+    DevGeneric* d_generic_fwd = nullptr;   // same tables, row 0 closed with pair_lse (forward)
+    DevBanded* d_banded = nullptr;
+    int banded_smem = 0;         // image bytes (0: not banded / does not fit)
+    advhmm_model_info info{};
+};
+
+// =============================================================================================
+// small device helpers
+// =============================================================================================
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ double shfl_up_f64(double v, int delta)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_up_sync(0xffffffffu, lo, delta);
+    hi = __shfl_up_sync(0xffffffffu, hi, delta);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int mask)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+    hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+    return __hiloint2double(hi, lo);
+}
+
+// symbol i of a 2-bit packed read
+__device__ __forceinline__ int packed_sym(const uint32_t* __restrict__ pk, int i)
+{
+    return (pk[i >> 4] >> ((i & 15) * 2)) & 3;
+}
+
+// lexicographic (max value, min index) warp all-reduce; result in every lane
+__device__ __forceinline__ void warp_argmax_first(double& v, int& idx)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = shfl_xor_f64(v, off);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+}
+
+// =============================================================================================
+// pack kernel: one CTA (32 threads) per result read
+// =============================================================================================
+struct PackArgs {
+    const uint8_t* seqs;
+    const int64_t* seq_off;     // [n_reads+1]
+    const int64_t* pk_off;      // [n_out] word offsets
+    uint32_t* pk;
+    int32_t* rlen;              // [n_out]
+    int32_t* bad;               // [1]: first read index with a code >= n_symbols (atomicMin)
+    int n_out, strands, n_symbols;
+};
+
+__global__ void __launch_bounds__(32) pack_reads_kernel(PackArgs a)
+{
+    const int q = blockIdx.x;
+    if (q >= a.n_out) return;
+    const int r = q / a.strands;
+    const bool rc = (a.strands == 2) && (q & 1);
+    const int64_t s0 = a.seq_off[r];
+    const int n = (int)(a.seq_off[r + 1] - s0);
+    const uint8_t* __restrict__ s = a.seqs + s0;
+    uint32_t* __restrict__ out = a.pk + a.pk_off[q];
+    const int words = (n + 15) / 16 + 1;
+    if (threadIdx.x == 0) a.rlen[q] = n;
+    bool bad = false;
+    for (int w = threadIdx.x; w < words; w += 32) {
+        uint32_t word = 0;
+        const int base = w * 16;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int p = base + k;
+            if (p < n) {
+                int code = rc ? s[n - 1 - p] : s[p];
+                if (code >= a.n_symbols) { bad = true; code = 0; }
+                if (rc) code = 3 - code;          // A<->T, C<->G under codes A,C,G,T = 0..3
+                word |= (uint32_t)(code & 3) << (2 * k);
+            }
+        }
+        out[w] = word;
+    }
+    if (bad) atomicMin(a.bad, r);
+}
+
+// =============================================================================================
+// banded fill kernel
+// =============================================================================================
+struct BandedArgs {
+    const Tile* tiles;
+    const int32_t* order;       // result-read id of every work item
+    int32_t chunk_base;         // first work item of this chunk (workspace slot = item - chunk_base)
+    const uint32_t* pk;
+    const int64_t* pk_off;
+    const int32_t* rlen;
+    double* logp;               // [n_out]
+    void* tbw;                  // traceback words, per slot 32 * Pmax words
+    size_t tbw_stride;          // words per slot
+    uint16_t* acc_tb;           // collector choice per (slot, position)
+    int acc_stride;             // entries per slot (32 * RPL)
+    double* vfin;               // last-row values, per slot 3 * Pmax
+    size_t vfin_stride;
+    int32_t* ftb;               // final-state choices, per slot 32
+};
+
+template <int RPL> struct TbWord { using type = uint32_t; };
+template <> struct TbWord<6> { using type = unsigned long long; };
+template <> struct TbWord<7> { using type = unsigned long long; };
+template <> struct TbWord<8> { using type = unsigned long long; };
+template <> struct TbWord<9> { using type = unsigned long long; };
+template <> struct TbWord<10> { using type = unsigned long long; };
+
+// first strict maximum of three candidates in order (hmm.pyx:2039: `if cand > best`)
+#define ADV_MAX3(a0, a1, a2, best, code)            \
+    do {                                            \
+        best = (a0); code = 0;                      \
+        if ((a1) > best) { best = (a1); code = 1; } \
+        if ((a2) > best) { best = (a2); code = 2; } \
+    } while (0)
+
+template <int RPL>
+__global__ void __launch_bounds__(kBandedWarps * 32)
+banded_fill_kernel(const BandedArgs a)
+{
+    using TBW = typename TbWord<RPL>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ double s_fval[kBandedWarps][32];
+
+    const Tile tile = a.tiles[blockIdx.x];
+    const DevBanded* __restrict__ M = reinterpret_cast<const DevBanded*>(tile.model);
+    const int P = M->P, NC = M->NC;
+
+    // ---- stage the model tables: one elected thread issues TMA bulk copies -----------------
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)M->image_bytes;
+        mbar_expect_tx(&s_bar, bytes);
+        for (uint32_t o = 0; o < bytes; o += 32768u) {
+            const uint32_t n = min(32768u, bytes - o);
+            tma_bulk_g2s(smem_raw + o, M->image + o, n, &s_bar);
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    mbar_wait(&s_bar, 0);
+    if (warp >= tile.cnt) return;
+
+    const double* __restrict__ sw = reinterpret_cast<const double*>(smem_raw);   // [9P]
+    const double* __restrict__ se = sw + 9 * P;                                   // [8P] I: sym, M: 4+sym
+    const double* __restrict__ sv1 = se + 8 * P;                                  // [8P]
+    const double* __restrict__ saccw = sv1 + 8 * P;                               // [P]
+    const unsigned char* __restrict__ sflag = reinterpret_cast<const unsigned char*>(saccw + P);
+
+    const int item = tile.first + warp;
+    const int q = a.order[item];
+    const size_t slot = (size_t)(item - a.chunk_base);
+    const int n = a.rlen[q];
+    if (n == 0) {
+        if (lane == 0) a.logp[q] = M->logp_empty;
+        return;
+    }
+    const int nl = (n + RPL - 1) / RPL;           // lanes in use
+    const int ln = (n - 1) / RPL, jn = (n - 1) % RPL;   // owner of the last row
+
+    // ---- my RPL symbols (2 bits each) ------------------------------------------------------
+    const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
+    uint32_t symbits;
+    {
+        const int bit = 2 * lane * RPL;
+        const int w = bit >> 5, sh = bit & 31;
+        const int last_word = (n + 15) / 16;      // allocation has (n+15)/16 + 1 words
+        const uint32_t lo = (w <= last_word) ? pk[w] : 0u;
+        const uint32_t hi = (w + 1 <= last_word) ? pk[w + 1] : 0u;
+        symbits = __funnelshift_r(lo, hi, sh);
+    }
+    int eoff[RPL];                                // sym * P
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) eoff[j] = (int)((symbits >> (2 * j)) & 3u) * P;
+
+    double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
+    int accarg[RPL];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; accarg[j] = 0; }
+    double bI = kNegInf, bM = kNegInf, bD = kNegInf;   // row above my block, previous column
+    int accord = 0;                                     // collector sources passed so far
+
+    TBW* __restrict__ tbw = reinterpret_cast<TBW*>(a.tbw) + slot * a.tbw_stride + (size_t)lane * P;
+    uint16_t* __restrict__ acc_tb = a.acc_tb + slot * (size_t)a.acc_stride + lane * RPL;
+    double* __restrict__ vfin = a.vfin + slot * a.vfin_stride;
+
+    const int steps = NC + nl - 1;
+    for (int t = 0; t < steps; ++t) {
+        // the row above my block at column c was finished by lane-1 in the previous step
+        const double uI0 = shfl_up_f64(cI[RPL - 1], 1);
+        const double uM0 = shfl_up_f64(cM[RPL - 1], 1);
+        const double uD0 = shfl_up_f64(cD[RPL - 1], 1);
+        const int c = t - lane;
+        if (c < 0 || c >= NC || lane >= nl) continue;
+
+        const double wII = sw[0 * P + c], wIM = sw[1 * P + c], wID = sw[2 * P + c];
+        const double wMI = sw[3 * P + c], wMM = sw[4 * P + c], wMD = sw[5 * P + c];
+        const double wDI = sw[6 * P + c], wDM = sw[7 * P + c], wDD = sw[8 * P + c];
+        const int flag = sflag[c];
+        const double aw = flag ? saccw[c] : kNegInf;
+
+        double uI = uI0, uM = uM0, uD = uD0;      // row above, this column
+        double oI = bI, oM = bM, oD = bD;         // row above, previous column
+        TBW word = 0;
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+            const double eI = se[eoff[j] + c];
+            const double eM = se[4 * P + eoff[j] + c];
+            double vI, vM, vD;
+            int kI, kM, kD;
+            ADV_MAX3((oI + wMI) + eM, (oM + wMM) + eM, (oD + wMD) + eM, vM, kM);
+            ADV_MAX3((uI + wII) + eI, (uM + wIM) + eI, (uD + wID) + eI, vI, kI);
+            ADV_MAX3(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, vD, kD);
+            if (j == 0 && lane == 0) {            // first read position: rows come from row 0
+                vI = sv1[eoff[0] + c];
+                vM = sv1[4 * P + eoff[0] + c];
+            }
+            if (flag & kColFlagAccDst) {
+                vD = acc[j];
+                acc_tb[j] = (uint16_t)accarg[j];
+            }
+            word |= (TBW)(kI | (kM << 2) | (kD << 4)) << (6 * j);
+            oI = cI[j]; oM = cM[j]; oD = cD[j];
+            cI[j] = vI; cM[j] = vM; cD[j] = vD;
+            uI = vI; uM = vM; uD = vD;
+            if (flag & kColFlagAccSrc) {
+                const double cand = vD + aw;
+                if (cand > acc[j]) { acc[j] = cand; accarg[j] = accord; }
+            }
+            if (j == jn && lane == ln) {
+                vfin[0 * P + c] = vI; vfin[1 * P + c] = vM; vfin[2 * P + c] = vD;
+            }
+        }
+        if (flag & kColFlagAccSrc) ++accord;
+        bI = uI0; bM = uM0; bD = uD0;
+        tbw[c] = word;
+    }
+    __syncwarp();
+
+    // ---- final-only silent states on the last row (hub reductions across the warp) ---------
+    const int NF = M->NF;
+    int32_t* __restrict__ ftb = a.ftb + slot * 32;
+    for (int f = 0; f < NF; ++f) {
+        const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
+        double best = kNegInf;
+        int arg = 0x7fffffff;
+        for (int k = k0 + lane; k < k1; k += 32) {
+            const int code = M->fin_src[k];
+            const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
+            const double cand = sv + M->fin_w[k];
+            if (cand > best) { best = cand; arg = k; }
+        }
+        warp_argmax_first(best, arg);
+        if (lane == 0) {
+            s_fval[warp][f] = best;
+            ftb[f] = (best > kNegInf) ? M->fin_src[arg] : 0;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) a.logp[q] = s_fval[warp][M->end_final];
+}
+
+// =============================================================================================
+// banded backtrack kernel: one thread per read
+// =============================================================================================
+struct BandedBtArgs {
+    const Tile* tiles;
+    const int32_t* order;
+    int32_t chunk_base;
+    int32_t n_items;            // work items in this chunk
+    int32_t rpl;                // RPL the fill kernel ran with
+    const uint32_t* pk;
+    const int64_t* pk_off;
+    const int32_t* rlen;
+    const double* logp;
+    const void* tbw;
+    size_t tbw_stride;
+    const uint16_t* acc_tb;
+    int acc_stride;
+    const int32_t* ftb;
+    const int32_t* item_tile;   // tile index of every work item
+    int32_t* path_len;          // [n_out]
+    int64_t* path_off;          // [n_out]
+    int32_t* path;
+    int64_t path_cap;
+    unsigned long long* cursor; // total path entries
+};
+
+template <typename Emit>
+__device__ __forceinline__ void banded_walk(const DevBanded* __restrict__ M, const BandedBtArgs& a,
+                                            size_t slot, int n, int sym0, Emit emit)
+{
+    const int P = M->P, rpl = a.rpl;
+    const int32_t* __restrict__ ftb = a.ftb + slot * 32;
+    int state;
+    if (n == 0) {
+        state = M->end;
+    } else {
+        int f = M->end_final, code;
+        for (;;) {
+            emit(M->fin_state[f]);
+            code = ftb[f];
+            if (code >= 0) break;
+            f = -(code + 1);
+        }
+        int sl = code / P, c = code - sl * P, r = n;
+        state = -1;
+        const bool wide = rpl > 5;
+        const uint32_t* tb32 = reinterpret_cast<const uint32_t*>(a.tbw) + slot * a.tbw_stride;
+        const unsigned long long* tb64 = reinterpret_cast<const unsigned long long*>(a.tbw) + slot * a.tbw_stride;
+        const uint16_t* acc_tb = a.acc_tb + slot * (size_t)a.acc_stride;
+        while (r >= 1) {
+            const int s = M->st[sl * M->NC + c];
+            emit(s);
+            const int ln = (r - 1) / rpl, j = (r - 1) - ln * rpl;
+            const size_t wi = (size_t)ln * P + c;
+            const uint32_t t = wide ? (uint32_t)(tb64[wi] >> (6 * j)) & 63u : (tb32[wi] >> (6 * j)) & 63u;
+            if (sl == SLOT_D) {
+                if (c == M->acc_col) c = M->acc_src_col[acc_tb[r - 1]];
+                else { sl = (t >> 4) & 3; c -= 1; }
+            } else if (r == 1) {
+                state = M->tb1[sym0 * M->S + s];
+                r = 0;
+            } else if (sl == SLOT_M) { sl = (t >> 2) & 3; c -= 1; r -= 1; }
+            else { sl = t & 3; r -= 1; }
+        }
+    }
+    // row 0: silent closure back to the start state
+    int guard = M->m + 1;
+    while (state != M->start && state >= 0 && guard-- > 0) { emit(state); state = M->tb0[state]; }
+    emit(state);
+}
+
+__global__ void __launch_bounds__(128) banded_backtrack_kernel(const BandedBtArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < a.n_items;
+    int len = 0, q = 0, n = 0, sym0 = 0;
+    size_t slot = 0;
+    const DevBanded* M = nullptr;
+    bool possible = false;
+    if (active) {
+        const int item = a.chunk_base + i;
+        q = a.order[item];
+        slot = (size_t)i;
+        M = reinterpret_cast<const DevBanded*>(a.tiles[a.item_tile[item]].model);
+        n = a.rlen[q];
+        possible = a.logp[q] > kNegInf;
+        if (possible) {
+            if (n > 0) sym0 = packed_sym(a.pk + a.pk_off[q], 0);
+            banded_walk(M, a, slot, n, sym0, [&](int) { ++len; });
+        }
+    }
+    // warp-aggregated allocation of output space
+    const unsigned lane = threadIdx.x & 31;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(a.cursor, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (!active) return;
+    if (!possible) { a.path_len[q] = -1; a.path_off[q] = 0; return; }
+    const int64_t off = (int64_t)base + (incl - len);
+    a.path_off[q] = off;
+    if (off + len > a.path_cap) { a.path_len[q] = -2; return; }   // caller buffer too small
+    a.path_len[q] = len;
+    int32_t* out = a.path + off;
+    int w = len;
+    banded_walk(M, a, slot, n, sym0, [&](int s) { out[--w] = s; });
+}
+
+// =============================================================================================
+// generic kernels (any baked model): one warp per read, rows in shared or global memory
+// =============================================================================================
+struct GenericArgs {
+    const Tile* tiles;
+    const int32_t* order;
+    int32_t chunk_base;
+    const uint32_t* pk;
+    const int64_t* pk_off;
+    const int32_t* rlen;
+    double* logp;
+    int32_t* end_state;         // [n_out] state the path ends in
+    uint16_t* tb;               // per slot: max_n * m slots (rows 1..n)
+    size_t tb_stride;
+    double* rows;               // global DP rows (2 * m per slot) when they do not fit in smem
+    size_t rows_stride;
+    int warps;                  // warps per CTA
+    int rows_in_smem;
+};
+
+template <bool FWD>
+__device__ __forceinline__ double pair_lse_dev(double x, double y)
+{
+    // utils.pyx:72-90
+    if (x == kNegInf) return y;
+    if (y == kNegInf) return x;
+    if (x > y) return x + log(exp(y - x) + 1.0);
+    return y + log(exp(x - y) + 1.0);
+}
+
+// FWD = false: Viterbi (max, traceback); FWD = true: forward (pair_lse, no traceback)
+template <bool FWD>
+__global__ void __launch_bounds__(kGenericWarpsMax * 32) generic_fill_kernel(const GenericArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const Tile tile = a.tiles[blockIdx.x];
+    const DevGeneric* __restrict__ G = reinterpret_cast<const DevGeneric*>(tile.model);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= tile.cnt) return;
+    const int item = tile.first + warp;
+    const int q = a.order[item];
+    const size_t slot = (size_t)(item - a.chunk_base);
+    const int n = a.rlen[q];
+    const int m = G->m, S = G->S, K = G->K;
+    double* prev;
+    double* cur;
+    if (a.rows_in_smem) {
+        prev = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * m;
+    } else {
+        prev = a.rows + slot * a.rows_stride;
+    }
+    cur = prev + m;
+    const int32_t* __restrict__ in_off = G->in_off;
+    const int32_t* __restrict__ in_src = G->in_src;
+    const double* __restrict__ in_w = G->in_w;
+    const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
+    uint16_t* __restrict__ tb = FWD ? nullptr : a.tb + slot * a.tb_stride;
+
+    for (int l = lane; l < m; l += 32) prev[l] = G->v0[l];
+    __syncwarp();
+    // NOTE: the forward recurrence's row 0 uses pair_lse instead of max; for FWD the caller passes
+    // a model whose v0 was computed with pair_lse (DevGeneric::v0 of the forward table set).
+    for (int i = 0; i < n; ++i) {
+        const int x = packed_sym(pk, i);
+        // emitting states (hmm.pyx:2026-2042 / 1427-1444)
+        for (int l = lane; l < S; l += 32) {
+            const double e = G->emis[(size_t)l * K + x];
+            const int k0 = in_off[l], k1 = in_off[l + 1];
+            double best = kNegInf;
+            int code = 0;
+            for (int k = k0; k < k1; ++k) {
+                if (FWD) {
+                    best = pair_lse_dev<true>(best, prev[in_src[k]] + in_w[k]);
+                } else {
+                    const double cand = (prev[in_src[k]] + in_w[k]) + e;
+                    if (cand > best) { best = cand; code = k - k0; }
+                }
+            }
+            if (FWD) best = best + e;
+            cur[l] = best;
+            if (!FWD) tb[(size_t)i * m + l] = (uint16_t)code;
+        }
+        __syncwarp();
+        // silent states, level by level (states of one level do not feed each other)
+        const int nlv = G->n_levels;
+        for (int L = 0; L < nlv; ++L) {
+            const int lo = G->lvl_off[L], hi = G->lvl_off[L + 1];
+            for (int p = lo + lane; p < hi; p += 32) {
+                const int l = G->lvl_state[p];
+                const int k0 = in_off[l], k1 = in_off[l + 1];
+                double best = kNegInf;
+                int code = 0;
+                if (FWD) {
+                    // pass 1 (emitting sources) and pass 2 (silent sources) are summed separately
+                    // and then combined (hmm.pyx:1446-1480)
+                    double acc2 = kNegInf;
+                    for (int k = k0; k < k1; ++k) {
+                        const int src = in_src[k];
+                        const double t = cur[src] + in_w[k];
+                        if (src < S) best = pair_lse_dev<true>(best, t);
+                        else acc2 = pair_lse_dev<true>(acc2, t);
+                    }
+                    best = pair_lse_dev<true>(best, acc2);
+                } else {
+                    for (int k = k0; k < k1; ++k) {
+                        const double cand = cur[in_src[k]] + in_w[k];
+                        if (cand > best) { best = cand; code = k - k0; }
+                    }
+                    tb[(size_t)i * m + l] = (uint16_t)code;
+                }
+                cur[l] = best;
+            }
+            __syncwarp();
+        }
+        double* t = prev; prev = cur; cur = t;
+    }
+    // termination (hmm.pyx:2089-2098 / 1300-1313)
+    if (G->finite) {
+        if (lane == 0) {
+            a.logp[q] = prev[G->end];
+            if (!FWD) a.end_state[q] = G->end;
+        }
+    } else if (FWD) {
+        if (lane == 0) {
+            double s = kNegInf;
+            for (int l = 0; l < S; ++l) s = pair_lse_dev<true>(s, prev[l]);
+            a.logp[q] = s;
+        }
+    } else {
+        double best = kNegInf;
+        int arg = 0x7fffffff;
+        for (int l = lane; l < m; l += 32)
+            if (prev[l] > best) { best = prev[l]; arg = l; }
+        warp_argmax_first(best, arg);
+        if (lane == 0) { a.logp[q] = best; a.end_state[q] = (best > kNegInf) ? arg : -1; }
+    }
+}
+
+struct GenericBtArgs {
+    const Tile* tiles;
+    const int32_t* order;
+    int32_t chunk_base;
+    int32_t n_items;
+    const int32_t* rlen;
+    const double* logp;
+    const int32_t* end_state;
+    const uint16_t* tb;
+    size_t tb_stride;
+    const int32_t* item_tile;
+    int32_t* path_len;
+    int64_t* path_off;
+    int32_t* path;
+    int64_t path_cap;
+    unsigned long long* cursor;
+};
+
+template <typename Emit>
+__device__ __forceinline__ void generic_walk(const DevGeneric* __restrict__ G, const uint16_t* __restrict__ tb,
+                                             int n, int end, Emit emit)
+{
+    const int m = G->m, S = G->S;
+    int px = n, py = end;
+    while (px > 0) {
+        emit(py);
+        const int src = G->in_src[G->in_off[py] + tb[(size_t)(px - 1) * m + py]];
+        if (py < S) --px;
+        py = src;
+    }
+    int guard = m + 1;
+    while (py != G->start && py >= 0 && guard-- > 0) { emit(py); py = G->tb0[py]; }
+    emit(py);
+}
+
+__global__ void __launch_bounds__(128) generic_backtrack_kernel(const GenericBtArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < a.n_items;
+    int len = 0, q = 0, n = 0, end = 0;
+    const DevGeneric* G = nullptr;
+    const uint16_t* tb = nullptr;
+    bool possible = false;
+    if (active) {
+        const int item = a.chunk_base + i;
+        q = a.order[item];
+        G = reinterpret_cast<const DevGeneric*>(a.tiles[a.item_tile[item]].model);
+        n = a.rlen[q];
+        tb = a.tb + (size_t)i * a.tb_stride;
+        end = a.end_state[q];
+        possible = a.logp[q] > kNegInf && end >= 0;
+        if (possible) generic_walk(G, tb, n, end, [&](int) { ++len; });
+    }
+    const unsigned lane = threadIdx.x & 31;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(a.cursor, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (!active) return;
+    if (!possible) { a.path_len[q] = -1; a.path_off[q] = 0; return; }
+    const int64_t off = (int64_t)base + (incl - len);
+    a.path_off[q] = off;
+    if (off + len > a.path_cap) { a.path_len[q] = -2; return; }
+    a.path_len[q] = len;
+    int32_t* out = a.path + off;
+    int w = len;
+    generic_walk(G, tb, n, end, [&](int s) { out[--w] = s; });
+}
+
+// =============================================================================================
+// host side: model upload
+// =============================================================================================
+struct BlobBuilder {
+    std::vector<unsigned char> bytes;
+    size_t add(const void* src, size_t n)
+    {
+        size_t off = (bytes.size() + 255) / 256 * 256;
+        bytes.resize(off + n);
+        if (n && src) memcpy(bytes.data() + off, src, n);
+        return off;
+    }
+    template <typename T> size_t add(const std::vector<T>& v) { return add(v.data(), v.size() * sizeof(T)); }
+};
+
+// forward-algorithm row 0 (hmm.pyx:1402-1424): same closure as Viterbi's with pair_lse
+std::vector<double> forward_row0(const GenericTables& g)
+{
+    auto lse = [](double x, double y) {
+        if (x == kNegInf) return y;
+        if (y == kNegInf) return x;
+        if (x > y) return x + std::log(std::exp(y - x) + 1.0);
+        return y + std::log(std::exp(x - y) + 1.0);
+    };
+    std::vector<double> f(g.m, kNegInf);
+    f[g.start] = 0.0;
+    for (int l = g.S; l < g.m; ++l) {
+        if (l == g.start) continue;
+        double acc = kNegInf;
+        for (int k = g.in_off[l]; k < g.in_off[l + 1]; ++k)
+            if (g.in_src[k] >= g.S) acc = lse(acc, f[g.in_src[k]] + g.in_w[k]);
+        f[l] = acc;
+    }
+    return f;
+}
+
+}  // namespace
+
+namespace {
+
+int upload_model(advhmm_model* mod)
+{
+    advhmm_context* ctx = mod->ctx;
+    const GenericTables& g = mod->cm.g;
+    const BandedTables& b = mod->cm.b;
+    BlobBuilder bb;
+    // generic tables
+    const size_t o_in_off = bb.add(g.in_off), o_in_src = bb.add(g.in_src), o_in_w = bb.add(g.in_w);
+    const size_t o_emis = bb.add(g.emis), o_v0 = bb.add(g.v0), o_tb0 = bb.add(g.tb0);
+    const size_t o_lvl_off = bb.add(g.lvl_off), o_lvl_state = bb.add(g.lvl_state);
+    const std::vector<double> f0 = forward_row0(g);
+    const size_t o_f0 = bb.add(f0);
+    // banded tables
+    size_t o_image = 0, o_st = 0, o_tb1 = 0, o_acc = 0, o_fs = 0, o_fo = 0, o_fsrc = 0, o_fw = 0;
+    int image_bytes = 0;
+    if (b.valid) {
+        const size_t P = b.NCpad;
+        std::vector<unsigned char> image((9 + 8 + 8 + 1) * P * sizeof(double) + (P + 15) / 16 * 16, 0);
+        double* d = reinterpret_cast<double*>(image.data());
+        memcpy(d, b.w.data(), 9 * P * sizeof(double));
+        memcpy(d + 9 * P, b.e.data(), 8 * P * sizeof(double));
+        memcpy(d + 17 * P, b.v1.data(), 8 * P * sizeof(double));
+        memcpy(d + 25 * P, b.accw.data(), P * sizeof(double));
+        unsigned char* fl = image.data() + 26 * P * sizeof(double);
+        for (int c : b.acc_src_col) fl[c] |= kColFlagAccSrc;
+        if (b.acc_col >= 0) fl[b.acc_col] |= kColFlagAccDst;
+        image_bytes = (int)image.size();
+        o_image = bb.add(image);
+        std::vector<int32_t> st(3 * (size_t)b.NC);
+        for (int t = 0; t < 3; ++t) memcpy(st.data() + (size_t)t * b.NC, b.st[t].data(), sizeof(int32_t) * b.NC);
+        o_st = bb.add(st); o_tb1 = bb.add(b.tb1); o_acc = bb.add(b.acc_src_col);
+        o_fs = bb.add(b.fin_state); o_fo = bb.add(b.fin_off); o_fsrc = bb.add(b.fin_src); o_fw = bb.add(b.fin_w);
+    }
+    const size_t o_dg = bb.add(nullptr, sizeof(DevGeneric));
+    const size_t o_dgf = bb.add(nullptr, sizeof(DevGeneric));
+    const size_t o_db = bb.add(nullptr, sizeof(DevBanded));
+
+    mod->info.kind = ADVHMM_KIND_GENERIC;
+    mod->info.n_states = g.m;
+    mod->info.n_edges = g.in_off[g.m];
+    mod->info.n_columns = g.n_levels;
+    mod->info.n_final_states = 0;
+    mod->info.smem_bytes = 0;
+    mod->info.max_in_degree = g.max_in_degree;
+    const size_t smem_limit = ctx->device >= 0 ? ctx->smem_optin : (size_t)232448;
+    const bool banded_ok = b.valid && (size_t)image_bytes + 4096 <= smem_limit;
+    if (banded_ok) {
+        mod->info.kind = ADVHMM_KIND_BANDED;
+        mod->info.n_columns = b.NC;
+        mod->info.n_final_states = (int)b.fin_state.size();
+        mod->info.smem_bytes = image_bytes;
+        mod->banded_smem = image_bytes;
+    }
+    if (ctx->device < 0) return ADVHMM_OK;   // host-only context: analysis only
+
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(mod->blob.ensure(bb.bytes.size()));
+    unsigned char* base = mod->blob.as<unsigned char>();
+    auto P8 = [&](size_t off) { return base + off; };
+    DevGeneric dg{};
+    dg.m = g.m; dg.S = g.S; dg.K = g.K; dg.start = g.start; dg.end = g.end; dg.finite = g.finite;
+    dg.n_levels = g.n_levels; dg.max_in_degree = g.max_in_degree;
+    dg.in_off = (const int32_t*)P8(o_in_off); dg.in_src = (const int32_t*)P8(o_in_src);
+    dg.in_w = (const double*)P8(o_in_w); dg.emis = (const double*)P8(o_emis);
+    dg.v0 = (const double*)P8(o_v0); dg.tb0 = (const int32_t*)P8(o_tb0);
+    dg.lvl_off = (const int32_t*)P8(o_lvl_off); dg.lvl_state = (const int32_t*)P8(o_lvl_state);
+    memcpy(bb.bytes.data() + o_dg, &dg, sizeof dg);
+    DevGeneric dgf = dg;
+    dgf.v0 = (const double*)P8(o_f0);
+    memcpy(bb.bytes.data() + o_dgf, &dgf, sizeof dgf);
+    if (b.valid) {
+        DevBanded db{};
+        db.NC = b.NC; db.P = b.NCpad; db.S = b.S; db.m = g.m; db.NF = (int)b.fin_state.size();
+        db.end_final = b.end_final; db.acc_col = b.acc_col; db.n_acc = (int)b.acc_src_col.size();
+        db.start = g.start; db.end = g.end; db.image_bytes = image_bytes;
+        db.logp_empty = g.v0[g.end];
+        db.image = P8(o_image); db.st = (const int32_t*)P8(o_st); db.tb1 = (const int32_t*)P8(o_tb1);
+        db.acc_src_col = (const int32_t*)P8(o_acc); db.fin_state = (const int32_t*)P8(o_fs);
+        db.fin_off = (const int32_t*)P8(o_fo); db.fin_src = (const int32_t*)P8(o_fsrc);
+        db.fin_w = (const double*)P8(o_fw); db.tb0 = (const int32_t*)P8(o_tb0);
+        memcpy(bb.bytes.data() + o_db, &db, sizeof db);
+    }
+    CU_TRY(cudaMemcpyAsync(base, bb.bytes.data(), bb.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    mod->d_generic = reinterpret_cast<DevGeneric*>(P8(o_dg));
+    mod->d_generic_fwd = reinterpret_cast<DevGeneric*>(P8(o_dgf));
+    mod->d_banded = banded_ok ? reinterpret_cast<DevBanded*>(P8(o_db)) : nullptr;
+    return ADVHMM_OK;
+}
+
+// =============================================================================================
+// host side: batch planning and launches
+// =============================================================================================
+struct Plan {
+    int n_reads = 0, n_out = 0, strands = 1;
+    std::vector<int64_t> pk_off;        // [n_out]
+    int64_t pk_words = 0;
+    // work items grouped by kernel family
+    std::vector<int32_t> order;         // banded items first, then generic items
+    std::vector<int32_t> item_tile;     // tile of every item
+    std::vector<Tile> tiles;            // banded tiles first
+    int n_banded_items = 0, n_banded_tiles = 0;
+    int max_len_banded = 0, max_len_generic = 0;
+    int max_P = 0, max_banded_smem = 0;
+    int max_m_generic = 0;
+};
+
+template <typename T> size_t vec_bytes(const std::vector<T>& v) { return v.size() * sizeof(T); }
+
+int launch_banded_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const BandedArgs& args)
+{
+#define ADV_CASE(R)                                                                                  \
+    case R: {                                                                                        \
+        if (smem > ctx->banded_smem_set[R]) {                                                        \
+            CU_TRY(cudaFuncSetAttribute(banded_fill_kernel<R>,                                       \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));         \
+            ctx->banded_smem_set[R] = smem;                                                          \
+        }                                                                                            \
+        banded_fill_kernel<R><<<grid, kBandedWarps * 32, smem, ctx->stream>>>(args);                 \
+        break;                                                                                       \
+    }
+    switch (rpl) {
+        ADV_CASE(1) ADV_CASE(2) ADV_CASE(3) ADV_CASE(4) ADV_CASE(5)
+        ADV_CASE(6) ADV_CASE(7) ADV_CASE(8) ADV_CASE(9) ADV_CASE(10)
+        default: return set_error(ADVHMM_EINVAL, "unsupported rows-per-lane %d", rpl);
+    }
+#undef ADV_CASE
+    CU_TRY(cudaGetLastError());
+    ctx->launches++;
+    return ADVHMM_OK;
+}
+
+struct OutPtrs {
+    double* logp; int32_t* path_len; int64_t* path_off; int32_t* path; int64_t path_cap;
+    unsigned long long* cursor;
+};
+
+// Runs the whole batch on the context's stream.  All pointers in `out` and d_seqs are device
+// pointers.  seq_off / group_off are HOST arrays (planning metadata).
+int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, const int64_t* group_off,
+              const uint8_t* d_seqs, const int64_t* seq_off, int n_reads, uint32_t flags,
+              const OutPtrs& out, bool forward, int32_t* d_bad)
+{
+    const bool want_path = (flags & ADVHMM_WANT_PATH) && !forward;
+    const int strands = (flags & ADVHMM_BOTH_STRANDS) ? 2 : 1;
+    const int n_out = n_reads * strands;
+    if (n_out == 0) return ADVHMM_OK;
+    if (flags & ADVHMM_FP32) return set_error(ADVHMM_EUNSUPPORTED, "fp32 mode is not available in this build");
+
+    // ---- plan ------------------------------------------------------------------------------
+    Plan pl;
+    pl.n_reads = n_reads; pl.n_out = n_out; pl.strands = strands;
+    pl.pk_off.resize(n_out);
+    int64_t words = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        const int64_t len = seq_off[r + 1] - seq_off[r];
+        if (len < 0 || len > 0x3fffffff) return set_error(ADVHMM_EINVAL, "bad seq_off at read %d", r);
+        for (int s = 0; s < strands; ++s) {
+            pl.pk_off[(size_t)r * strands + s] = words;
+            words += (len + 15) / 16 + 1;
+        }
+    }
+    pl.pk_words = words;
+    std::vector<int32_t> generic_items;
+    std::vector<int32_t> generic_item_model;
+    pl.order.reserve(n_out);
+    pl.item_tile.reserve(n_out);
+    std::vector<Tile> generic_tiles;
+    for (int gi = 0; gi < n_models; ++gi) {
+        advhmm_model* mod = models[gi];
+        if (!mod || mod->ctx != ctx) return set_error(ADVHMM_EINVAL, "model %d does not belong to this context", gi);
+        const int64_t r0 = group_off[gi], r1 = group_off[gi + 1];
+        if (r0 < 0 || r1 < r0 || r1 > n_reads) return set_error(ADVHMM_EINVAL, "bad group_off at model %d", gi);
+        const bool banded_model = !forward && mod->d_banded && !(flags & ADVHMM_FORCE_GENERIC);
+        int in_tile = 0;
+        for (int64_t r = r0; r < r1; ++r) {
+            const int len = (int)(seq_off[r + 1] - seq_off[r]);
+            for (int s = 0; s < strands; ++s) {
+                const int32_t q = (int32_t)(r * strands + s);
+                if (banded_model && len <= 32 * kMaxRPL) {
+                    if (in_tile == 0 || in_tile == kBandedWarps) {
+                        pl.tiles.push_back(Tile{mod->d_banded, (int32_t)pl.order.size(), 0});
+                        in_tile = 0;
+                    }
+                    pl.tiles.back().cnt = ++in_tile;
+                    pl.item_tile.push_back((int32_t)pl.tiles.size() - 1);
+                    pl.order.push_back(q);
+                    pl.max_len_banded = std::max(pl.max_len_banded, len);
+                    pl.max_P = std::max(pl.max_P, mod->cm.b.NCpad);
+                    pl.max_banded_smem = std::max(pl.max_banded_smem, mod->banded_smem);
+                } else {
+                    generic_items.push_back(q);
+                    generic_item_model.push_back(gi);
+                    pl.max_len_generic = std::max(pl.max_len_generic, len);
+                    pl.max_m_generic = std::max(pl.max_m_generic, mod->cm.g.m);
+                }
+            }
+        }
+    }
+    pl.n_banded_items = (int)pl.order.size();
+    pl.n_banded_tiles = (int)pl.tiles.size();
+    // generic launch geometry: as many warps per CTA as DP rows fit in shared memory
+    int gwarps = kGenericWarpsMax, rows_in_smem = 1;
+    if (!generic_items.empty()) {
+        const size_t per_warp = (size_t)pl.max_m_generic * 2 * sizeof(double);
+        const size_t budget = ctx->smem_optin > 8192 ? ctx->smem_optin - 8192 : 0;
+        gwarps = (int)std::min<size_t>(kGenericWarpsMax, per_warp ? budget / per_warp : kGenericWarpsMax);
+        if (gwarps < 1) { gwarps = 4; rows_in_smem = 0; }
+        int in_tile = 0, last_model = -1;
+        for (size_t i = 0; i < generic_items.size(); ++i) {
+            const int gi = generic_item_model[i];
+            if (in_tile == 0 || in_tile == gwarps || gi != last_model) {
+                const void* dm = forward ? (const void*)models[gi]->d_generic_fwd : (const void*)models[gi]->d_generic;
+                pl.tiles.push_back(Tile{dm, (int32_t)pl.order.size(), 0});
+                in_tile = 0;
+            }
+            last_model = gi;
+            pl.tiles.back().cnt = ++in_tile;
+            pl.item_tile.push_back((int32_t)pl.tiles.size() - 1);
+            pl.order.push_back(generic_items[i]);
+        }
+    }
+    const int n_generic_items = (int)pl.order.size() - pl.n_banded_items;
+
+    // ---- metadata upload (pinned staging, one H2D) -----------------------------------------
+    const size_t b_seq_off = (size_t)(n_reads + 1) * sizeof(int64_t);
+    const size_t b_pk_off = vec_bytes(pl.pk_off), b_order = vec_bytes(pl.order);
+    const size_t b_item_tile = vec_bytes(pl.item_tile), b_tiles = vec_bytes(pl.tiles);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_seq_off = 0, o_pk_off = o_seq_off + al(b_seq_off), o_order = o_pk_off + al(b_pk_off);
+    const size_t o_item_tile = o_order + al(b_order), o_tiles = o_item_tile + al(b_item_tile);
+    const size_t meta_bytes = o_tiles + al(b_tiles);
+    if (ctx->meta_done) CU_TRY(cudaEventSynchronize(ctx->meta_done));
+    CU_TRY(ctx->h_meta.ensure(meta_bytes));
+    CU_TRY(ctx->d_meta.ensure(meta_bytes));
+    unsigned char* hm = static_cast<unsigned char*>(ctx->h_meta.p);
+    memcpy(hm + o_seq_off, seq_off, b_seq_off);
+    memcpy(hm + o_pk_off, pl.pk_off.data(), b_pk_off);
+    memcpy(hm + o_order, pl.order.data(), b_order);
+    memcpy(hm + o_item_tile, pl.item_tile.data(), b_item_tile);
+    memcpy(hm + o_tiles, pl.tiles.data(), b_tiles);
+    CU_TRY(cudaMemcpyAsync(ctx->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->meta_done) CU_TRY(cudaEventCreateWithFlags(&ctx->meta_done, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(ctx->meta_done, ctx->stream));
+    unsigned char* dm = ctx->d_meta.as<unsigned char>();
+    const int64_t* d_seq_off = reinterpret_cast<const int64_t*>(dm + o_seq_off);
+    const int64_t* d_pk_off = reinterpret_cast<const int64_t*>(dm + o_pk_off);
+    const int32_t* d_order = reinterpret_cast<const int32_t*>(dm + o_order);
+    const int32_t* d_item_tile = reinterpret_cast<const int32_t*>(dm + o_item_tile);
+    const Tile* d_tiles = reinterpret_cast<const Tile*>(dm + o_tiles);
+
+    // ---- pack ------------------------------------------------------------------------------
+    const size_t pk_words_al = (size_t)(pl.pk_words + 63) / 64 * 64;
+    CU_TRY(ctx->d_pk.ensure(pk_words_al * sizeof(uint32_t) + (size_t)n_out * sizeof(int32_t)));
+    uint32_t* d_pk = ctx->d_pk.as<uint32_t>();
+    int32_t* d_rlen = reinterpret_cast<int32_t*>(d_pk + pk_words_al);
+    {
+        PackArgs pa{d_seqs, d_seq_off, d_pk_off, d_pk, d_rlen, d_bad, n_out, strands, 0};
+        pa.n_symbols = models[0]->cm.g.K;
+        pack_reads_kernel<<<n_out, 32, 0, ctx->stream>>>(pa);
+        CU_TRY(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (want_path) CU_TRY(cudaMemsetAsync(out.cursor, 0, sizeof(unsigned long long), ctx->stream));
+
+    // ---- workspace: sized once for both kernel families, chunks end on tile boundaries -------
+    const int rpl = std::max(1, (pl.max_len_banded + 31) / 32);
+    const size_t P = (size_t)pl.max_P;
+    const size_t word_bytes = rpl > 5 ? 8 : 4;
+    const size_t b_per_item = pl.n_banded_items
+        ? 32 * P * word_bytes + 3 * P * sizeof(double) + (size_t)32 * rpl * 2 + 32 * 4 : 0;
+    const size_t gm = (size_t)pl.max_m_generic;
+    const size_t g_tb_per = (want_path && n_generic_items)
+        ? (size_t)std::max(pl.max_len_generic, 1) * gm * sizeof(uint16_t) : 0;
+    const size_t g_rows_per = (n_generic_items && !rows_in_smem) ? 2 * gm * sizeof(double) : 0;
+    const size_t g_per_item = n_generic_items ? g_tb_per + g_rows_per + 8 : 0;
+    size_t b_chunk = 0, g_chunk = 0;
+    if (pl.n_banded_items) {
+        b_chunk = std::max<size_t>(ctx->workspace_budget / b_per_item, (size_t)kBandedWarps * ctx->sm_count);
+        b_chunk = std::min<size_t>(b_chunk, (size_t)pl.n_banded_items);
+    }
+    if (n_generic_items) {
+        g_chunk = std::max<size_t>(ctx->workspace_budget / g_per_item, (size_t)gwarps);
+        g_chunk = std::min<size_t>(g_chunk, (size_t)n_generic_items);
+    }
+    // banded layout
+    const size_t o_tbw = 0, o_vfin = al(b_chunk * 32 * P * word_bytes);
+    const size_t o_acc = o_vfin + al(b_chunk * 3 * P * sizeof(double));
+    const size_t o_ftb = o_acc + al(b_chunk * 32 * rpl * 2);
+    const size_t b_bytes = o_ftb + al(b_chunk * 32 * 4);
+    // generic layout (shares the buffer: the two families run one after the other on the stream)
+    const size_t o_gtb = 0, o_grows = al(g_chunk * g_tb_per);
+    const size_t g_bytes = o_grows + al(g_chunk * g_rows_per);
+    const size_t o_end = std::max(b_bytes, g_bytes);           // end_state[n_out], whole batch
+    CU_TRY(ctx->d_work.ensure(o_end + al((size_t)n_out * sizeof(int32_t))));
+    unsigned char* w = ctx->d_work.as<unsigned char>();
+
+    // [lo, hi) item ranges that start and end on tile boundaries and hold <= cap items
+    auto next_chunk = [&](int lo, int end, size_t cap) {
+        int hi = (int)std::min<size_t>((size_t)end, (size_t)lo + cap);
+        if (hi < end)
+            while (hi > lo && pl.item_tile[hi] == pl.item_tile[hi - 1]) --hi;
+        if (hi == lo) {   // a single tile larger than cap cannot happen (cap >= warps per CTA)
+            hi = lo + 1;
+            while (hi < end && pl.item_tile[hi] == pl.item_tile[hi - 1]) ++hi;
+        }
+        return hi;
+    };
+
+    // ---- banded reads -----------------------------------------------------------------------
+    for (int lo = 0; lo < pl.n_banded_items;) {
+        const int hi = next_chunk(lo, pl.n_banded_items, b_chunk);
+        const int items = hi - lo;
+        const int tile0 = pl.item_tile[lo], tile1 = pl.item_tile[hi - 1] + 1;
+        BandedArgs fa{};
+        fa.tiles = d_tiles + tile0; fa.order = d_order; fa.chunk_base = lo;
+        fa.pk = d_pk; fa.pk_off = d_pk_off; fa.rlen = d_rlen; fa.logp = out.logp;
+        fa.tbw = w + o_tbw; fa.tbw_stride = 32 * P;
+        fa.acc_tb = reinterpret_cast<uint16_t*>(w + o_acc); fa.acc_stride = 32 * rpl;
+        fa.vfin = reinterpret_cast<double*>(w + o_vfin); fa.vfin_stride = 3 * P;
+        fa.ftb = reinterpret_cast<int32_t*>(w + o_ftb);
+        int rc = launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_banded_smem, fa);
+        if (rc) return rc;
+        if (want_path) {
+            BandedBtArgs ba{};
+            ba.tiles = d_tiles; ba.order = d_order; ba.chunk_base = lo; ba.n_items = items; ba.rpl = rpl;
+            ba.pk = d_pk; ba.pk_off = d_pk_off; ba.rlen = d_rlen; ba.logp = out.logp;
+            ba.tbw = w + o_tbw; ba.tbw_stride = 32 * P;
+            ba.acc_tb = reinterpret_cast<const uint16_t*>(w + o_acc); ba.acc_stride = 32 * rpl;
+            ba.ftb = reinterpret_cast<const int32_t*>(w + o_ftb);
+            ba.item_tile = d_item_tile;
+            ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = out.path;
+            ba.path_cap = out.path_cap; ba.cursor = out.cursor;
+            banded_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
+            CU_TRY(cudaGetLastError());
+            ctx->launches++;
+        }
+        lo = hi;
+    }
+
+    // ---- everything else: generic kernel ----------------------------------------------------
+    if (n_generic_items > 0) {
+        const int smem = rows_in_smem ? (int)(gwarps * 2 * gm * sizeof(double)) : 0;
+        if (smem > 48 * 1024 && smem > ctx->generic_smem_set) {
+            CU_TRY(cudaFuncSetAttribute(generic_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU_TRY(cudaFuncSetAttribute(generic_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            ctx->generic_smem_set = smem;
+        }
+        const int gend = (int)pl.order.size();
+        for (int lo = pl.n_banded_items; lo < gend;) {
+            const int hi = next_chunk(lo, gend, g_chunk);
+            const int items = hi - lo;
+            const int tile0 = pl.item_tile[lo], tile1 = pl.item_tile[hi - 1] + 1;
+            GenericArgs ga{};
+            ga.tiles = d_tiles + tile0; ga.order = d_order; ga.chunk_base = lo;
+            ga.pk = d_pk; ga.pk_off = d_pk_off; ga.rlen = d_rlen; ga.logp = out.logp;
+            ga.end_state = reinterpret_cast<int32_t*>(w + o_end);
+            ga.tb = reinterpret_cast<uint16_t*>(w + o_gtb); ga.tb_stride = g_tb_per / sizeof(uint16_t);
+            ga.rows = reinterpret_cast<double*>(w + o_grows); ga.rows_stride = 2 * gm;
+            ga.warps = gwarps; ga.rows_in_smem = rows_in_smem;
+            if (forward) generic_fill_kernel<true><<<tile1 - tile0, gwarps * 32, smem, ctx->stream>>>(ga);
+            else generic_fill_kernel<false><<<tile1 - tile0, gwarps * 32, smem, ctx->stream>>>(ga);
+            CU_TRY(cudaGetLastError());
+            ctx->launches++;
+            if (want_path) {
+                GenericBtArgs ba{};
+                ba.tiles = d_tiles; ba.order = d_order; ba.chunk_base = lo; ba.n_items = items;
+                ba.rlen = d_rlen; ba.logp = out.logp; ba.end_state = ga.end_state;
+                ba.tb = ga.tb; ba.tb_stride = ga.tb_stride; ba.item_tile = d_item_tile;
+                ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = out.path;
+                ba.path_cap = out.path_cap; ba.cursor = out.cursor;
+                generic_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
+                CU_TRY(cudaGetLastError());
+                ctx->launches++;
+            }
+            lo = hi;
+        }
+    }
+    return ADVHMM_OK;
+}
+
+// host-buffer front end shared by the three public decoding calls
+int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, const int64_t* group_off,
+             const uint8_t* seqs, const int64_t* seq_off, int n_reads, uint32_t flags, bool forward,
+             double* logp, int32_t* path_len, int64_t* path_off, int32_t* path, int64_t path_cap,
+             int64_t* path_total)
+{
+    if (!ctx || ctx->device < 0) return set_error(ADVHMM_ECUDA, "this context has no CUDA device (host-only analysis context)");
+    if (n_reads < 0 || !seq_off || (n_reads > 0 && (!logp || !models || n_models <= 0)))
+        return set_error(ADVHMM_EINVAL, "null or negative argument");
+    const bool want_path = (flags & ADVHMM_WANT_PATH) && !forward;
+    if (want_path && (!path_len || !path_off || !path_total || (path_cap > 0 && !path)))
+        return set_error(ADVHMM_EINVAL, "ADVHMM_WANT_PATH needs path_len, path_off, path and path_total");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int strands = (flags & ADVHMM_BOTH_STRANDS) ? 2 : 1;
+    const int n_out = n_reads * strands;
+    if (path_total) *path_total = 0;
+    if (n_out == 0) return ADVHMM_OK;
+    const int64_t n_bases = seq_off[n_reads];
+    if (seq_off[0] != 0 || n_bases < 0) return set_error(ADVHMM_EINVAL, "seq_off must start at 0 and be non-decreasing");
+    if (n_bases > 0 && !seqs) return set_error(ADVHMM_EINVAL, "seqs is null");
+
+    CU_TRY(ctx->d_seqs.ensure((size_t)n_bases + 16));
+    if (n_bases) CU_TRY(cudaMemcpyAsync(ctx->d_seqs.p, seqs, (size_t)n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    // outputs: logp | path_len | path_off | cursor | bad
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_logp = 0, o_plen = al((size_t)n_out * 8), o_poff = o_plen + al((size_t)n_out * 4);
+    const size_t o_cursor = o_poff + al((size_t)n_out * 8), o_bad = o_cursor + 256, out_bytes = o_bad + 256;
+    CU_TRY(ctx->d_out.ensure(out_bytes));
+    unsigned char* d = ctx->d_out.as<unsigned char>();
+    int64_t cap = want_path ? path_cap : 0;
+    if (want_path) CU_TRY(ctx->d_paths.ensure((size_t)std::max<int64_t>(cap, 1) * sizeof(int32_t)));
+    OutPtrs op{reinterpret_cast<double*>(d + o_logp), reinterpret_cast<int32_t*>(d + o_plen),
+               reinterpret_cast<int64_t*>(d + o_poff), ctx->d_paths.as<int32_t>(), cap,
+               reinterpret_cast<unsigned long long*>(d + o_cursor)};
+    int32_t* d_bad = reinterpret_cast<int32_t*>(d + o_bad);
+    CU_TRY(cudaMemsetAsync(d_bad, 0x7f, sizeof(int32_t), ctx->stream));
+    int rc = run_batch(ctx, models, n_models, group_off, ctx->d_seqs.as<uint8_t>(), seq_off, n_reads, flags, op,
+                       forward, d_bad);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    // results back
+    CU_TRY(ctx->h_out.ensure(out_bytes));
+    CU_TRY(cudaMemcpyAsync(ctx->h_out.p, d, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    const unsigned char* h = static_cast<const unsigned char*>(ctx->h_out.p);
+    int32_t bad;
+    memcpy(&bad, h + o_bad, sizeof bad);
+    if (bad != 0x7f7f7f7f) return set_error(ADVHMM_ESYMBOL, "read %d contains a symbol code outside the model alphabet", bad);
+    memcpy(logp, h + o_logp, (size_t)n_out * 8);
+    if (want_path) {
+        memcpy(path_len, h + o_plen, (size_t)n_out * 4);
+        memcpy(path_off, h + o_poff, (size_t)n_out * 8);
+        unsigned long long total;
+        memcpy(&total, h + o_cursor, sizeof total);
+        *path_total = (int64_t)total;
+        if ((int64_t)total > path_cap)
+            return set_error(ADVHMM_ECAPACITY, "path buffer too small: need %lld entries, have %lld",
+                             (long long)total, (long long)path_cap);
+        if (total) {
+            CU_TRY(cudaMemcpyAsync(path, ctx->d_paths.p, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return ADVHMM_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" {
+
+const char* advhmm_last_error(void) { return g_last_error.c_str(); }
+int advhmm_abi_version(void) { return ADVHMM_ABI_VERSION; }
+
+int64_t advhmm_encode_acgt(const char* ascii, int64_t n, uint8_t* codes)
+{
+    static const struct Lut {
+        uint8_t t[256];
+        Lut() { memset(t, 255, sizeof t); t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3; }
+    } lut;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t c = lut.t[(unsigned char)ascii[i]];
+        if (c == 255) return i;
+        codes[i] = c;
+    }
+    return -1;
+}
+
+int advhmm_context_create(int device, void* stream, advhmm_context** out)
+{
+    if (!out) return set_error(ADVHMM_EINVAL, "out is null");
+    *out = nullptr;
+    std::unique_ptr<advhmm_context> ctx(new (std::nothrow) advhmm_context);
+    if (!ctx) return set_error(ADVHMM_ENOMEM, "out of host memory");
+    ctx->device = device;
+    if (device >= 0) {
+        int count = 0;
+        CU_TRY(cudaGetDeviceCount(&count));
+        if (device >= count) return set_error(ADVHMM_EINVAL, "device %d does not exist (%d visible)", device, count);
+        CU_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) return set_error(ADVHMM_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->smem_optin = prop.sharedMemPerBlockOptin;
+        if (stream) { ctx->stream = static_cast<cudaStream_t>(stream); }
+        else { CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->owns_stream = true; }
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+        ctx->workspace_budget = std::min<size_t>((size_t)6 << 30, free_b / 4);
+        const char* env = getenv("ADVHMM_WORKSPACE_MB");
+        if (env && atoll(env) > 0) ctx->workspace_budget = (size_t)atoll(env) << 20;
+    }
+    *out = ctx.release();
+    return ADVHMM_OK;
+}
+
+void advhmm_context_destroy(advhmm_context* ctx)
+{
+    if (!ctx) return;
+    if (ctx->device >= 0) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        for (DevBuf* b : {&ctx->d_seqs, &ctx->d_seq_off, &ctx->d_pk, &ctx->d_meta, &ctx->d_work, &ctx->d_out, &ctx->d_paths, &ctx->d_flags}) b->release();
+        ctx->h_meta.release(); ctx->h_out.release();
+        if (ctx->meta_done) cudaEventDestroy(ctx->meta_done);
+        if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+int advhmm_context_synchronize(advhmm_context* ctx)
+{
+    if (!ctx || ctx->device < 0) return ADVHMM_OK;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return ADVHMM_OK;
+}
+
+void* advhmm_context_stream(advhmm_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t advhmm_context_launch_count(advhmm_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int advhmm_model_create(advhmm_context* ctx, const advhmm_model_desc* desc, advhmm_model** out)
+{
+    if (!ctx || !desc || !out) return set_error(ADVHMM_EINVAL, "null argument");
+    *out = nullptr;
+    std::unique_ptr<advhmm_model> mod(new (std::nothrow) advhmm_model);
+    if (!mod) return set_error(ADVHMM_ENOMEM, "out of host memory");
+    mod->ctx = ctx;
+    std::string err;
+    if (!compile_model(*desc, mod->cm, err)) return set_error(ADVHMM_EINVAL, "%s", err.c_str());
+    if (mod->cm.g.max_in_degree > 65535) return set_error(ADVHMM_EUNSUPPORTED, "in-degree %d exceeds the 16-bit traceback slot", mod->cm.g.max_in_degree);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    int rc = upload_model(mod.get());
+    if (rc) return rc;
+    *out = mod.release();
+    return ADVHMM_OK;
+}
+
+void advhmm_model_destroy(advhmm_model* model)
+{
+    if (!model) return;
+    if (model->ctx && model->ctx->device >= 0) {
+        cudaSetDevice(model->ctx->device);
+        cudaStreamSynchronize(model->ctx->stream);
+        model->blob.release();
+    }
+    delete model;
+}
+
+int advhmm_model_info_get(const advhmm_model* model, advhmm_model_info* out)
+{
+    if (!model || !out) return set_error(ADVHMM_EINVAL, "null argument");
+    *out = model->info;
+    return ADVHMM_OK;
+}
+
+int advhmm_viterbi_batch(advhmm_model* model, const uint8_t* seqs, const int64_t* seq_off, int32_t n_reads,
+                         uint32_t flags, double* logp, int32_t* path_len, int64_t* path_off,
+                         int32_t* path, int64_t path_cap, int64_t* path_total)
+{
+    if (!model) return set_error(ADVHMM_EINVAL, "model is null");
+    const int64_t group_off[2] = {0, n_reads};
+    advhmm_model* models[1] = {model};
+    return run_host(model->ctx, models, 1, group_off, seqs, seq_off, n_reads, flags & ~ADVHMM_DEVICE_BUFFERS, false,
+                    logp, path_len, path_off, path, path_cap, path_total);
+}
+
+int advhmm_log_probability_batch(advhmm_model* model, const uint8_t* seqs, const int64_t* seq_off,
+                                 int32_t n_reads, uint32_t flags, double* logp)
+{
+    if (!model) return set_error(ADVHMM_EINVAL, "model is null");
+    const int64_t group_off[2] = {0, n_reads};
+    advhmm_model* models[1] = {model};
+    return run_host(model->ctx, models, 1, group_off, seqs, seq_off, n_reads,
+                    flags & ~(ADVHMM_DEVICE_BUFFERS | ADVHMM_WANT_PATH | ADVHMM_BOTH_STRANDS), true,
+                    logp, nullptr, nullptr, nullptr, 0, nullptr);
+}
+
+int advhmm_viterbi_multi(advhmm_context* ctx, advhmm_model* const* models, int32_t n_models,
+                         const int64_t* group_off, const uint8_t* seqs, const int64_t* seq_off,
+                         int32_t n_reads, uint32_t flags, double* logp, int32_t* path_len,
+                         int64_t* path_off, int32_t* path, int64_t path_cap, int64_t* path_total)
+{
+    if (!ctx || !models || !group_off || n_models <= 0) return set_error(ADVHMM_EINVAL, "null argument");
+    if (!(flags & ADVHMM_DEVICE_BUFFERS))
+        return run_host(ctx, models, n_models, group_off, seqs, seq_off, n_reads, flags, false,
+                        logp, path_len, path_off, path, path_cap, path_total);
+    // device-resident buffers: asynchronous on the context's stream, nothing is copied back
+    if (ctx->device < 0) return set_error(ADVHMM_ECUDA, "this context has no CUDA device");
+    const bool want_path = flags & ADVHMM_WANT_PATH;
+    if (!seq_off || !logp || (want_path && (!path_len || !path_off || !path_total)))
+        return set_error(ADVHMM_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(ctx->d_flags.ensure(256));
+    int32_t* d_bad = ctx->d_flags.as<int32_t>();
+    CU_TRY(cudaMemsetAsync(d_bad, 0x7f, sizeof(int32_t), ctx->stream));
+    OutPtrs op{logp, path_len, path_off, path, want_path ? path_cap : 0,
+               reinterpret_cast<unsigned long long*>(path_total)};
+    return run_batch(ctx, models, n_models, group_off, seqs, seq_off, n_reads, flags & ~ADVHMM_DEVICE_BUFFERS, op,
+                     false, d_bad);
+}
+
+}  // extern "C"

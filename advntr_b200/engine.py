@@ -1,0 +1,268 @@
+"""ctypes binding of the C-ABI (``include/advhmm.h``) -- the only way this package decodes.
+
+There is no CPU fallback: if ``libadvhmm.so`` is missing or no sm_100 GPU is visible, the
+decoding calls raise.  Build the library with ``python -m advntr_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libadvhmm.so")
+
+OK, EINVAL, ECUDA, ENOMEM, ESYMBOL, ECAPACITY, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+WANT_PATH, BOTH_STRANDS, FP32, FORCE_GENERIC, DEVICE_BUFFERS = 0x1, 0x2, 0x4, 0x8, 0x100
+KIND_GENERIC, KIND_BANDED = 0, 1
+
+EXPORTS = (
+    "advhmm_context_create", "advhmm_context_destroy", "advhmm_context_synchronize",
+    "advhmm_context_stream", "advhmm_context_launch_count",
+    "advhmm_model_create", "advhmm_model_destroy", "advhmm_model_info_get",
+    "advhmm_viterbi_batch", "advhmm_log_probability_batch", "advhmm_viterbi_multi",
+    "advhmm_last_error", "advhmm_abi_version", "advhmm_encode_acgt",
+)
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "advhmm error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("n_states", C.c_int32), ("silent_start", C.c_int32), ("start_index", C.c_int32),
+                ("end_index", C.c_int32), ("finite", C.c_int32), ("n_symbols", C.c_int32),
+                ("in_off", C.c_void_p), ("in_src", C.c_void_p), ("in_logp", C.c_void_p),
+                ("emis", C.c_void_p)]
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_states", C.c_int32), ("n_edges", C.c_int32),
+                ("n_columns", C.c_int32), ("n_final_states", C.c_int32), ("smem_bytes", C.c_int32),
+                ("max_in_degree", C.c_int32), ("reserved", C.c_int32)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """Load ``libadvhmm.so`` (no compute is started).  Raises ImportError when it is not built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("advntr_b200: %s is not built -- run `python -m advntr_b200.build` "
+                              "(there is no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+        lib.advhmm_context_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+        lib.advhmm_context_destroy.argtypes = [vp]
+        lib.advhmm_context_destroy.restype = None
+        lib.advhmm_context_synchronize.argtypes = [vp]
+        lib.advhmm_context_stream.argtypes = [vp]
+        lib.advhmm_context_stream.restype = vp
+        lib.advhmm_context_launch_count.argtypes = [vp]
+        lib.advhmm_context_launch_count.restype = i64
+        lib.advhmm_model_create.argtypes = [vp, C.POINTER(ModelDesc), C.POINTER(vp)]
+        lib.advhmm_model_destroy.argtypes = [vp]
+        lib.advhmm_model_destroy.restype = None
+        lib.advhmm_model_info_get.argtypes = [vp, C.POINTER(ModelInfo)]
+        lib.advhmm_viterbi_batch.argtypes = [vp, vp, vp, i32, u32, vp, vp, vp, vp, i64, vp]
+        lib.advhmm_log_probability_batch.argtypes = [vp, vp, vp, i32, u32, vp]
+        lib.advhmm_viterbi_multi.argtypes = [vp, vp, i32, vp, vp, vp, i32, u32, vp, vp, vp, vp, i64, vp]
+        lib.advhmm_last_error.restype = C.c_char_p
+        lib.advhmm_abi_version.restype = C.c_int
+        lib.advhmm_encode_acgt.argtypes = [C.c_char_p, i64, vp]
+        lib.advhmm_encode_acgt.restype = i64
+        _lib = lib
+        return lib
+
+
+def _check(rc):
+    if rc != OK:
+        raise EngineError(rc, load_library().advhmm_last_error().decode("utf-8", "replace"))
+
+
+def encode_acgt(seq):
+    """ASCII DNA -> uint8 codes (A,C,G,T = 0..3).  Returns (codes, index of first bad byte or -1)."""
+    raw = seq.encode("ascii", "replace") if isinstance(seq, str) else bytes(seq)
+    out = np.empty(len(raw), dtype=np.uint8)
+    bad = load_library().advhmm_encode_acgt(raw, len(raw), out.ctypes.data)
+    return out, int(bad)
+
+
+def pack_reads(codes):
+    """list of uint8 arrays -> (flat uint8, int64 offsets[R+1])."""
+    R = len(codes)
+    off = np.zeros(R + 1, dtype=np.int64)
+    if R:
+        np.cumsum(np.fromiter((len(c) for c in codes), dtype=np.int64, count=R), out=off[1:])
+    flat = np.empty(max(int(off[-1]), 1), dtype=np.uint8)
+    for c, a, b in zip(codes, off[:-1], off[1:]):
+        flat[a:b] = c
+    return flat, off
+
+
+class Context(object):
+    """One engine context (device + stream + workspaces).  ``device=-1``: host-only analysis."""
+
+    _default = {}
+
+    def __init__(self, device=0, stream=None):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib.advhmm_context_create(int(device), C.c_void_p(stream or 0), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    @classmethod
+    def default(cls, device=None):
+        if device is None:
+            device = int(os.environ.get("ADVHMM_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        ctx = cls._default.get(device)
+        if ctx is None:
+            ctx = cls._default[device] = cls(device)
+        return ctx
+
+    @property
+    def stream(self):
+        return self._lib.advhmm_context_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.advhmm_context_launch_count(self._h))
+
+    def synchronize(self):
+        _check(self._lib.advhmm_context_synchronize(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.advhmm_context_destroy(self._h)
+            self._h = None
+
+    # -- many loci in one call -----------------------------------------------------------
+    def viterbi_multi(self, models, groups, both_strands=False, want_path=True,
+                      force_generic=False, path_cap=None):
+        """``groups[g]`` = list of uint8 code arrays decoded against ``models[g]``."""
+        flat_codes = [c for grp in groups for c in grp]
+        goff = np.zeros(len(groups) + 1, dtype=np.int64)
+        np.cumsum([len(g) for g in groups], out=goff[1:])
+        seqs, off = pack_reads(flat_codes)
+        return self._run(models, goff, seqs, off, both_strands, want_path, force_generic, path_cap)
+
+    def _run(self, models, goff, seqs, off, both_strands, want_path, force_generic, path_cap):
+        R = len(off) - 1
+        strands = 2 if both_strands else 1
+        n_out = R * strands
+        flags = (WANT_PATH if want_path else 0) | (BOTH_STRANDS if both_strands else 0) | \
+                (FORCE_GENERIC if force_generic else 0)
+        handles = (C.c_void_p * len(models))(*[m._h for m in models])
+        logp = np.empty(n_out, dtype=np.float64)
+        plen = np.full(n_out, -1, dtype=np.int32)
+        poff = np.zeros(n_out, dtype=np.int64)
+        total = C.c_int64(0)
+        if want_path and path_cap is None:
+            lens = np.repeat(off[1:] - off[:-1], strands)
+            extra = max(m.path_extra for m in models) if models else 0
+            path_cap = int(lens.sum() + n_out * extra) + 16
+        cap = int(path_cap or 0)
+        while True:
+            path = np.empty(max(cap, 1), dtype=np.int32)
+            rc = self._lib.advhmm_viterbi_multi(
+                self._h, handles, len(models), goff.ctypes.data, seqs.ctypes.data, off.ctypes.data, R,
+                flags, logp.ctypes.data, plen.ctypes.data, poff.ctypes.data, path.ctypes.data, cap,
+                C.byref(total))
+            if rc == ECAPACITY and total.value > cap:
+                cap = int(total.value) + 16
+                continue
+            _check(rc)
+            break
+        return ViterbiResult(logp, plen, poff, path[:max(int(total.value), 0)])
+
+
+class ViterbiResult(object):
+    """Arrays returned by one batched decode; ``path(i)`` is read i's state-index path."""
+
+    __slots__ = ("logp", "path_len", "path_off", "paths")
+
+    def __init__(self, logp, path_len, path_off, paths):
+        self.logp, self.path_len, self.path_off, self.paths = logp, path_len, path_off, paths
+
+    def __len__(self):
+        return len(self.logp)
+
+    def path(self, i):
+        n = int(self.path_len[i])
+        if n < 0:
+            return None
+        o = int(self.path_off[i])
+        return self.paths[o:o + n]
+
+
+class DeviceModel(object):
+    """A baked model uploaded to one context (``advhmm_model``)."""
+
+    def __init__(self, ctx, baked):
+        self._lib = load_library()
+        self.ctx = ctx
+        # keep the arrays alive for the duration of the create call
+        in_off = np.ascontiguousarray(baked["in_off"], dtype=np.int32)
+        in_src = np.ascontiguousarray(baked["in_src"], dtype=np.int32)
+        in_logp = np.ascontiguousarray(baked["in_logp"], dtype=np.float64)
+        emis = np.ascontiguousarray(baked["emis"], dtype=np.float64)
+        S = int(baked["silent_start"])
+        K = int(emis.shape[1]) if emis.ndim == 2 and S else 4
+        desc = ModelDesc(int(baked["n_states"]), S, int(baked["start_index"]), int(baked["end_index"]),
+                         int(baked["finite"]), K, in_off.ctypes.data, in_src.ctypes.data,
+                         in_logp.ctypes.data, emis.ctypes.data)
+        h = C.c_void_p()
+        _check(self._lib.advhmm_model_create(ctx._h, C.byref(desc), C.byref(h)))
+        self._h = h
+        info = ModelInfo()
+        _check(self._lib.advhmm_model_info_get(h, C.byref(info)))
+        self.info = info
+        self.n_states = int(baked["n_states"])
+        self.n_symbols = K
+        # upper bound on (path length - read length): every silent state once, plus ends
+        self.path_extra = self.n_states - S + 2
+
+    @classmethod
+    def from_baked(cls, baked, ctx=None):
+        return cls(ctx or Context.default(), baked)
+
+    @property
+    def kind(self):
+        return "banded" if self.info.kind == KIND_BANDED else "generic"
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self._lib.advhmm_model_destroy(self._h)
+        self._h = None
+
+    def viterbi(self, codes, both_strands=False, want_path=True, precision="fp64",
+                force_generic=False, path_cap=None):
+        if precision != "fp64":
+            raise EngineError(EUNSUPPORTED, "only fp64 is available in this build")
+        seqs, off = pack_reads(codes)
+        goff = np.array([0, len(codes)], dtype=np.int64)
+        return self.ctx._run([self], goff, seqs, off, both_strands, want_path, force_generic, path_cap)
+
+    def log_probability(self, codes):
+        seqs, off = pack_reads(codes)
+        R = len(codes)
+        logp = np.empty(R, dtype=np.float64)
+        _check(self._lib.advhmm_log_probability_batch(self._h, seqs.ctypes.data, off.ctypes.data, R, 0,
+                                                      logp.ctypes.data))
+        return logp
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

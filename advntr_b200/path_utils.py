@@ -1,0 +1,164 @@
+"""Consumers of a Viterbi state path (the contract downstream of the hot path).
+
+Restates ``/root/reference/advntr/hmm_utils.py:70-91, 122-286`` and the recruitment /
+spanning predicates of ``vntr_finder.py:179-190, 311-322``.  They read nothing but the state
+NAMES on the path (``vpath[1:-1]``: the model's own start/end are dropped), which is why the
+engine returns the reference's exact state indices.  Implemented as one pass over the path
+that fills a ``PathSummary``; the reference-named helpers are thin views of it.
+"""
+from __future__ import annotations
+
+MIN_BP_IN_REPEAT = 3     # hmm_utils.py:165
+
+
+def is_match_state(name):
+    return name.startswith("M")
+
+
+def is_emitting_state(name):
+    return name.startswith(("M", "I", "start_random_matches", "end_random_matches"))
+
+
+def _names(vpath):
+    return [state.name for _, state in vpath[1:-1]]
+
+
+class PathSummary(object):
+    """Everything adVNTR derives from one path, computed in a single walk."""
+
+    __slots__ = ("n_emitted", "n_match", "repeat_bp", "left_bp", "right_bp", "unit_starts",
+                 "unit_ends", "repeats", "unit_lengths")
+
+    def __init__(self, names):
+        emitted = [is_emitting_state(n) for n in names]
+        total = sum(emitted)
+        self.n_emitted = total
+        self.n_match = sum(1 for n in names if is_match_state(n))
+        self.repeat_bp = self.left_bp = self.right_bp = 0
+        starts = ends = 0
+        first_start = last_start = first_end = last_end = None
+        lengths, open_at = [], None
+        bp = 0
+        for n, emits in zip(names, emitted):
+            if emits:
+                bp += 1
+                if n.endswith("suffix"):
+                    self.left_bp += 1
+                elif n.endswith("prefix"):
+                    self.right_bp += 1
+                if not n.endswith("fix"):
+                    self.repeat_bp += 1
+            if n.startswith("unit_start"):
+                if total - bp >= MIN_BP_IN_REPEAT:
+                    if first_start is None:
+                        first_start = bp
+                    last_start = bp
+                    starts += 1
+            if n.startswith("unit_end"):
+                if open_at is not None:
+                    lengths.append(bp - open_at)
+                if bp >= MIN_BP_IN_REPEAT:
+                    if first_end is None:
+                        first_end = bp
+                    last_end = bp
+                    ends += 1
+            if n.startswith("unit_start"):
+                open_at = bp
+        bonus = 0
+        if None not in (first_start, last_start, first_end, last_end):
+            if first_end < first_start and last_start > last_end:
+                bonus = 1       # partial unit at both ends of the read (hmm_utils.py:184-187)
+        self.unit_starts, self.unit_ends = starts, ends
+        self.repeats = max(starts, ends) + bonus
+        self.unit_lengths = lengths
+
+
+def summarize(vpath):
+    return PathSummary(_names(vpath))
+
+
+def get_number_of_repeats_in_vpath(vpath):
+    return summarize(vpath).repeats
+
+
+def get_number_of_matches_in_vpath(vpath):
+    return summarize(vpath).n_match
+
+
+def get_number_of_repeat_bp_matches_in_vpath(vpath):
+    return summarize(vpath).repeat_bp
+
+
+def get_left_flanking_region_size_in_vpath(vpath):
+    return summarize(vpath).left_bp
+
+
+def get_right_flanking_region_size_in_vpath(vpath):
+    return summarize(vpath).right_bp
+
+
+def get_repeating_pattern_lengths(visited_states):
+    return PathSummary(list(visited_states)).unit_lengths
+
+
+def get_flanking_regions_matching_rate(vpath, sequence, left_flank, right_flank, accuracy_filter=False):
+    """Fraction of flank match states whose read base equals the flank base; the smaller of the
+    two flanks' rates (``hmm_utils.py:209-268``)."""
+    names = _names(vpath)
+    deepest = -1                      # index of the last left-flank column the path used
+    prev = names[0]
+    for n in names:
+        if "suffix_end_suffix" in n:
+            deepest = int(prev.split("_")[0][1:])
+            break
+        prev = n
+    hits = {"prefix": 0, "suffix": 0}
+    bases = {"prefix": 0, "suffix": 0}
+    pos = 0
+    for n in names:
+        if "start" in n or "end" in n:
+            continue
+        col = int(n.split("_")[0][1:])
+        emits = is_emitting_state(n)
+        for side in ("prefix", "suffix"):
+            if n.endswith(side):
+                if is_match_state(n):
+                    want = right_flank[col - 1] if side == "prefix" else left_flank[-(deepest - col + 1)]
+                    if sequence[pos] == want:
+                        hits[side] += 1
+                if emits:
+                    bases[side] += 1
+        if emits:
+            pos += 1
+    empty = 0.00001 if accuracy_filter else 1
+    right = float(hits["prefix"]) / bases["prefix"] if bases["prefix"] else empty
+    left = float(hits["suffix"]) / bases["suffix"] if bases["suffix"] else empty
+    return min(right, left)
+
+
+def extract_repeating_segments_from_read(sequence, visited_states):
+    """Read substrings (and their state runs) between unit_start and unit_end
+    (``hmm_utils.py:70-91``)."""
+    repeats, runs = [], []
+    open_pos = open_idx = None
+    pos = 0
+    for i, n in enumerate(visited_states):
+        if n.startswith("unit_end") and open_pos is not None:
+            repeats.append(sequence[open_pos:pos])
+            runs.append(list(visited_states[open_idx + 1:i]))
+        if n.startswith("unit_start"):
+            open_pos, open_idx = pos, i
+        if is_emitting_state(n):
+            pos += 1
+    return repeats, runs
+
+
+def recruit_read(logp, vpath, min_score_to_count_read, read_sequence, left_flank, right_flank):
+    """``vntr_finder.py:179-190``: does this read belong to the locus?"""
+    if min_score_to_count_read is not None and logp > min_score_to_count_read:
+        return get_flanking_regions_matching_rate(vpath, read_sequence, left_flank, right_flank) >= 0.9
+    length = len(read_sequence)
+    if min_score_to_count_read is None and \
+            get_number_of_matches_in_vpath(vpath) >= 0.9 * length and logp > -length:
+        return get_flanking_regions_matching_rate(vpath, read_sequence, left_flank, right_flank) >= 0.9
+    return False

@@ -1,0 +1,129 @@
+"""Synthetic loci and reads of the shapes BASELINE.json names.
+
+There is no network and no real data set; every benchmark and parity test runs on these
+generators.  Everything is driven by ``random.Random(seed)`` so the same inputs are
+produced in this container and on the GPU box.
+"""
+from __future__ import annotations
+
+import random
+
+from . import read_matcher
+
+_COMP = {"A": "T", "C": "G", "G": "C", "T": "A"}
+
+
+def rand_dna(rng, n):
+    return "".join(rng.choice("ACGT") for _ in range(n))
+
+
+def revcomp(s):
+    return "".join(_COMP[c] for c in reversed(s))
+
+
+def substitute(rng, s, rate):
+    return "".join(rng.choice("ACGT") if rng.random() < rate else c for c in s)
+
+
+def sequencing_errors(rng, s, sub, ins, dele):
+    out = []
+    for c in s:
+        x = rng.random()
+        if x < dele:
+            continue
+        if x < dele + ins:
+            out.append(c)
+            out.append(rng.choice("ACGT"))
+        elif x < dele + ins + sub:
+            out.append(rng.choice("ACGT"))
+        else:
+            out.append(c)
+    return "".join(out)
+
+
+class Locus(object):
+    """A synthetic VNTR locus: flanks, repeat segments of the reference allele, read model."""
+
+    def __init__(self, locus_id, left, right, segments, read_length=150, flank=150, error_rate=0.05):
+        self.id = locus_id
+        self.left, self.right, self.segments = left, right, list(segments)
+        self.pattern = segments[0]
+        self.read_length = read_length
+        self.flank = flank
+        self.error_rate = error_rate
+        self.copies = read_matcher.copies_for_read_length(read_length, len(self.pattern))
+
+    @property
+    def sequence(self):
+        return self.left + "".join(self.segments) + self.right
+
+    def build_model(self):
+        """vntr_finder.py:117-138 -> get_read_matcher_model on the trimmed flanks."""
+        return read_matcher.build_vntr_matcher_hmm(self.left, self.right, self.segments, self.copies,
+                                                   flank_size=self.flank, error_rate=self.error_rate)
+
+    def reads(self, rng, n, sub=0.01, ins=0.001, dele=0.001, length=None):
+        """Uniform windows of the locus with Illumina-like errors, trimmed to the read length."""
+        length = length or self.read_length
+        seq = self.sequence
+        out = []
+        for _ in range(n):
+            s = rng.randrange(0, max(1, len(seq) - length))
+            out.append(sequencing_errors(rng, seq[s:s + length + 8], sub, ins, dele)[:length])
+        return out
+
+
+def config1_locus():
+    """BASELINE config 1: 30 bp RU x 10 identical copies, 100 bp flanks."""
+    rng = random.Random(1)
+    ru = rand_dna(rng, 30)
+    left = rand_dna(rng, 100)
+    right = rand_dna(rng, 100)
+    return Locus(1, left, right, [ru] * 10, read_length=150, flank=150)
+
+
+def config1_reads(n=1000, seed=11):
+    loc = config1_locus()
+    return loc.reads(random.Random(seed), n)
+
+
+def config2_locus(locus_id, read_length=150):
+    """BASELINE config 2: loci shaped like the recommended hg19 Illumina set (section 8d):
+    RU length 6..70, total VNTR length < 140 bp, 2 % divergence between copies, 500 bp flanks
+    of which the 150 nearest bases enter the model."""
+    rng = random.Random(1000003 * locus_id + 17)
+    R = rng.randint(6, 70)
+    ncopies = max(2, 139 // R)
+    ru = rand_dna(rng, R)
+    segments = [substitute(rng, ru, 0.02) for _ in range(ncopies)]
+    left = rand_dna(rng, 500)
+    right = rand_dna(rng, 500)
+    return Locus(locus_id, left, right, segments, read_length=read_length, flank=150)
+
+
+def config2_reads(locus, coverage=30, decoys=50, seed=None):
+    """Mapped reads overlapping the VNTR at `coverage`x (decoded on one strand) and decoy
+    unmapped reads (decoded on both strands, vntr_finder.py:235-254)."""
+    rng = random.Random(7919 * locus.id + 3 if seed is None else seed)
+    vntr_len = sum(len(s) for s in locus.segments)
+    L = locus.read_length
+    n_mapped = max(1, int(round((vntr_len + L) * coverage / float(L))))
+    lo = max(0, len(locus.left) - L + 1)
+    hi = len(locus.left) + vntr_len - 1
+    seq = locus.sequence
+    mapped = []
+    for _ in range(n_mapped):
+        s = rng.randint(lo, max(lo, min(hi, len(seq) - L)))
+        mapped.append(sequencing_errors(rng, seq[s:s + L + 8], 0.01, 0.001, 0.001)[:L])
+    unmapped = [rand_dna(rng, L) for _ in range(decoys)]
+    return mapped, unmapped
+
+
+def config3_locus(copies=100, R=60, flank=100):
+    """BASELINE config 3: long-RU VNTR for PacBio-like reads (error rate 0.3)."""
+    rng = random.Random(3)
+    ru = rand_dna(rng, R)
+    loc = Locus(3, rand_dna(rng, flank), rand_dna(rng, flank), [ru] * copies, read_length=R * copies + 2 * flank,
+                flank=flank, error_rate=0.3)
+    loc.copies = copies
+    return loc

@@ -129,14 +129,17 @@ int advhmm_log_probability_batch(advhmm_model* model,
 
 /* ---- decoding, many loci in one launch ---------------------------------------------------
  * The batched form of the per-locus loop (genome_analyzer.py:280 x vntr_finder.py:727-767):
- * read r is decoded against models[read_model[r]].  All models must belong to one context.
- * Buffers are HOST buffers unless ADVHMM_DEVICE_BUFFERS is set, in which case every pointer
- * except `models` is a device pointer, nothing is copied, the call is asynchronous on the
- * context's stream and *path_total is a device int64 (ECAPACITY is reported by path_len=-2). */
+ * reads group_off[g] .. group_off[g+1]-1 are decoded against models[g] (the caller loops over
+ * loci anyway, so reads arrive grouped).  All models must belong to `ctx`.
+ * group_off[n_models+1] and seq_off[n_reads+1] are always HOST arrays (planning metadata).
+ * With ADVHMM_DEVICE_BUFFERS every other buffer (seqs, logp, path_len, path_off, path,
+ * path_total) is a DEVICE pointer on ctx's device: nothing is copied, the call only queues
+ * work on the context's stream and returns; *path_total is a device int64; reads whose path
+ * did not fit in path_cap get path_len = -2. */
 #define ADVHMM_DEVICE_BUFFERS 0x100u
 int advhmm_viterbi_multi(advhmm_context* ctx,
                          advhmm_model* const* models, int32_t n_models,
-                         const int32_t* read_model,
+                         const int64_t* group_off,
                          const uint8_t* seqs, const int64_t* seq_off, int32_t n_reads,
                          uint32_t flags,
                          double* logp, int32_t* path_len, int64_t* path_off,

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ FROM THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference and oracle/_ref):
+
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+
+For every case the model is built by the reference's own ``advntr/hmm_utils.py``
+(``get_read_matcher_model``) on the compiled, unmodified vendored pomegranate, and decoded
+by that engine's ``viterbi`` / ``log_probability``.  Stored per case (``<case>.npz``):
+
+  baked arrays   in_off, in_src, in_logp, emis, names, scalars   (what bake() produced)
+  inputs         left, right, segments, copies, error_rate, reads
+  outputs        logp[R] (bit patterns), paths (concatenated state indices) + path_off,
+                 forward[R], ru_count[R] (hmm_utils.get_number_of_repeats_in_vpath)
+
+plus ``fingerprint.npz`` (numpy.exp / libm log of a fixed vector: the builder round-trips
+through both, so bit-exact builder parity is only expected where they reproduce).
+"""
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
+
+import refenv   # noqa: E402
+import oracle   # noqa: E402
+from advntr_b200 import synth   # noqa: E402  (input generators only)
+
+
+def case_inputs(name):
+    if name == "config1":
+        loc = synth.config1_locus()
+        rng = random.Random(11)
+        reads = [loc.left[-30:] + loc.pattern * 3 + loc.right[:30], "", "A", synth.rand_dna(rng, 150),
+                 loc.pattern * 5, loc.left[-100:] + loc.pattern[:20], loc.pattern[10:] + loc.right[:120],
+                 "ACGT" * 37, "A" * 150, loc.left[-100:] + loc.right[:50], synth.rand_dna(rng, 7)]
+        reads += loc.reads(rng, 85)
+        reads += [synth.revcomp(r) for r in reads[11:27]]
+        reads += [loc.reads(rng, 1, length=L)[0] for L in (1, 2, 31, 32, 33, 64, 100, 149, 151, 160, 200, 250)]
+        return loc.left[-150:], loc.right[:150], loc.segments, loc.copies, 0.05, reads
+    rng = random.Random({"small_a": 2, "small_b": 3, "divergent": 4}[name])
+    if name == "small_a":
+        R, nseg, Ll, Lr, copies, eps = 12, 5, 60, 70, 4, 0.05
+    elif name == "small_b":
+        R, nseg, Ll, Lr, copies, eps = 7, 8, 40, 33, 9, 0.3
+    else:
+        R, nseg, Ll, Lr, copies, eps = 23, 6, 150, 150, 7, 0.05
+    ru = synth.rand_dna(rng, R)
+    left, right = synth.rand_dna(rng, Ll), synth.rand_dna(rng, Lr)
+    segs = [synth.substitute(rng, ru, 0.1) for _ in range(nseg)]
+    locus = left + "".join(segs) + right
+    reads = ["", "C", synth.rand_dna(rng, 50)]
+    for _ in range(45):
+        L = rng.choice((20, 47, 80, 100, 150))
+        s = rng.randrange(0, max(1, len(locus) - L))
+        reads.append(synth.sequencing_errors(rng, locus[s:s + L + 8], 0.02, 0.01, 0.01)[:L])
+    return left, right, segs, copies, eps, reads
+
+
+def main():
+    pom = refenv.reference_pomegranate()
+    hu = refenv.reference_hmm_utils(pom, "ref")
+    settings = refenv.reference_settings()
+    for name in ("config1", "small_a", "small_b", "divergent"):
+        left, right, segs, copies, eps, reads = case_inputs(name)
+        settings.MAX_ERROR_RATE = eps
+        model = hu.get_read_matcher_model(left, right, segs, copies=copies)
+        settings.MAX_ERROR_RATE = 0.05
+        b = oracle.baked_from_reference_model(model)
+        logp, fwd, ru, paths, off, consumers = [], [], [], [], [0], []
+        for r in reads:
+            lp, vp = model.viterbi(r)
+            logp.append(lp)
+            fwd.append(model.log_probability(r))
+            if vp is None:
+                ru.append(-1)
+                consumers.append([0, 0, 0, 0, 0.0])
+            else:
+                paths.extend(i for i, _ in vp)
+                ru.append(hu.get_number_of_repeats_in_vpath(vp))
+                # the other path consumers of hmm_utils.py:191-286 (rate needs a non-empty read)
+                consumers.append([hu.get_number_of_matches_in_vpath(vp),
+                                  hu.get_number_of_repeat_bp_matches_in_vpath(vp),
+                                  hu.get_left_flanking_region_size_in_vpath(vp),
+                                  hu.get_right_flanking_region_size_in_vpath(vp),
+                                  hu.get_flanking_regions_matching_rate(vp, r, left, right) if r else -1.0])
+            off.append(len(paths))
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            in_off=b["in_off"], in_src=b["in_src"], in_logp=b["in_logp"], emis=b["emis"],
+            scalars=np.array([b["n_states"], b["silent_start"], b["start_index"], b["end_index"], b["finite"]]),
+            names=np.array("\n".join(b["names"])),
+            inputs=np.array(json.dumps({"left": left, "right": right, "segments": segs, "copies": copies,
+                                        "error_rate": eps, "reads": reads})),
+            logp=np.array(logp, dtype=np.float64), forward=np.array(fwd, dtype=np.float64),
+            ru_count=np.array(ru, dtype=np.int32), consumers=np.array(consumers, dtype=np.float64),
+            paths=np.array(paths, dtype=np.int32),
+            path_off=np.array(off, dtype=np.int64))
+        print(name, "states", b["n_states"], "edges", len(b["in_src"]), "reads", len(reads))
+    # the one fixture the reference's own tests hold for this path (tests/test_hmm_utils.py:15-17):
+    # a recorded Viterbi path (state names) + read + the repeat segments it must yield
+    with open(os.path.join(refenv.REF_ROOT, "tests", "data", "hmm_utils.json")) as fh:
+        fx = json.load(fh)
+    with open(os.path.join(HERE, "ref_tests_hmm_utils.json"), "w") as fh:
+        json.dump({"provenance": "reference tests/data/hmm_utils.json (test fixture, copied verbatim)",
+                   "visited_states": fx["visited_states"], "sequence": fx["sequence"],
+                   "correct_repeats": fx["correct_repeats"]}, fh)
+    x = np.linspace(-30.0, 0.0, 4097)
+    import math
+    np.savez_compressed(os.path.join(HERE, "fingerprint.npz"), x=x, exp=np.exp(x),
+                        log=np.array([math.log(v) for v in np.exp(x)]))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+"""GPU parity: the CUDA path, called through the C-ABI (ctypes), against the golden vectors
+made from the reference engine and against the oracle on fresh seeded inputs.
+Bit-exact bar: log-probabilities compared as 64-bit patterns, state paths as arrays."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import Golden, assert_paths_equal, same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from advntr_b200 import engine
+    c = engine.Context(device=0)
+    yield c
+    c.close()
+
+
+def _decode(ctx, baked, codes, **kw):
+    from advntr_b200 import engine
+    dm = engine.DeviceModel(ctx, baked)
+    try:
+        res = dm.viterbi(codes, **kw)
+        return dm.kind, res
+    finally:
+        dm.close()
+
+
+@pytest.mark.parametrize("force_generic", [False, True], ids=["banded", "generic"])
+def test_viterbi_matches_golden(ctx, golden, force_generic):
+    kind, res = _decode(ctx, golden.baked, golden.codes(), force_generic=force_generic)
+    assert kind == "banded"
+    assert same_bits(res.logp, golden.logp)
+    assert_paths_equal([res.path(i) for i in range(len(res))],
+                       [golden.path(i) for i in range(len(golden.reads))], golden.name)
+
+
+def test_both_strands(ctx, golden_config1):
+    g = golden_config1
+    from advntr_b200 import synth
+    reads = [r for r in g.reads if r][:40]
+    codes = [oracle.encode(r) for r in reads]
+    _, res = _decode(ctx, g.baked, codes, both_strands=True)
+    om = oracle.OracleModel(g.baked)
+    both = []
+    for r in reads:
+        both += [oracle.encode(r), oracle.encode(synth.revcomp(r))]
+    lp, paths = om.viterbi(both)
+    assert same_bits(res.logp, lp)
+    assert_paths_equal([res.path(i) for i in range(len(res))], paths)
+
+
+def test_score_only(ctx, golden_config1):
+    g = golden_config1
+    _, res = _decode(ctx, g.baked, g.codes(), want_path=False)
+    assert same_bits(res.logp, g.logp)
+
+
+def test_forward_log_probability(ctx, golden):
+    from advntr_b200 import engine
+    dm = engine.DeviceModel(ctx, golden.baked)
+    fwd = dm.log_probability(golden.codes())
+    dm.close()
+    # north-star tolerance for log-probabilities: 1e-9 relative (device exp/log vs glibc)
+    assert np.allclose(fwd, golden.forward, rtol=1e-9, atol=0)
+
+
+def test_fresh_reads_vs_oracle_and_chunking(ctx, golden_config1, monkeypatch):
+    """1,000 config-1 reads; a tiny workspace budget forces many chunks through the same buffers."""
+    from advntr_b200 import engine, synth
+    g = golden_config1
+    reads = synth.config1_reads(1000)
+    codes = [oracle.encode(r) for r in reads]
+    om = oracle.OracleModel(g.baked)
+    lp, paths = om.viterbi(codes)
+    monkeypatch.setenv("ADVHMM_WORKSPACE_MB", "8")
+    small = engine.Context(device=0)
+    try:
+        for force in (False, True):
+            _, res = _decode(small, g.baked, codes, force_generic=force)
+            assert same_bits(res.logp, lp)
+            assert_paths_equal([res.path(i) for i in range(len(res))], paths)
+    finally:
+        small.close()
+
+
+def test_many_loci_one_call(ctx):
+    """advhmm_viterbi_multi: reads of several loci (different models) in one launch."""
+    from advntr_b200 import engine
+    cases = [Golden(n) for n in ("small_a", "small_b", "divergent", "config1")]
+    models = [engine.DeviceModel(ctx, c.baked) for c in cases]
+    groups = [c.codes() for c in cases]
+    res = ctx.viterbi_multi(models, groups)
+    want_lp = np.concatenate([c.logp for c in cases])
+    want_paths = [c.path(i) for c in cases for i in range(len(c.reads))]
+    assert same_bits(res.logp, want_lp)
+    assert_paths_equal([res.path(i) for i in range(len(res))], want_paths)
+    for m in models:
+        m.close()
+
+
+def test_long_reads_take_the_generic_kernel(ctx, golden_config1):
+    """Reads longer than the banded kernel's 320 positions are routed to the generic kernel."""
+    g = golden_config1
+    from advntr_b200 import synth
+    loc = synth.config1_locus()
+    rng = random.Random(4)
+    reads = [loc.sequence[:400], loc.sequence[50:450], synth.rand_dna(rng, 333)] + g.reads[:5]
+    codes = [oracle.encode(r) for r in reads]
+    lp, paths = oracle.OracleModel(g.baked).viterbi(codes)
+    _, res = _decode(ctx, g.baked, codes)
+    assert same_bits(res.logp, lp)
+    assert_paths_equal([res.path(i) for i in range(len(res))], paths)
+
+
+def test_non_profile_model_on_device(ctx):
+    in_off = np.array([0, 2, 4, 4, 4], dtype=np.int32)
+    in_src = np.array([0, 2, 0, 1], dtype=np.int32)
+    in_logp = np.log(np.array([0.6, 1.0, 0.4, 1.0]))
+    emis = np.log(np.array([[0.7, 0.1, 0.1, 0.1], [0.1, 0.1, 0.1, 0.7]]))
+    baked = {"n_states": 4, "silent_start": 2, "start_index": 2, "end_index": 3, "finite": 0,
+             "in_off": in_off, "in_src": in_src, "in_logp": in_logp, "emis": emis}
+    codes = [np.array(x, dtype=np.uint8) for x in ([0, 0, 3, 3], [3], [0, 1, 2, 3, 0], [])]
+    lp, paths = oracle.OracleModel(baked).viterbi(codes)
+    kind, res = _decode(ctx, baked, codes)
+    assert kind == "generic"
+    assert same_bits(res.logp, lp)
+    assert_paths_equal([res.path(i) for i in range(len(res))], paths)
+
+
+def test_bad_symbol_is_rejected(ctx, golden_config1):
+    from advntr_b200 import engine
+    dm = engine.DeviceModel(ctx, golden_config1.baked)
+    with pytest.raises(engine.EngineError) as ei:
+        dm.viterbi([np.array([0, 1, 7, 2], dtype=np.uint8)])
+    assert ei.value.code == engine.ESYMBOL
+    dm.close()
+
+
+def test_drop_in_surface(ctx):
+    """model.viterbi(seq) -> (logp, [(idx, State)...]) through the pomegranate-compatible class,
+    with the reference's error behaviour (hmm.pyx:72-79, 1944-1945, 1967)."""
+    from advntr_b200 import pomegranate as pom, read_matcher, synth
+    from advntr_b200 import path_utils
+    g = Golden("config1")
+    loc = synth.config1_locus()
+    model = loc.build_model()
+    assert [s.name for s in model.states] == g.names
+    logp, vpath = model.viterbi(g.reads[0])
+    assert logp == g.logp[0]
+    assert [i for i, _ in vpath] == list(g.path(0))
+    assert all(s is model.states[i] for i, s in vpath)
+    assert path_utils.get_number_of_repeats_in_vpath(vpath) == g.ru_count[0]
+    assert model.viterbi("")[0] == g.logp[1]
+    assert abs(model.log_probability(g.reads[0]) - g.forward[0]) <= 1e-9 * abs(g.forward[0])
+    with pytest.raises(ValueError, match="Symbol 'N' is not defined in a distribution"):
+        model.viterbi("ACGTN")
+    with pytest.raises(ValueError, match="must bake model"):
+        pom.HiddenMarkovModel("x").viterbi("A")
+    res = model.viterbi_batch(g.reads[:30])
+    assert same_bits(res.logp, g.logp[:30])
