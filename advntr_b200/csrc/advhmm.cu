@@ -29,6 +29,8 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "model_compile.hpp"
@@ -115,7 +117,7 @@ struct DevBanded {
     int NC, P, S, m, NF, end_final, acc_col, n_acc;
     int start, end, image_bytes, pad0;
     double logp_empty;            // v0[end]: the answer for an empty read
-    const unsigned char* image;   // smem image: doubles w[9P] e[8P] v1[8P] accw[P], bytes cflag[P]
+    const unsigned char* image;   // smem image, see kImg* (208 bytes per column)
     const int32_t* st;            // [3*NC] slot -> state
     const int32_t* tb1;           // [4*S]
     const int32_t* acc_src_col;   // [n_acc]
@@ -132,8 +134,6 @@ struct Tile {
     int32_t cnt;         // reads in this tile (<= warps per block)
 };
 
-constexpr int kColFlagAccSrc = 1;
-constexpr int kColFlagAccDst = 2;
 constexpr int kMaxRPL = 10;             // read positions per lane: reads up to 320 bases on the banded path
 constexpr int kBandedWarps = 8;         // reads per CTA (banded)
 constexpr int kGenericWarpsMax = 8;
@@ -151,6 +151,10 @@ struct advhmm_context {
     DevBuf d_seqs, d_seq_off, d_pk, d_meta, d_work, d_out, d_paths, d_flags;
     PinnedBuf h_meta, h_out;
     cudaEvent_t meta_done = nullptr;
+    // optional per-kernel timing (bench.py roofline): event pairs around every fill launch
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];   // [0] banded fill, [1] backtrack
+    size_t prof_used[2] = {0, 0};
     int banded_smem_set[kMaxRPL + 1] = {0};   // dynamic-smem opt-in already applied per RPL
     int generic_smem_set = 0;
     std::mutex mu;
@@ -288,35 +292,174 @@ struct BandedArgs {
     const int64_t* pk_off;
     const int32_t* rlen;
     double* logp;               // [n_out]
-    void* tbw;                  // traceback words, per slot 32 * Pmax words
-    size_t tbw_stride;          // words per slot
-    uint16_t* acc_tb;           // collector choice per (slot, position)
+    uint32_t* tbw;              // traceback words, per slot 32 * Pmax * (RPL > 5 ? 2 : 1) words
+    size_t tbw_stride;          // 32-bit words per slot
+    uint16_t* acc_tb;           // collector choice (source column) per (slot, position)
     int acc_stride;             // entries per slot (32 * RPL)
     double* vfin;               // last-row values, per slot 3 * Pmax
     size_t vfin_stride;
     int32_t* ftb;               // final-state choices, per slot 32
 };
 
-template <int RPL> struct TbWord { using type = uint32_t; };
-template <> struct TbWord<6> { using type = unsigned long long; };
-template <> struct TbWord<7> { using type = unsigned long long; };
-template <> struct TbWord<8> { using type = unsigned long long; };
-template <> struct TbWord<9> { using type = unsigned long long; };
-template <> struct TbWord<10> { using type = unsigned long long; };
+// shared-memory image of a banded model (byte offsets from the start of dynamic smem), P = NCpad:
+//   [0, 80P)          w10[c][10] : wII wIM wID | wMI wMM wMD | wDI wDM wDD | accw      (doubles)
+//   [80P, 144P)       e2[sym][c][2] : emission log-prob of the I and M slot           (doubles)
+//   [144P, 208P)      v1[sym][c][2] : first-row values of the I and M slot            (doubles)
+// One 16-byte row per (sym, c) means a lane fetches both emissions with one LDS.128, and all ten
+// weights of a column with five LDS.128 off a single address register (80-byte stride: the
+// quarter-warp's eight 16-byte accesses fall into disjoint bank groups).
+constexpr int kImgW = 0, kImgE = 80, kImgV1 = 144, kImgBytesPerCol = 208;
 
-// first strict maximum of three candidates in order (hmm.pyx:2039: `if cand > best`)
-#define ADV_MAX3(a0, a1, a2, best, code)            \
-    do {                                            \
-        best = (a0); code = 0;                      \
-        if ((a1) > best) { best = (a1); code = 1; } \
-        if ((a2) > best) { best = (a2); code = 2; } \
-    } while (0)
+__device__ __forceinline__ double2 lds128(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// First strict maximum of three candidates in candidate order (hmm.pyx:2039 `if cand > best`).
+// Two traceback bits: bit0 = (a1 > a0), bit1 = (a2 > max(a0, a1));  source = bit1 ? 2 : bit0.
+template <int J, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (J < N) {
+        f(std::integral_constant<int, J>{});
+        static_for<J + 1, N>(f);
+    }
+}
+
+template <int SH>
+__device__ __forceinline__ double max3_first(double a0, double a1, double a2, uint32_t& bits)
+{
+    // written in PTX so that each compare costs one DSETP, one 64-bit select and one predicated OR
+    double m;
+    asm("{\n\t"
+        ".reg .pred p1, p2;\n\t"
+        ".reg .f64 t;\n\t"
+        "setp.gt.f64 p1, %3, %2;\n\t"
+        "selp.f64 t, %3, %2, p1;\n\t"
+        "@p1 or.b32 %1, %1, %5;\n\t"
+        "setp.gt.f64 p2, %4, t;\n\t"
+        "selp.f64 %0, %4, t, p2;\n\t"
+        "@p2 or.b32 %1, %1, %6;\n\t"
+        "}"
+        : "=d"(m), "+r"(bits)
+        : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
+    return m;
+}
+
+// ALIGNED: the read length is a multiple of RPL, so the last read position is the last row of a
+// lane and its values can be stored from fixed registers.
+template <int RPL, bool ALIGNED>
+__device__ __forceinline__ void banded_sweep(const int NC, const int P, const int nl, const int ln, const int jn,
+                                             const int lane, const uint32_t s_base, const uint32_t symbits,
+                                             const int acc_col, uint32_t* __restrict__ tbw,
+                                             uint16_t* __restrict__ acc_tb, double* __restrict__ vfin)
+{
+    constexpr int NW = RPL > 5 ? 2 : 1;
+    uint32_t eaddr[RPL];                           // smem address of e2[sym_j][0]
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+        eaddr[j] = s_base + (uint32_t)kImgE * P + ((symbits >> (2 * j)) & 3u) * (uint32_t)(16 * P);
+    const uint32_t v1_delta = (uint32_t)(kImgV1 - kImgE) * P;
+
+    double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
+    int accarg[RPL];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; accarg[j] = 0; }
+    double bI = kNegInf, bM = kNegInf, bD = kNegInf;   // row above my block, previous column
+    const bool store_last = ALIGNED && lane == ln;
+    // lane-skewed views: index them with the step t (column c = t - lane).  The empty asm keeps
+    // ptxas from re-deriving these addresses inside the loop.
+    uint32_t* tbw_t = tbw - (ptrdiff_t)lane * NW;
+    double* vfin_t = vfin - lane;
+    uint32_t w_t = s_base - (uint32_t)lane * 80u;       // + 80 t  -> w10[c]
+    uint32_t e_t[RPL];                                  // + 16 t  -> e2[sym_j][c]
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) { e_t[j] = eaddr[j] - (uint32_t)lane * 16u; asm volatile("" : "+r"(e_t[j])); }
+    asm volatile("" : "+l"(tbw_t), "+l"(vfin_t), "+r"(w_t));
+
+    const int steps = NC + nl - 1;
+#pragma unroll 1
+    for (int t = 0; t < steps; ++t) {
+        // the row above my block at column c was finished by lane-1 in the previous step
+        const double uI0 = shfl_up_f64(cI[RPL - 1], 1);
+        const double uM0 = shfl_up_f64(cM[RPL - 1], 1);
+        const double uD0 = shfl_up_f64(cD[RPL - 1], 1);
+        const int c = t - lane;
+        if (c < 0 || c >= NC || lane >= nl) continue;
+
+        const uint32_t wa = w_t + (uint32_t)t * 80u;
+        const double2 w01 = lds128(wa), w23 = lds128(wa + 16), w45 = lds128(wa + 32);
+        const double2 w67 = lds128(wa + 48), w89 = lds128(wa + 64);
+        const double wII = w01.x, wIM = w01.y, wID = w23.x, wMI = w23.y, wMM = w45.x, wMD = w45.y;
+        const double wDI = w67.x, wDM = w67.y, wDD = w89.x, aw = w89.y;
+        const uint32_t cb = (uint32_t)t * 16u;
+
+        // M and D slots depend only on values of the previous column / previous step
+        double nM[RPL], nD[RPL], eIr[RPL];
+        uint32_t word[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) word[k] = 0;
+        static_for<0, RPL>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            const double2 e = lds128(e_t[j] + cb);             // {eI, eM}
+            eIr[j] = e.x;
+            const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
+            nM[j] = max3_first<6 * (j % 5) + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
+            nD[j] = max3_first<6 * (j % 5) + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
+        });
+        if (lane == 0) {                                       // first read position: from row 0
+            const double2 f = lds128(e_t[0] + v1_delta + cb);
+            nM[0] = f.y;
+            eIr[0] = f.x;                                      // (carries vI of row 1, see below)
+        }
+        // collector (end_repeating_pattern_match): D of its column is the best unit_end so far.
+        // Both cases are rare per lane (1 and `copies` columns of NC), hence real branches.
+        if (c == acc_col) {
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
+        }
+        if (aw > kNegInf) {                                    // a unit_end column
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                const double cand = nD[j] + aw;
+                if (cand > acc[j]) { acc[j] = cand; accarg[j] = c; }
+            }
+        }
+        // I slots chain down the rows of this column
+        double uI = uI0, uM = uM0, uD = uD0;
+        static_for<0, RPL>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            double vI = max3_first<6 * (j % 5)>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
+            if (j == 0 && lane == 0) vI = eIr[0];
+            uI = vI; uM = nM[j]; uD = nD[j];
+            cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
+        });
+        bI = uI0; bM = uM0; bD = uD0;
+        if (NW == 1) tbw_t[t] = word[0];
+        else reinterpret_cast<uint2*>(tbw_t)[t] = make_uint2(word[0], word[NW - 1]);
+        if (ALIGNED) {
+            if (store_last) { vfin_t[t] = cI[RPL - 1]; vfin_t[P + t] = cM[RPL - 1]; vfin_t[2 * P + t] = cD[RPL - 1]; }
+        } else if (lane == ln) {
+            double fI = cI[0], fM = cM[0], fD = cD[0];
+#pragma unroll
+            for (int j = 1; j < RPL; ++j)
+                if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
+            vfin_t[t] = fI; vfin_t[P + t] = fM; vfin_t[2 * P + t] = fD;
+        }
+    }
+    // which unit_end fed the collector, per read position (read by the backtrack only)
+    if (lane < nl) {
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) acc_tb[j] = (uint16_t)accarg[j];
+    }
+}
 
 template <int RPL>
 __global__ void __launch_bounds__(kBandedWarps * 32)
 banded_fill_kernel(const BandedArgs a)
 {
-    using TBW = typename TbWord<RPL>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ double s_fval[kBandedWarps][32];
@@ -331,20 +474,13 @@ banded_fill_kernel(const BandedArgs a)
     if (threadIdx.x == 0) {
         const uint32_t bytes = (uint32_t)M->image_bytes;
         mbar_expect_tx(&s_bar, bytes);
-        for (uint32_t o = 0; o < bytes; o += 32768u) {
-            const uint32_t n = min(32768u, bytes - o);
-            tma_bulk_g2s(smem_raw + o, M->image + o, n, &s_bar);
-        }
+#pragma unroll 1
+        for (uint32_t o = 0; o < bytes; o += 65536u)
+            tma_bulk_g2s(smem_raw + o, M->image + o, min(65536u, bytes - o), &s_bar);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     mbar_wait(&s_bar, 0);
     if (warp >= tile.cnt) return;
-
-    const double* __restrict__ sw = reinterpret_cast<const double*>(smem_raw);   // [9P]
-    const double* __restrict__ se = sw + 9 * P;                                   // [8P] I: sym, M: 4+sym
-    const double* __restrict__ sv1 = se + 8 * P;                                  // [8P]
-    const double* __restrict__ saccw = sv1 + 8 * P;                               // [P]
-    const unsigned char* __restrict__ sflag = reinterpret_cast<const unsigned char*>(saccw + P);
 
     const int item = tile.first + warp;
     const int q = a.order[item];
@@ -354,8 +490,8 @@ banded_fill_kernel(const BandedArgs a)
         if (lane == 0) a.logp[q] = M->logp_empty;
         return;
     }
-    const int nl = (n + RPL - 1) / RPL;           // lanes in use
-    const int ln = (n - 1) / RPL, jn = (n - 1) % RPL;   // owner of the last row
+    const int nl = (n + RPL - 1) / RPL;                 // lanes in use
+    const int ln = (n - 1) / RPL, jn = (n - 1) % RPL;   // owner of the last read position
 
     // ---- my RPL symbols (2 bits each) ------------------------------------------------------
     const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
@@ -363,77 +499,20 @@ banded_fill_kernel(const BandedArgs a)
     {
         const int bit = 2 * lane * RPL;
         const int w = bit >> 5, sh = bit & 31;
-        const int last_word = (n + 15) / 16;      // allocation has (n+15)/16 + 1 words
+        const int last_word = (n + 15) / 16;            // allocation has (n+15)/16 + 1 words
         const uint32_t lo = (w <= last_word) ? pk[w] : 0u;
         const uint32_t hi = (w + 1 <= last_word) ? pk[w + 1] : 0u;
         symbits = __funnelshift_r(lo, hi, sh);
     }
-    int eoff[RPL];                                // sym * P
-#pragma unroll
-    for (int j = 0; j < RPL; ++j) eoff[j] = (int)((symbits >> (2 * j)) & 3u) * P;
-
-    double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
-    int accarg[RPL];
-#pragma unroll
-    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; accarg[j] = 0; }
-    double bI = kNegInf, bM = kNegInf, bD = kNegInf;   // row above my block, previous column
-    int accord = 0;                                     // collector sources passed so far
-
-    TBW* __restrict__ tbw = reinterpret_cast<TBW*>(a.tbw) + slot * a.tbw_stride + (size_t)lane * P;
+    constexpr int NW = RPL > 5 ? 2 : 1;
+    uint32_t* __restrict__ tbw = a.tbw + slot * a.tbw_stride + (size_t)lane * P * NW;
     uint16_t* __restrict__ acc_tb = a.acc_tb + slot * (size_t)a.acc_stride + lane * RPL;
     double* __restrict__ vfin = a.vfin + slot * a.vfin_stride;
-
-    const int steps = NC + nl - 1;
-    for (int t = 0; t < steps; ++t) {
-        // the row above my block at column c was finished by lane-1 in the previous step
-        const double uI0 = shfl_up_f64(cI[RPL - 1], 1);
-        const double uM0 = shfl_up_f64(cM[RPL - 1], 1);
-        const double uD0 = shfl_up_f64(cD[RPL - 1], 1);
-        const int c = t - lane;
-        if (c < 0 || c >= NC || lane >= nl) continue;
-
-        const double wII = sw[0 * P + c], wIM = sw[1 * P + c], wID = sw[2 * P + c];
-        const double wMI = sw[3 * P + c], wMM = sw[4 * P + c], wMD = sw[5 * P + c];
-        const double wDI = sw[6 * P + c], wDM = sw[7 * P + c], wDD = sw[8 * P + c];
-        const int flag = sflag[c];
-        const double aw = flag ? saccw[c] : kNegInf;
-
-        double uI = uI0, uM = uM0, uD = uD0;      // row above, this column
-        double oI = bI, oM = bM, oD = bD;         // row above, previous column
-        TBW word = 0;
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) {
-            const double eI = se[eoff[j] + c];
-            const double eM = se[4 * P + eoff[j] + c];
-            double vI, vM, vD;
-            int kI, kM, kD;
-            ADV_MAX3((oI + wMI) + eM, (oM + wMM) + eM, (oD + wMD) + eM, vM, kM);
-            ADV_MAX3((uI + wII) + eI, (uM + wIM) + eI, (uD + wID) + eI, vI, kI);
-            ADV_MAX3(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, vD, kD);
-            if (j == 0 && lane == 0) {            // first read position: rows come from row 0
-                vI = sv1[eoff[0] + c];
-                vM = sv1[4 * P + eoff[0] + c];
-            }
-            if (flag & kColFlagAccDst) {
-                vD = acc[j];
-                acc_tb[j] = (uint16_t)accarg[j];
-            }
-            word |= (TBW)(kI | (kM << 2) | (kD << 4)) << (6 * j);
-            oI = cI[j]; oM = cM[j]; oD = cD[j];
-            cI[j] = vI; cM[j] = vM; cD[j] = vD;
-            uI = vI; uM = vM; uD = vD;
-            if (flag & kColFlagAccSrc) {
-                const double cand = vD + aw;
-                if (cand > acc[j]) { acc[j] = cand; accarg[j] = accord; }
-            }
-            if (j == jn && lane == ln) {
-                vfin[0 * P + c] = vI; vfin[1 * P + c] = vM; vfin[2 * P + c] = vD;
-            }
-        }
-        if (flag & kColFlagAccSrc) ++accord;
-        bI = uI0; bM = uM0; bD = uD0;
-        tbw[c] = word;
-    }
+    const uint32_t s_base = smem_u32(smem_raw);
+    if (jn == RPL - 1)
+        banded_sweep<RPL, true>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
+    else
+        banded_sweep<RPL, false>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
     __syncwarp();
 
     // ---- final-only silent states on the last row (hub reductions across the warp) ---------
@@ -472,7 +551,7 @@ struct BandedBtArgs {
     const int64_t* pk_off;
     const int32_t* rlen;
     const double* logp;
-    const void* tbw;
+    const uint32_t* tbw;
     size_t tbw_stride;
     const uint16_t* acc_tb;
     int acc_stride;
@@ -504,24 +583,26 @@ __device__ __forceinline__ void banded_walk(const DevBanded* __restrict__ M, con
         }
         int sl = code / P, c = code - sl * P, r = n;
         state = -1;
-        const bool wide = rpl > 5;
-        const uint32_t* tb32 = reinterpret_cast<const uint32_t*>(a.tbw) + slot * a.tbw_stride;
-        const unsigned long long* tb64 = reinterpret_cast<const unsigned long long*>(a.tbw) + slot * a.tbw_stride;
+        const int nw = rpl > 5 ? 2 : 1;
+        const uint32_t* tbw = a.tbw + slot * a.tbw_stride;
         const uint16_t* acc_tb = a.acc_tb + slot * (size_t)a.acc_stride;
         while (r >= 1) {
             const int s = M->st[sl * M->NC + c];
             emit(s);
             const int ln = (r - 1) / rpl, j = (r - 1) - ln * rpl;
-            const size_t wi = (size_t)ln * P + c;
-            const uint32_t t = wide ? (uint32_t)(tb64[wi] >> (6 * j)) & 63u : (tb32[wi] >> (6 * j)) & 63u;
+            const uint32_t t = tbw[((size_t)ln * P + c) * nw + j / 5] >> (6 * (j % 5));
+            // two bits per slot: bit0 = second candidate beat the first, bit1 = third beat both
+            const int kI = (t & 2u) ? 2 : (int)(t & 1u);
+            const int kM = (t & 8u) ? 2 : (int)((t >> 2) & 1u);
+            const int kD = (t & 32u) ? 2 : (int)((t >> 4) & 1u);
             if (sl == SLOT_D) {
-                if (c == M->acc_col) c = M->acc_src_col[acc_tb[r - 1]];
-                else { sl = (t >> 4) & 3; c -= 1; }
+                if (c == M->acc_col) c = acc_tb[r - 1];
+                else { sl = kD; c -= 1; }
             } else if (r == 1) {
                 state = M->tb1[sym0 * M->S + s];
                 r = 0;
-            } else if (sl == SLOT_M) { sl = (t >> 2) & 3; c -= 1; r -= 1; }
-            else { sl = t & 3; r -= 1; }
+            } else if (sl == SLOT_M) { sl = kM; c -= 1; r -= 1; }
+            else { sl = kI; r -= 1; }
         }
     }
     // row 0: silent closure back to the start state
@@ -843,15 +924,19 @@ int upload_model(advhmm_model* mod)
     int image_bytes = 0;
     if (b.valid) {
         const size_t P = b.NCpad;
-        std::vector<unsigned char> image((9 + 8 + 8 + 1) * P * sizeof(double) + (P + 15) / 16 * 16, 0);
-        double* d = reinterpret_cast<double*>(image.data());
-        memcpy(d, b.w.data(), 9 * P * sizeof(double));
-        memcpy(d + 9 * P, b.e.data(), 8 * P * sizeof(double));
-        memcpy(d + 17 * P, b.v1.data(), 8 * P * sizeof(double));
-        memcpy(d + 25 * P, b.accw.data(), P * sizeof(double));
-        unsigned char* fl = image.data() + 26 * P * sizeof(double);
-        for (int c : b.acc_src_col) fl[c] |= kColFlagAccSrc;
-        if (b.acc_col >= 0) fl[b.acc_col] |= kColFlagAccDst;
+        std::vector<unsigned char> image((size_t)kImgBytesPerCol * P, 0);
+        double* w10 = reinterpret_cast<double*>(image.data() + (size_t)kImgW * P);
+        double* e2 = reinterpret_cast<double*>(image.data() + (size_t)kImgE * P);
+        double* v12 = reinterpret_cast<double*>(image.data() + (size_t)kImgV1 * P);
+        for (size_t c = 0; c < P; ++c) {
+            for (int k = 0; k < 9; ++k) w10[c * 10 + k] = b.w[(size_t)k * P + c];
+            w10[c * 10 + 9] = b.accw[c];
+            for (int x = 0; x < 4; ++x)
+                for (int sl = 0; sl < 2; ++sl) {       // sl: 0 = I slot, 1 = M slot
+                    e2[((size_t)x * P + c) * 2 + sl] = b.e[((size_t)sl * 4 + x) * P + c];
+                    v12[((size_t)x * P + c) * 2 + sl] = b.v1[((size_t)sl * 4 + x) * P + c];
+                }
+        }
         image_bytes = (int)image.size();
         o_image = bb.add(image);
         std::vector<int32_t> st(3 * (size_t)b.NC);
@@ -935,8 +1020,28 @@ struct Plan {
 
 template <typename T> size_t vec_bytes(const std::vector<T>& v) { return v.size() * sizeof(T); }
 
+// event pair bracketing one kernel launch when profiling is on (kind: 0 banded fill, 1 backtrack)
+struct ProfScope {
+    advhmm_context* ctx; int kind; cudaEvent_t stop = nullptr;
+    ProfScope(advhmm_context* c, int k) : ctx(c), kind(k)
+    {
+        if (!ctx->profile) return;
+        auto& ev = ctx->prof_events[kind];
+        if (ctx->prof_used[kind] == ev.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            ev.emplace_back(a, b);
+        }
+        auto& pr = ev[ctx->prof_used[kind]++];
+        cudaEventRecord(pr.first, ctx->stream);
+        stop = pr.second;
+    }
+    ~ProfScope() { if (stop) cudaEventRecord(stop, ctx->stream); }
+};
+
 int launch_banded_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const BandedArgs& args)
 {
+    ProfScope prof(ctx, 0);
 #define ADV_CASE(R)                                                                                  \
     case R: {                                                                                        \
         if (smem > ctx->banded_smem_set[R]) {                                                        \
@@ -1143,7 +1248,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         BandedArgs fa{};
         fa.tiles = d_tiles + tile0; fa.order = d_order; fa.chunk_base = lo;
         fa.pk = d_pk; fa.pk_off = d_pk_off; fa.rlen = d_rlen; fa.logp = out.logp;
-        fa.tbw = w + o_tbw; fa.tbw_stride = 32 * P;
+        fa.tbw = reinterpret_cast<uint32_t*>(w + o_tbw); fa.tbw_stride = 32 * P * (word_bytes / 4);
         fa.acc_tb = reinterpret_cast<uint16_t*>(w + o_acc); fa.acc_stride = 32 * rpl;
         fa.vfin = reinterpret_cast<double*>(w + o_vfin); fa.vfin_stride = 3 * P;
         fa.ftb = reinterpret_cast<int32_t*>(w + o_ftb);
@@ -1153,13 +1258,16 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
             BandedBtArgs ba{};
             ba.tiles = d_tiles; ba.order = d_order; ba.chunk_base = lo; ba.n_items = items; ba.rpl = rpl;
             ba.pk = d_pk; ba.pk_off = d_pk_off; ba.rlen = d_rlen; ba.logp = out.logp;
-            ba.tbw = w + o_tbw; ba.tbw_stride = 32 * P;
+            ba.tbw = reinterpret_cast<const uint32_t*>(w + o_tbw); ba.tbw_stride = 32 * P * (word_bytes / 4);
             ba.acc_tb = reinterpret_cast<const uint16_t*>(w + o_acc); ba.acc_stride = 32 * rpl;
             ba.ftb = reinterpret_cast<const int32_t*>(w + o_ftb);
             ba.item_tile = d_item_tile;
             ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = out.path;
             ba.path_cap = out.path_cap; ba.cursor = out.cursor;
-            banded_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
+            {
+                ProfScope prof(ctx, 1);
+                banded_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
+            }
             CU_TRY(cudaGetLastError());
             ctx->launches++;
         }
@@ -1276,6 +1384,28 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
 }  // namespace
 
 // =============================================================================================
+// fp64 add/compare issue-rate microbenchmark (the roofline denominator of the fill kernel)
+// =============================================================================================
+namespace {
+// Each thread runs 8 independent dependent-chains of DADD; with 1024 threads per SM resident the
+// fp64 pipe is saturated.  ops = threads * iters * 8.
+__global__ void __launch_bounds__(256) fp64_add_peak_kernel(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double d = seed * 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a0 = __dadd_rn(a0, d); a1 = __dadd_rn(a1, d); a2 = __dadd_rn(a2, d); a3 = __dadd_rn(a3, d);
+            a4 = __dadd_rn(a4, d); a5 = __dadd_rn(a5, d); a6 = __dadd_rn(a6, d); a7 = __dadd_rn(a7, d);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+}  // namespace
+
+// =============================================================================================
 // C-ABI
 // =============================================================================================
 extern "C" {
@@ -1335,6 +1465,8 @@ void advhmm_context_destroy(advhmm_context* ctx)
         for (DevBuf* b : {&ctx->d_seqs, &ctx->d_seq_off, &ctx->d_pk, &ctx->d_meta, &ctx->d_work, &ctx->d_out, &ctx->d_paths, &ctx->d_flags}) b->release();
         ctx->h_meta.release(); ctx->h_out.release();
         if (ctx->meta_done) cudaEventDestroy(ctx->meta_done);
+        for (auto& v : ctx->prof_events)
+            for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -1348,6 +1480,62 @@ int advhmm_context_synchronize(advhmm_context* ctx)
 }
 
 void* advhmm_context_stream(advhmm_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int advhmm_context_profile(advhmm_context* ctx, int enable)
+{
+    if (!ctx) return set_error(ADVHMM_EINVAL, "ctx is null");
+    ctx->profile = enable != 0;
+    ctx->prof_used[0] = ctx->prof_used[1] = 0;
+    return ADVHMM_OK;
+}
+
+int advhmm_context_profile_read(advhmm_context* ctx, double* fill_ms, int64_t* fill_launches,
+                                double* backtrack_ms, int64_t* backtrack_launches)
+{
+    if (!ctx || ctx->device < 0) return set_error(ADVHMM_EINVAL, "no device context");
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    double ms[2] = {0, 0};
+    for (int k = 0; k < 2; ++k)
+        for (size_t i = 0; i < ctx->prof_used[k]; ++i) {
+            float t = 0;
+            CU_TRY(cudaEventElapsedTime(&t, ctx->prof_events[k][i].first, ctx->prof_events[k][i].second));
+            ms[k] += t;
+        }
+    if (fill_ms) *fill_ms = ms[0];
+    if (fill_launches) *fill_launches = (int64_t)ctx->prof_used[0];
+    if (backtrack_ms) *backtrack_ms = ms[1];
+    if (backtrack_launches) *backtrack_launches = (int64_t)ctx->prof_used[1];
+    ctx->prof_used[0] = ctx->prof_used[1] = 0;
+    return ADVHMM_OK;
+}
+
+int advhmm_fp64_add_peak(advhmm_context* ctx, double* gops)
+{
+    if (!ctx || ctx->device < 0 || !gops) return set_error(ADVHMM_EINVAL, "no device context");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    CU_TRY(ctx->d_flags.ensure((size_t)blocks * threads * sizeof(double) + 256));
+    double* out = reinterpret_cast<double*>(ctx->d_flags.as<unsigned char>() + 256);
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreate(&a));
+    CU_TRY(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(cudaEventRecord(a, ctx->stream));
+        fp64_add_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 1.0 + rep);
+        CU_TRY(cudaEventRecord(b, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, a, b));
+        const double ops = (double)blocks * threads * iters * 64.0;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e9);
+        ctx->launches++;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *gops = best;
+    return ADVHMM_OK;
+}
 int64_t advhmm_context_launch_count(advhmm_context* ctx) { return ctx ? ctx->launches : 0; }
 
 int advhmm_model_create(advhmm_context* ctx, const advhmm_model_desc* desc, advhmm_model** out)

@@ -20,7 +20,8 @@ KIND_GENERIC, KIND_BANDED = 0, 1
 
 EXPORTS = (
     "advhmm_context_create", "advhmm_context_destroy", "advhmm_context_synchronize",
-    "advhmm_context_stream", "advhmm_context_launch_count",
+    "advhmm_context_stream", "advhmm_context_launch_count", "advhmm_context_profile",
+    "advhmm_context_profile_read", "advhmm_fp64_add_peak",
     "advhmm_model_create", "advhmm_model_destroy", "advhmm_model_info_get",
     "advhmm_viterbi_batch", "advhmm_log_probability_batch", "advhmm_viterbi_multi",
     "advhmm_last_error", "advhmm_abi_version", "advhmm_encode_acgt",
@@ -69,6 +70,9 @@ def load_library():
         lib.advhmm_context_stream.restype = vp
         lib.advhmm_context_launch_count.argtypes = [vp]
         lib.advhmm_context_launch_count.restype = i64
+        lib.advhmm_context_profile.argtypes = [vp, C.c_int]
+        lib.advhmm_context_profile_read.argtypes = [vp, vp, vp, vp, vp]
+        lib.advhmm_fp64_add_peak.argtypes = [vp, vp]
         lib.advhmm_model_create.argtypes = [vp, C.POINTER(ModelDesc), C.POINTER(vp)]
         lib.advhmm_model_destroy.argtypes = [vp]
         lib.advhmm_model_destroy.restype = None
@@ -140,6 +144,22 @@ class Context(object):
 
     def synchronize(self):
         _check(self._lib.advhmm_context_synchronize(self._h))
+
+    def profile(self, enable=True):
+        _check(self._lib.advhmm_context_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(fill_ms, fill_launches, backtrack_ms, backtrack_launches) since the last read."""
+        fm, bm = C.c_double(0), C.c_double(0)
+        fl, bl = C.c_int64(0), C.c_int64(0)
+        _check(self._lib.advhmm_context_profile_read(self._h, C.addressof(fm), C.addressof(fl),
+                                                     C.addressof(bm), C.addressof(bl)))
+        return fm.value, fl.value, bm.value, bl.value
+
+    def fp64_add_peak(self):
+        g = C.c_double(0)
+        _check(self._lib.advhmm_fp64_add_peak(self._h, C.addressof(g)))
+        return g.value
 
     def close(self):
         if getattr(self, "_h", None):

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .pomegranate import DiscreteDistribution, HiddenMarkovModel, State
+from . import pomegranate as _default_backend
 
 ALPHABET = "ACGT"
 DEFAULT_MAX_ERROR_RATE = 0.05     # settings.py:28 (Illumina); 0.3 for PacBio/nanopore
@@ -144,7 +144,7 @@ def align_repeat_segments(segments):
 
 
 # ------------------------------------------------------------------------------ flank models
-def _flank_matcher(pattern, tag, error_rate):
+def _flank_matcher(pattern, tag, error_rate, pom=None):
     """Suffix (left flank, ``tag='suffix'``) or prefix (right flank) matcher.
 
     ``hmm_utils.py:357-420`` / ``:290-353``.  They differ in three places only: the suffix
@@ -152,9 +152,11 @@ def _flank_matcher(pattern, tag, error_rate):
     prefix matcher may be left from any match column with probability 0.01 (a read can end
     inside the flank), and the order in which the entry transitions are declared.
     """
+    pom = pom or _default_backend
+    State, DiscreteDistribution = pom.State, pom.DiscreteDistribution
     L = len(pattern)
     title = "Suffix Matcher HMM Model" if tag == "suffix" else "Prefix Matcher HMM Model"
-    hmm = HiddenMarkovModel(name=title)
+    hmm = pom.HiddenMarkovModel(name=title)
     uniform = DiscreteDistribution(dict.fromkeys(ALPHABET, 0.25))
     ins = [State(uniform, name="I%s_%s" % (i, tag)) for i in range(L + 1)]
     mat = []
@@ -214,19 +216,21 @@ def _flank_matcher(pattern, tag, error_rate):
     return hmm
 
 
-def get_suffix_matcher_hmm(pattern, error_rate=DEFAULT_MAX_ERROR_RATE):
-    return _flank_matcher(pattern, "suffix", error_rate)
+def get_suffix_matcher_hmm(pattern, error_rate=DEFAULT_MAX_ERROR_RATE, pom=None):
+    return _flank_matcher(pattern, "suffix", error_rate, pom)
 
 
-def get_prefix_matcher_hmm(pattern, error_rate=DEFAULT_MAX_ERROR_RATE):
-    return _flank_matcher(pattern, "prefix", error_rate)
+def get_prefix_matcher_hmm(pattern, error_rate=DEFAULT_MAX_ERROR_RATE, pom=None):
+    return _flank_matcher(pattern, "prefix", error_rate, pom)
 
 
 # ----------------------------------------------------------------------------- repeat models
 def get_constant_number_of_repeats_matcher_hmm(patterns, copies, error_rate=DEFAULT_MAX_ERROR_RATE,
-                                               profile=None):
+                                               profile=None, pom=None):
     """``copies`` unrolled copies of the repeat-unit profile (``hmm_utils.py:424-497``)."""
-    hmm = HiddenMarkovModel(name="Repeating Pattern Matcher HMM Model")
+    pom = pom or _default_backend
+    State, DiscreteDistribution = pom.State, pom.DiscreteDistribution
+    hmm = pom.HiddenMarkovModel(name="Repeating Pattern Matcher HMM Model")
     trans, emis = profile or repeat_profile(align_repeat_segments(patterns), error_rate)
     R = sum(1 for label in emis if label.startswith("M"))
     T = hmm.add_transition
@@ -281,13 +285,15 @@ def _last_nonzero(row):
 
 
 def get_variable_number_of_repeats_matcher_hmm(patterns, copies=1, error_rate=DEFAULT_MAX_ERROR_RATE,
-                                               profile=None):
+                                               profile=None, pom=None):
     """Let a read leave the repeat block after any unit (``hmm_utils.py:501-549``).
 
     Goes through the same dense-matrix round trip as the reference (exp of the stored logs,
     edit, ``from_matrix`` re-logs) because the resulting last-ulp values are part of parity.
     """
-    base = get_constant_number_of_repeats_matcher_hmm(patterns, copies, error_rate, profile)
+    pom = pom or _default_backend
+    State = pom.State
+    base = get_constant_number_of_repeats_matcher_hmm(patterns, copies, error_rate, profile, pom)
     mat = base.dense_transition_matrix()
     m = len(mat)
     states = list(base.states)
@@ -312,7 +318,7 @@ def get_variable_number_of_repeats_matcher_hmm(patterns, copies=1, error_rate=DE
     starts[base.start_index] = 1.0
     ends = np.zeros(m + 2)
     ends[base.end_index] = 1.0
-    out = HiddenMarkovModel.from_matrix(mat, [s.distribution for s in states], starts, ends,
+    out = pom.HiddenMarkovModel.from_matrix(mat, [s.distribution for s in states], starts, ends,
                                         name="Repeat Matcher HMM Model",
                                         state_names=[s.name for s in states], merge=None)
     out.bake(merge=None)
@@ -320,14 +326,15 @@ def get_variable_number_of_repeats_matcher_hmm(patterns, copies=1, error_rate=DE
 
 
 def get_read_matcher_model(left_flanking_region, right_flanking_region, patterns, copies=1,
-                           vpaths=None, error_rate=DEFAULT_MAX_ERROR_RATE, profile=None):
+                           vpaths=None, error_rate=DEFAULT_MAX_ERROR_RATE, profile=None, pom=None):
     """The model every read of a locus is decoded against (``hmm_utils.py:553-595``)."""
     if vpaths:
         raise NotImplementedError("re-estimating the repeat profile from Viterbi paths "
                                   "(--update, hmm_utils.py:428-430) is outside the hot path")
-    hmm = get_suffix_matcher_hmm(left_flanking_region, error_rate)
-    hmm.concatenate(get_variable_number_of_repeats_matcher_hmm(patterns, copies, error_rate, profile))
-    hmm.concatenate(get_prefix_matcher_hmm(right_flanking_region, error_rate))
+    pom = pom or _default_backend
+    hmm = get_suffix_matcher_hmm(left_flanking_region, error_rate, pom)
+    hmm.concatenate(get_variable_number_of_repeats_matcher_hmm(patterns, copies, error_rate, profile, pom))
+    hmm.concatenate(get_prefix_matcher_hmm(right_flanking_region, error_rate, pom))
     hmm.bake(merge=None)
 
     mat = hmm.dense_transition_matrix()
@@ -357,7 +364,7 @@ def get_read_matcher_model(left_flanking_region, right_flanking_region, patterns
     starts[hmm.start_index] = 1.0
     ends = np.zeros(len(names))
     ends[hmm.end_index] = 1.0
-    out = HiddenMarkovModel.from_matrix(mat, [s.distribution for s in hmm.states], starts, ends,
+    out = pom.HiddenMarkovModel.from_matrix(mat, [s.distribution for s in hmm.states], starts, ends,
                                         name="Read Matcher", state_names=names, merge=None)
     out.bake(merge=None)
     return out
@@ -369,7 +376,9 @@ def copies_for_read_length(read_length, pattern_length):
 
 
 def build_vntr_matcher_hmm(left_flank, right_flank, repeat_segments, copies, flank_size=100,
-                           error_rate=DEFAULT_MAX_ERROR_RATE):
-    """``vntr_finder.py:108-115``: trim the flanks and build the read matcher."""
+                           error_rate=DEFAULT_MAX_ERROR_RATE, pom=None):
+    """``vntr_finder.py:108-115``: trim the flanks and build the read matcher.  ``pom`` selects the
+    engine the model is built on (default: this package's; tests and the CPU baseline pass the
+    compiled reference pomegranate to get a reference-engine model with identical tables)."""
     return get_read_matcher_model(left_flank[-flank_size:], right_flank[:flank_size],
-                                  repeat_segments, copies, error_rate=error_rate)
+                                  repeat_segments, copies, error_rate=error_rate, pom=pom)

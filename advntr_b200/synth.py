@@ -127,3 +127,55 @@ def config3_locus(copies=100, R=60, flank=100):
                 flank=flank, error_rate=0.3)
     loc.copies = copies
     return loc
+
+
+# ------------------------------------------------------------------ bulk (numpy) read generators
+import numpy as np
+
+_CODE = np.full(256, 255, dtype=np.uint8)
+for _i, _c in enumerate("ACGT"):
+    _CODE[ord(_c)] = _i
+
+
+def encode(seq):
+    """ASCII DNA -> uint8 codes A,C,G,T = 0..3 (host-side helper for synthetic inputs)."""
+    return _CODE[np.frombuffer(seq.encode("ascii"), dtype=np.uint8)]
+
+
+def revcomp_codes(codes):
+    return (3 - codes[::-1]).astype(np.uint8)
+
+
+def config2_read_codes(locus, coverage=30, decoys=50, seed=None):
+    """Bench-scale version of :func:`config2_reads`: returns ``(flat uint8 codes, lengths)`` for
+    one locus -- mapped reads (one strand) followed by decoy reads, each decoy as forward and
+    reverse complement (the both-strands call site, vntr_finder.py:239-246)."""
+    rng = np.random.Generator(np.random.PCG64(7919 * locus.id + 3 if seed is None else seed))
+    L = locus.read_length
+    seq = encode(locus.sequence)
+    vntr_len = sum(len(s) for s in locus.segments)
+    n_mapped = max(1, int(round((vntr_len + L) * coverage / float(L))))
+    lo = max(0, len(locus.left) - L + 1)
+    hi = max(lo, min(len(locus.left) + vntr_len - 1, len(seq) - L - 8))
+    starts = rng.integers(lo, hi + 1, size=n_mapped)
+    win = seq[starts[:, None] + np.arange(L + 8)[None, :]]
+    sub = rng.random(win.shape) < 0.01
+    win = np.where(sub, rng.integers(0, 4, size=win.shape, dtype=np.uint8), win).astype(np.uint8)
+    reads = []
+    indel = rng.random(win.shape) < 0.002          # 0.1 % insertions + 0.1 % deletions
+    for r in range(n_mapped):
+        row = win[r]
+        pos = np.nonzero(indel[r])[0]
+        if len(pos):
+            for p in pos[::-1]:
+                if rng.random() < 0.5:
+                    row = np.delete(row, p)
+                else:
+                    row = np.insert(row, p, rng.integers(0, 4))
+        reads.append(row[:L])
+    dec = rng.integers(0, 4, size=(decoys, L), dtype=np.uint8)
+    for d in dec:
+        reads.append(d)
+        reads.append(revcomp_codes(d))
+    lengths = np.fromiter((len(r) for r in reads), dtype=np.int64, count=len(reads))
+    return np.concatenate(reads), lengths

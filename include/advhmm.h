@@ -98,6 +98,16 @@ void* advhmm_context_stream(advhmm_context* ctx);
 /* Number of kernels this context has launched since creation (bench `gpu_launches`). */
 int64_t advhmm_context_launch_count(advhmm_context* ctx);
 
+/* Per-kernel device timing for roofline reports: when enabled, every banded fill / backtrack
+ * launch is bracketed by CUDA events on the context's stream.  profile_read() synchronises,
+ * returns the summed durations (ms) and launch counts since the last read, and resets. */
+int  advhmm_context_profile(advhmm_context* ctx, int enable);
+int  advhmm_context_profile_read(advhmm_context* ctx, double* fill_ms, int64_t* fill_launches,
+                                 double* backtrack_ms, int64_t* backtrack_launches);
+/* Measured fp64 add issue rate of this device in Gop/s (lane-operations): the denominator of
+ * the fill kernel's compute roofline (the DP is fp64 add + compare, no FMA, no tensor cores). */
+int  advhmm_fp64_add_peak(advhmm_context* ctx, double* gops);
+
 /* ---- models ---------------------------------------------------------------------------
  * Replaces the tail of HiddenMarkovModel.bake() (hmm.pyx:932-1023: building the C arrays
  * the DP kernels read) -- the host analyses the graph once (silent levels / profile
