@@ -135,7 +135,7 @@ struct Tile {
 };
 
 constexpr int kMaxRPL = 10;             // read positions per lane: reads up to 320 bases on the banded path
-constexpr int kBandedWarps = 8;         // reads per CTA (banded)
+constexpr int kBandedWarpsMax = 16;     // reads per CTA (banded): run-time choice, see ctx->banded_warps
 constexpr int kGenericWarpsMax = 8;
 
 }  // namespace
@@ -155,7 +155,10 @@ struct advhmm_context {
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];   // [0] banded fill, [1] backtrack
     size_t prof_used[2] = {0, 0};
-    int banded_smem_set[kMaxRPL + 1] = {0};   // dynamic-smem opt-in already applied per RPL
+    int banded_smem_set[kMaxRPL + 4] = {0};   // dynamic-smem opt-in already applied per kernel variant
+    int banded_warps = 8;        // reads per CTA of the banded kernel
+    bool int_compare = false;    // integer-pipe compares (ADVHMM_ICMP=1); needs all tables <= 0
+    bool launch_int_compare = false;   // ... and every model of the current batch qualifies
     int generic_smem_set = 0;
     std::mutex mu;
 };
@@ -328,29 +331,52 @@ __device__ __forceinline__ void static_for(F&& f)
     }
 }
 
-template <int SH>
+template <int SH, bool ICMP>
 __device__ __forceinline__ double max3_first(double a0, double a1, double a2, uint32_t& bits)
 {
-    // written in PTX so that each compare costs one DSETP, one 64-bit select and one predicated OR
     double m;
-    asm("{\n\t"
-        ".reg .pred p1, p2;\n\t"
-        ".reg .f64 t;\n\t"
-        "setp.gt.f64 p1, %3, %2;\n\t"
-        "selp.f64 t, %3, %2, p1;\n\t"
-        "@p1 or.b32 %1, %1, %5;\n\t"
-        "setp.gt.f64 p2, %4, t;\n\t"
-        "selp.f64 %0, %4, t, p2;\n\t"
-        "@p2 or.b32 %1, %1, %6;\n\t"
-        "}"
-        : "=d"(m), "+r"(bits)
-        : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
+    if (ICMP) {
+        // All DP values are <= 0 (sums of log-probabilities; checked when the model is compiled),
+        // so a > b  <=>  bits(a) < bits(b) as unsigned 64-bit integers (+0.0 is the largest value
+        // and the smallest pattern, -inf the smallest value and the largest non-NaN pattern).
+        // The compares then run on the integer pipe and leave the fp64 pipe to the adds.
+        asm("{\n\t"
+            ".reg .pred p1, p2;\n\t"
+            ".reg .b64 t, x0, x1, x2;\n\t"
+            "mov.b64 x0, %2;\n\t"
+            "mov.b64 x1, %3;\n\t"
+            "mov.b64 x2, %4;\n\t"
+            "setp.lt.u64 p1, x1, x0;\n\t"
+            "selp.b64 t, x1, x0, p1;\n\t"
+            "@p1 or.b32 %1, %1, %5;\n\t"
+            "setp.lt.u64 p2, x2, t;\n\t"
+            "selp.b64 t, x2, t, p2;\n\t"
+            "@p2 or.b32 %1, %1, %6;\n\t"
+            "mov.b64 %0, t;\n\t"
+            "}"
+            : "=d"(m), "+r"(bits)
+            : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
+    } else {
+        // written in PTX so that each compare costs one DSETP, one 64-bit select and one predicated OR
+        asm("{\n\t"
+            ".reg .pred p1, p2;\n\t"
+            ".reg .f64 t;\n\t"
+            "setp.gt.f64 p1, %3, %2;\n\t"
+            "selp.f64 t, %3, %2, p1;\n\t"
+            "@p1 or.b32 %1, %1, %5;\n\t"
+            "setp.gt.f64 p2, %4, t;\n\t"
+            "selp.f64 %0, %4, t, p2;\n\t"
+            "@p2 or.b32 %1, %1, %6;\n\t"
+            "}"
+            : "=d"(m), "+r"(bits)
+            : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
+    }
     return m;
 }
 
 // ALIGNED: the read length is a multiple of RPL, so the last read position is the last row of a
 // lane and its values can be stored from fixed registers.
-template <int RPL, bool ALIGNED>
+template <int RPL, bool ALIGNED, bool ICMP>
 __device__ __forceinline__ void banded_sweep(const int NC, const int P, const int nl, const int ln, const int jn,
                                              const int lane, const uint32_t s_base, const uint32_t symbits,
                                              const int acc_col, uint32_t* __restrict__ tbw,
@@ -406,8 +432,8 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
             const double2 e = lds128(e_t[j] + cb);             // {eI, eM}
             eIr[j] = e.x;
             const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-            nM[j] = max3_first<6 * (j % 5) + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
-            nD[j] = max3_first<6 * (j % 5) + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
+            nM[j] = max3_first<6 * (j % 5) + 2, ICMP>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
+            nD[j] = max3_first<6 * (j % 5) + 4, ICMP>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
         });
         if (lane == 0) {                                       // first read position: from row 0
             const double2 f = lds128(e_t[0] + v1_delta + cb);
@@ -431,7 +457,7 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
         double uI = uI0, uM = uM0, uD = uD0;
         static_for<0, RPL>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
-            double vI = max3_first<6 * (j % 5)>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
+            double vI = max3_first<6 * (j % 5), ICMP>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
             if (j == 0 && lane == 0) vI = eIr[0];
             uI = vI; uM = nM[j]; uD = nD[j];
             cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
@@ -456,13 +482,13 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
     }
 }
 
-template <int RPL>
-__global__ void __launch_bounds__(kBandedWarps * 32)
+template <int RPL, int WPB, bool ICMP>
+__global__ void __launch_bounds__(WPB * 32, 2)
 banded_fill_kernel(const BandedArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ double s_fval[kBandedWarps][32];
+    __shared__ double s_fval[WPB][32];
 
     const Tile tile = a.tiles[blockIdx.x];
     const DevBanded* __restrict__ M = reinterpret_cast<const DevBanded*>(tile.model);
@@ -510,9 +536,9 @@ banded_fill_kernel(const BandedArgs a)
     double* __restrict__ vfin = a.vfin + slot * a.vfin_stride;
     const uint32_t s_base = smem_u32(smem_raw);
     if (jn == RPL - 1)
-        banded_sweep<RPL, true>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
+        banded_sweep<RPL, true, ICMP>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
     else
-        banded_sweep<RPL, false>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
+        banded_sweep<RPL, false, ICMP>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
     __syncwarp();
 
     // ---- final-only silent states on the last row (hub reductions across the warp) ---------
@@ -1039,25 +1065,35 @@ struct ProfScope {
     ~ProfScope() { if (stop) cudaEventRecord(stop, ctx->stream); }
 };
 
+template <int RPL, int WPB, bool ICMP>
+int launch_banded_variant(advhmm_context* ctx, int grid, int smem, const BandedArgs& args, int slot)
+{
+    if (smem > ctx->banded_smem_set[slot]) {
+        CU_TRY(cudaFuncSetAttribute(banded_fill_kernel<RPL, WPB, ICMP>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ctx->banded_smem_set[slot] = smem;
+    }
+    banded_fill_kernel<RPL, WPB, ICMP><<<grid, WPB * 32, smem, ctx->stream>>>(args);
+    return ADVHMM_OK;
+}
+
 int launch_banded_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const BandedArgs& args)
 {
     ProfScope prof(ctx, 0);
-#define ADV_CASE(R)                                                                                  \
-    case R: {                                                                                        \
-        if (smem > ctx->banded_smem_set[R]) {                                                        \
-            CU_TRY(cudaFuncSetAttribute(banded_fill_kernel<R>,                                       \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));         \
-            ctx->banded_smem_set[R] = smem;                                                          \
-        }                                                                                            \
-        banded_fill_kernel<R><<<grid, kBandedWarps * 32, smem, ctx->stream>>>(args);                 \
-        break;                                                                                       \
-    }
+    int rc = ADVHMM_OK;
+    const bool ic = ctx->launch_int_compare;
+    // 8 reads per CTA, 2 CTAs per SM (126 registers/thread).  Wider CTAs (10 / 12 warps, 96 / 80
+    // registers) spill and measured 25-40 % slower on B200; see profiles/r1_variants.md.
+#define ADV_CASE(R)                                                                              \
+    case R: rc = ic ? launch_banded_variant<R, 8, true>(ctx, grid, smem, args, R)                 \
+                    : launch_banded_variant<R, 8, false>(ctx, grid, smem, args, R); break;
     switch (rpl) {
         ADV_CASE(1) ADV_CASE(2) ADV_CASE(3) ADV_CASE(4) ADV_CASE(5)
         ADV_CASE(6) ADV_CASE(7) ADV_CASE(8) ADV_CASE(9) ADV_CASE(10)
         default: return set_error(ADVHMM_EINVAL, "unsupported rows-per-lane %d", rpl);
     }
 #undef ADV_CASE
+    if (rc) return rc;
     CU_TRY(cudaGetLastError());
     ctx->launches++;
     return ADVHMM_OK;
@@ -1098,6 +1134,23 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     std::vector<int32_t> generic_item_model;
     pl.order.reserve(n_out);
     pl.item_tile.reserve(n_out);
+    // rows per lane follow from the longest read on the banded path; it selects the CTA width
+    int pre_max_len = 0;
+    bool all_nonpositive = true;
+    for (int gi = 0; gi < n_models; ++gi) {
+        advhmm_model* mod = models[gi];
+        if (!mod || mod->ctx != ctx) return set_error(ADVHMM_EINVAL, "model %d does not belong to this context", gi);
+        if (forward || !mod->d_banded || (flags & ADVHMM_FORCE_GENERIC)) continue;
+        all_nonpositive = all_nonpositive && mod->cm.b.nonpositive;
+        for (int64_t r = std::max<int64_t>(group_off[gi], 0); r < std::min<int64_t>(group_off[gi + 1], n_reads); ++r) {
+            const int len = (int)(seq_off[r + 1] - seq_off[r]);
+            if (len <= 32 * kMaxRPL) pre_max_len = std::max(pre_max_len, len);
+        }
+    }
+    const int pre_rpl = std::max(1, (pre_max_len + 31) / 32);
+    const int wpb = ctx->banded_warps;
+    (void)pre_rpl;
+    ctx->launch_int_compare = ctx->int_compare && all_nonpositive;
     std::vector<Tile> generic_tiles;
     for (int gi = 0; gi < n_models; ++gi) {
         advhmm_model* mod = models[gi];
@@ -1111,7 +1164,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
             for (int s = 0; s < strands; ++s) {
                 const int32_t q = (int32_t)(r * strands + s);
                 if (banded_model && len <= 32 * kMaxRPL) {
-                    if (in_tile == 0 || in_tile == kBandedWarps) {
+                    if (in_tile == 0 || in_tile == wpb) {
                         pl.tiles.push_back(Tile{mod->d_banded, (int32_t)pl.order.size(), 0});
                         in_tile = 0;
                     }
@@ -1209,7 +1262,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     const size_t g_per_item = n_generic_items ? g_tb_per + g_rows_per + 8 : 0;
     size_t b_chunk = 0, g_chunk = 0;
     if (pl.n_banded_items) {
-        b_chunk = std::max<size_t>(ctx->workspace_budget / b_per_item, (size_t)kBandedWarps * ctx->sm_count);
+        b_chunk = std::max<size_t>(ctx->workspace_budget / b_per_item, (size_t)kBandedWarpsMax * ctx->sm_count);
         b_chunk = std::min<size_t>(b_chunk, (size_t)pl.n_banded_items);
     }
     if (n_generic_items) {
@@ -1451,6 +1504,8 @@ int advhmm_context_create(int device, void* stream, advhmm_context** out)
         ctx->workspace_budget = std::min<size_t>((size_t)6 << 30, free_b / 4);
         const char* env = getenv("ADVHMM_WORKSPACE_MB");
         if (env && atoll(env) > 0) ctx->workspace_budget = (size_t)atoll(env) << 20;
+        env = getenv("ADVHMM_ICMP");
+        if (env) ctx->int_compare = atoi(env) != 0;
     }
     *out = ctx.release();
     return ADVHMM_OK;

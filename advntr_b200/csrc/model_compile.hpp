@@ -77,6 +77,7 @@ struct BandedTables {
     std::vector<int32_t> fin_off, fin_src;
     std::vector<double>  fin_w;
     int end_final = -1;              // ordinal of the end state among the final states
+    bool nonpositive = false;        // every table entry <= 0: DP values can be ordered as integers
 };
 
 struct CompiledModel {
@@ -331,6 +332,8 @@ inline void build_banded(const GenericTables& g, BandedTables& b)
     b.end_final = fin_ord[g.end];
     if (b.fin_state.size() > 32) return fail("too many final-only states");
     if (b.acc_src_col.size() > 65535) return fail("collector has too many sources");
+    auto le0 = [](const std::vector<double>& v) { for (double x : v) if (x > 0.0 || (x == 0.0 && std::signbit(x))) return false; return true; };
+    b.nonpositive = le0(b.w) && le0(b.e) && le0(b.v1) && le0(b.accw) && le0(b.fin_w) && le0(g.v0);
     b.valid = true;
 }
 

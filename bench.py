@@ -256,8 +256,12 @@ def run_ours(args):
 
     t_build = time.time()
     wl = build_workload(rank, args.loci, args.coverage, args.decoys)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it, and the torch events that
+    # time the region are recorded on the very same stream
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     ctx = engine.Context(device=local, stream=stream.cuda_stream)
+    assert stream.cuda_stream != 0 and ctx.stream == stream.cuda_stream
     models = [engine.DeviceModel(ctx, b) for b in wl["baked"]]
     t_build = time.time() - t_build
     lib = engine.load_library()
