@@ -1,0 +1,111 @@
+"""The call sites of the hot path, batched: every read of a locus in ONE device call.
+
+``vntr_finder.py`` decodes one read at a time (``:738`` mapped reads, ``:239-246`` unmapped
+reads on both strands).  ``LocusDecoder`` keeps the same decisions -- which strand of an
+unmapped read wins, which reads are recruited, which are spanning -- but feeds all reads of
+the locus (or of many loci, ``decode_many``) to the engine at once and applies the path
+consumers to the returned paths.  BAM / FASTA input, the genotype likelihood and the DNN
+pre-filter stay outside (out of scope).
+"""
+from __future__ import annotations
+
+from . import engine, fast_compile, path_utils, read_matcher
+
+
+class SelectedRead(object):
+    """``vntr_finder.py:49-60``."""
+
+    def __init__(self, sequence, logp, vpath, is_mapped=True, query_name=None):
+        self.sequence, self.logp, self.vpath = sequence, logp, vpath
+        self.is_mapped, self.query_name = is_mapped, query_name
+
+
+_COMP = str.maketrans("ACGT", "TGCA")
+
+
+def reverse_complement(seq):
+    return seq.translate(_COMP)[::-1]
+
+
+class LocusDecoder(object):
+    def __init__(self, left_flank, right_flank, repeat_segments, read_length=150, scaled_score=None,
+                 error_rate=read_matcher.DEFAULT_MAX_ERROR_RATE, flank_size=150, locus_id=None):
+        self.id = locus_id
+        self.left_flank, self.right_flank = left_flank, right_flank
+        self.segments = list(repeat_segments)
+        self.pattern = self.segments[0]
+        self.read_length = read_length
+        self.scaled_score = scaled_score
+        self.min_repeat_bp_to_add_read = 2            # vntr_finder.py:66-69
+        copies = read_matcher.copies_for_read_length(read_length, len(self.pattern))
+        self.model = fast_compile.build_vntr_matcher_hmm(left_flank, right_flank, self.segments, copies,
+                                                         flank_size=flank_size, error_rate=error_rate)
+
+    # vntr_finder.py:174-177
+    def min_score_to_select_a_read(self, read_length=None):
+        if not self.scaled_score:
+            return None
+        return self.scaled_score * (read_length or self.read_length)
+
+    def _vpath(self, res, i):
+        p = res.path(i)
+        if p is None:
+            return None
+        st = self.model.states
+        return [(int(k), st[k]) for k in p]
+
+    def select_reads(self, mapped_reads, unmapped_reads=()):
+        """``select_illumina_reads`` (``vntr_finder.py:701-773``) minus the file IO: mapped reads
+        are decoded as given, unmapped reads on both strands keeping the better one."""
+        mapped = [r.upper() for r in mapped_reads if "N" not in r.upper()]
+        unmapped = [r.upper() for r in unmapped_reads if "N" not in r.upper() and len(r) >= self.read_length]
+        batch = mapped + [s for r in unmapped for s in (r, reverse_complement(r))]
+        res = self.model.viterbi_batch(batch)
+        score = self.min_score_to_select_a_read()
+        selected = []
+        for i, seq in enumerate(mapped):
+            vp = self._vpath(res, i)
+            if vp is None:
+                continue
+            if path_utils.recruit_read(res.logp[i], vp, score, seq, self.left_flank, self.right_flank):
+                selected.append(SelectedRead(seq, float(res.logp[i]), vp, True))
+        base = len(mapped)
+        for j, seq in enumerate(unmapped):
+            f, r = base + 2 * j, base + 2 * j + 1
+            k, s = (r, reverse_complement(seq)) if res.logp[f] < res.logp[r] else (f, seq)
+            vp = self._vpath(res, k)
+            if vp is None:
+                continue
+            repeat_bp = path_utils.get_number_of_repeat_bp_matches_in_vpath(vp)
+            if path_utils.recruit_read(res.logp[k], vp, score, s, self.left_flank, self.right_flank) and \
+                    repeat_bp > self.min_repeat_bp_to_add_read:
+                selected.append(SelectedRead(s, float(res.logp[k]), vp, False))
+        return selected
+
+    def observed_repeats(self, selected, accuracy_filter=False):
+        """``find_repeat_count_from_alignment_file`` (``vntr_finder.py:810-850``): repeat counts
+        of spanning reads and (lower bounds from) flanking reads."""
+        covered, flanking = [], []
+        for read in selected:
+            n = path_utils.get_number_of_repeats_in_vpath(read.vpath)
+            if path_utils.read_flanks_repeats_with_confidence(read.vpath, read.sequence, self.left_flank,
+                                                              self.right_flank):
+                covered.append(n)
+            elif not accuracy_filter:
+                flanking.append(n)
+        return covered, sorted(flanking)
+
+    def frameshift_candidate(self, selected):
+        """Most frequent frame-shifting indel state among the selected reads and its count
+        (``vntr_finder.py:265-300``); the binomial test on it is ``identify_frameshift``."""
+        mutations, repeat_bp = path_utils.frameshift_mutations(selected, len(self.pattern))
+        ranked = sorted(mutations.items(), key=lambda x: x[1])
+        return (ranked[-1] if ranked else (None, 0)), repeat_bp
+
+
+def decode_many(decoders, reads_per_locus, ctx=None, both_strands=False):
+    """One device call for the reads of many loci (``advhmm_viterbi_multi``)."""
+    ctx = ctx or engine.Context.default()
+    models = [d.model._device_model() for d in decoders]
+    groups = [[d.model._encode(r) for r in reads] for d, reads in zip(decoders, reads_per_locus)]
+    return ctx.viterbi_multi(models, groups, both_strands=both_strands)

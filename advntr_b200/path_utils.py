@@ -162,3 +162,51 @@ def recruit_read(logp, vpath, min_score_to_count_read, read_sequence, left_flank
             get_number_of_matches_in_vpath(vpath) >= 0.9 * length and logp > -length:
         return get_flanking_regions_matching_rate(vpath, read_sequence, left_flank, right_flank) >= 0.9
     return False
+
+
+def get_emitted_basepair_from_visited_states(state, visited_states, sequence):
+    """Read base emitted at the first visit of ``state`` (``hmm_utils.py:105-112``)."""
+    pos = 0
+    for n in visited_states:
+        if n == state:
+            return sequence[pos]
+        if is_emitting_state(n):
+            pos += 1
+    return None
+
+
+def read_flanks_repeats_with_confidence(vpath, sequence, left_flank, right_flank, min_left=5, min_right=5):
+    """Spanning-read predicate (``vntr_finder.py:311-322``)."""
+    if get_flanking_regions_matching_rate(vpath, sequence, left_flank, right_flank) < 0.95:
+        return False
+    s = summarize(vpath)
+    return s.left_bp > min_left and s.right_bp > min_right
+
+
+def frameshift_mutations(selected, pattern_length):
+    """Indel states inside repeat units whose emitted length is off by <= 2 bp, counted over the
+    selected reads (the path-walking part of ``vntr_finder.py:265-296``).  ``selected`` is an
+    iterable of objects with ``.vpath`` and ``.sequence``.  Returns ``(mutations, repeat_bp)``."""
+    mutations, repeat_bp = {}, 0
+    for read in selected:
+        names = _names(read.vpath)
+        lengths = get_repeating_pattern_lengths(names)
+        repeat_bp += get_number_of_repeat_bp_matches_in_vpath(read.vpath)
+        unit = None
+        for n in names:
+            if n.endswith("fix") or n.startswith("M"):
+                continue
+            if n.startswith("unit_start"):
+                unit = 0 if unit is None else unit + 1
+            if unit is None or unit >= len(lengths):
+                continue
+            if not n.startswith("I") and not n.startswith("D"):
+                continue
+            if lengths[unit] == pattern_length:
+                continue
+            label = n.split("_")[0]
+            if label.startswith("I"):
+                label += get_emitted_basepair_from_visited_states(n, names, read.sequence)
+            if abs(lengths[unit] - pattern_length) <= 2:
+                mutations[label] = mutations.get(label, 0) + 1
+    return mutations, repeat_bp

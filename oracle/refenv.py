@@ -160,3 +160,64 @@ def reference_hmm_utils(backend, tag: str):
         else:
             sys.modules.pop("pomegranate", None)
     return mod
+
+
+def _install_io_stubs():
+    """Import-time stand-ins for the IO / ML packages ``advntr/vntr_finder.py`` pulls in at module
+    level (pysam, keras, Biopython's Seq/SeqIO/pairwise2).  None of them is on the hot path; only
+    ``Seq(...).reverse_complement()`` is actually exercised (``vntr_finder.py:241``)."""
+    _install_bio_stubs()
+    bio = sys.modules["Bio"]
+    if hasattr(bio, "Seq"):
+        return
+    comp = str.maketrans("ACGTacgt", "TGCAtgca")
+
+    class Seq(str):
+        def reverse_complement(self):
+            return Seq(str(self).translate(comp)[::-1])
+
+    class SeqRecord(object):
+        def __init__(self, seq=None, id=None, **kw):
+            self.seq, self.id = seq, id
+
+    seqmod = _stub("Bio.Seq", Seq=Seq)
+    seqio = _stub("Bio.SeqIO", SeqRecord=SeqRecord, parse=lambda *a, **k: iter(()), write=lambda *a, **k: 0)
+    pw = _stub("Bio.pairwise2", align=None)
+    recmod = _stub("Bio.SeqRecord", SeqRecord=SeqRecord)
+    bio.Seq, bio.SeqIO, bio.pairwise2, bio.SeqRecord = seqmod, seqio, pw, recmod
+    sys.modules.update({"Bio.Seq": seqmod, "Bio.SeqIO": seqio, "Bio.pairwise2": pw, "Bio.SeqRecord": recmod})
+    if "pysam" not in sys.modules:
+        sys.modules["pysam"] = _stub("pysam", AlignmentFile=None)
+    if "keras" not in sys.modules:
+        keras = _stub("keras")
+        km = _stub("keras.models", Sequential=None, load_model=None)
+        kl = _stub("keras.layers", Dense=None, Activation=None)
+        keras.models, keras.layers = km, kl
+        sys.modules.update({"keras": keras, "keras.models": km, "keras.layers": kl})
+
+
+def reference_vntr_finder(backend, tag: str):
+    """The reference's ``advntr/vntr_finder.py`` (THIS container only) bound to ``backend``."""
+    name = "_advntr_ref_vntr_finder_" + tag
+    if name in sys.modules:
+        return sys.modules[name]
+    reference_settings()
+    _install_io_stubs()
+    saved = sys.modules.get("pomegranate")
+    saved_hu = sys.modules.pop("advntr.hmm_utils", None)
+    sys.modules["pomegranate"] = backend
+    try:
+        spec = importlib.util.spec_from_file_location(
+            name, os.path.join(REF_ROOT, "advntr", "vntr_finder.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        sys.modules.pop("advntr.hmm_utils", None)
+        if saved_hu is not None:
+            sys.modules["advntr.hmm_utils"] = saved_hu
+        if saved is not None:
+            sys.modules["pomegranate"] = saved
+        else:
+            sys.modules.pop("pomegranate", None)
+    return mod

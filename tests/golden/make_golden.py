@@ -64,6 +64,96 @@ def case_inputs(name):
     return left, right, segs, copies, eps, reads
 
 
+def callsite_inputs():
+    """Config-4 style inputs: a coding-VNTR-like locus, mapped reads of which half carry a 1 bp
+    deletion inside one repeat unit (a frameshift), and unmapped reads (reverse-strand reads of
+    the locus + random decoys)."""
+    rng = random.Random(404)
+    ru = synth.rand_dna(rng, 30)
+    left, right = synth.rand_dna(rng, 200), synth.rand_dna(rng, 200)
+    segs = [ru] * 6
+    locus = left + "".join(segs) + right
+    shifted = left + ru * 2 + ru[:13] + ru[14:] + ru * 3 + right      # 1 bp deleted in unit 3
+    mapped = []
+    for i in range(60):
+        src = shifted if i % 2 else locus
+        s = rng.randrange(120, 170)
+        mapped.append(synth.sequencing_errors(rng, src[s:s + 158], 0.005, 0.0, 0.0)[:150])
+    unmapped = [synth.revcomp(locus[s:s + 150]) for s in range(125, 165, 4)]
+    unmapped += [synth.rand_dna(rng, 150) for _ in range(10)]
+    return left, right, segs, mapped, unmapped
+
+
+def make_callsite_case(pom):
+    """Decisions of the reference's own VNTRFinder (vntr_finder.py) on those reads: which mapped
+    reads recruit_read() accepts, what process_unmapped_read() selects, repeat counts of
+    spanning / flanking reads, and the frameshift candidate + its count."""
+    vf = refenv.reference_vntr_finder(pom, "ref")
+    left, right, segs, mapped, unmapped = callsite_inputs()
+
+    class FakeVNTR(object):
+        id, pattern, chromosome, start_point, scaled_score = 4, segs[0], "chr1", 1000, None
+        left_flanking_region, right_flanking_region = left, right
+
+        def get_repeat_segments(self):
+            return segs
+
+        def get_length(self):
+            return sum(len(x) for x in segs)
+
+    finder = vf.VNTRFinder(FakeVNTR())
+    hmm = finder.get_vntr_matcher_hmm(read_length=150)
+    score = finder.get_min_score_to_select_a_read(150)
+    selected, mapped_ok = [], []
+    for r in mapped:                                       # vntr_finder.py:736-748
+        logp, vpath = hmm.viterbi(r)
+        ok = bool(finder.recruit_read(logp, vpath, score, r))
+        mapped_ok.append(ok)
+        if ok:
+            selected.append(vf.SelectedRead(sequence=r, logp=logp, vpath=vpath, reference_start=1))
+    n_mapped_selected = len(selected)
+
+    class Acc(object):
+        value = 0.0
+    for r in unmapped:                                     # vntr_finder.py:757-764
+        finder.process_unmapped_read(None, r, hmm, score, Acc(), selected)
+    covered, flanking = [], []
+    for sr in selected:                                    # vntr_finder.py:810-847
+        n = vf.get_number_of_repeats_in_vpath(sr.vpath)
+        if finder.read_flanks_repeats_with_confidence(sr.vpath, sr.sequence):
+            covered.append(n)
+        else:
+            flanking.append(n)
+    seen = {}
+    finder.identify_frameshift = lambda cov, cnt, exp, error_rate=0.01: seen.update(cov=cov, cnt=cnt) or False
+    import logging
+
+    class Grab(logging.Handler):
+        def emit(self, record):
+            msg = record.getMessage()
+            if msg.startswith("Frameshift Candidate and Occurrence"):
+                seen["candidate"] = msg.split("Occurrence ")[1].split(":")[0]
+    grab = Grab()
+    logging.getLogger().addHandler(grab)
+    logging.getLogger().setLevel(logging.INFO)
+    finder.find_frameshift_from_selected_reads(selected)
+    logging.getLogger().removeHandler(grab)
+    real = vf.VNTRFinder(FakeVNTR())
+    with open(os.path.join(HERE, "callsite_frameshift.json"), "w") as fh:
+        json.dump({"left": left, "right": right, "segments": segs, "mapped": mapped, "unmapped": unmapped,
+                   "mapped_recruited": mapped_ok,
+                   "selected_sequences": [sr.sequence for sr in selected],
+                   "selected_logp": [sr.logp for sr in selected],
+                   "n_mapped_selected": n_mapped_selected,
+                   "covered_repeats": covered, "flanking_repeats": sorted(flanking),
+                   "frameshift_candidate": seen.get("candidate"),
+                   "frameshift_count": seen["cnt"], "avg_bp_coverage": seen["cov"],
+                   "frameshift_result": real.find_frameshift_from_selected_reads(selected)}, fh)
+    print("callsite: %d/%d mapped recruited, %d selected in total, covered %s, frameshift %r x%d" % (
+        sum(mapped_ok), len(mapped), len(selected), covered[:8], real.find_frameshift_from_selected_reads(selected),
+        seen["cnt"]))
+
+
 def main():
     pom = refenv.reference_pomegranate()
     hu = refenv.reference_hmm_utils(pom, "ref")
@@ -104,6 +194,7 @@ def main():
             paths=np.array(paths, dtype=np.int32),
             path_off=np.array(off, dtype=np.int64))
         print(name, "states", b["n_states"], "edges", len(b["in_src"]), "reads", len(reads))
+    make_callsite_case(pom)
     # the one fixture the reference's own tests hold for this path (tests/test_hmm_utils.py:15-17):
     # a recorded Viterbi path (state names) + read + the repeat segments it must yield
     with open(os.path.join(refenv.REF_ROOT, "tests", "data", "hmm_utils.json")) as fh:

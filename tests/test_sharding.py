@@ -1,0 +1,60 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the locus sharding + host gather.  Each rank
+"decodes" its loci with the oracle (this is a test: the product path needs a GPU) and the gathered
+result must equal the single-process result."""
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from advntr_b200 import sharding
+
+
+def test_lpt_is_a_balanced_partition():
+    costs = [9, 7, 6, 5, 5, 4, 3, 1]
+    owner, load = sharding.lpt_assign(costs, 3)
+    assert sorted(sum((sharding.my_units(owner, r) for r in range(3)), [])) == list(range(len(costs)))
+    assert max(load) - min(load) <= max(costs)
+    assert sharding.lpt_assign(costs, 1)[0] == [0] * len(costs)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import oracle
+    from conftest import Golden
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cases = [Golden(n) for n in ("small_a", "small_b", "divergent", "config1")]
+    costs = [sharding.locus_cost(len(c.baked["in_src"]), [len(r) for r in c.reads]) for c in cases]
+    owner, _ = sharding.lpt_assign(costs, world)
+    local = {}
+    for i in sharding.my_units(owner, rank):
+        logp, paths = oracle.OracleModel(cases[i].baked).viterbi(cases[i].codes())
+        local[i] = (logp, [None if p is None else p.tolist() for p in paths])
+    full = sharding.gather_results(local, owner, rank, world)
+    ok = all(np.array_equal(full[i][0].view(np.int64), c.logp.view(np.int64)) for i, c in enumerate(cases))
+    ok = ok and all(full[i][1][j] == (None if c.path(j) is None else c.path(j).tolist())
+                    for i, c in enumerate(cases) for j in range(len(c.reads)))
+    ok = ok and len(set(owner)) == world
+    open(os.path.join(out_dir, "rank%d.ok" % rank), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_and_gather(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(os.path.join(str(tmp_path), "rank%d.ok" % r)).read() == "1"
