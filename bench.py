@@ -407,9 +407,19 @@ def roofline(ctx, wl, fill_ms, fill_n, bt_ms, bt_n, total_ms, steps):
     fill_s = fill_ms * 1e-3
     achieved = bytes_per_step * steps / fill_s / 1e9 if fill_s > 0 else None
     fp64_peak = ctx.fp64_add_peak()
-    out = {"kernel": "banded_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+    # measured DRAM bytes per read of this kernel from the committed ncu --set full capture
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_fill_traffic.json")
+    if os.path.exists(tpath) and fill_n:
+        try:
+            traffic = json.load(open(tpath))["dram_bytes_per_read"] * len(lens) * steps / fill_n
+        except Exception:
+            traffic = None
+    out = {"kernel": "banded_fill_kernel", "bound": "hbm",
+           "achieved": achieved, "peak": hbm_peak,
            "peak_source": which, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
-           "traffic": None, "launches": int(fill_n), "avg_launch_ms": fill_ms / max(fill_n, 1),
+           "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_step * steps / max(fill_n, 1),
+           "launches": int(fill_n), "avg_launch_ms": fill_ms / max(fill_n, 1),
            "share_of_step": fill_ms / total_ms if total_ms else None,
            "backtrack_share_of_step": bt_ms / total_ms if total_ms else None,
            "fp64": {"achieved_gops": ops * steps / fill_s / 1e9 if fill_s > 0 else None,
