@@ -565,6 +565,212 @@ banded_fill_kernel(const BandedArgs a)
 }
 
 // =============================================================================================
+// banded fill kernel for long reads / large models (PacBio-like, BASELINE config 3)
+//
+// Same recurrence, tables and traceback encoding as banded_fill_kernel, but
+//   * a read is cut into stripes of 32*RPL positions that one warp sweeps one after the other;
+//     the last position of a stripe is carried to the next stripe through a per-read buffer in
+//     global memory (3 doubles per column, updated in place: writes trail reads by >= 32 columns)
+//     that lane 0 consumes through a double-buffered 32-column ring in shared memory;
+//   * the model tables are read from global memory through the read-only path (the image of a
+//     100-copy model is > 1 MB); the warps of an SM walk the columns together, so L1 serves them.
+// =============================================================================================
+struct LongArgs {
+    const Tile* tiles;
+    const int32_t* order;
+    int32_t chunk_base;
+    const uint32_t* pk;
+    const int64_t* pk_off;
+    const int32_t* rlen;
+    double* logp;
+    uint32_t* tbw;              // per slot: stripes_max * 32 * Pmax * 2 words
+    size_t tbw_stride;
+    uint16_t* acc_tb;           // per slot: stripes_max * 32 * RPL entries
+    size_t acc_stride;
+    double* vfin;               // per slot 3 * Pmax
+    size_t vfin_stride;
+    double* carry;              // per slot 3 * Pmax
+    size_t carry_stride;
+    int32_t* ftb;               // per slot 32
+};
+
+constexpr int kLongRPL = 8;
+constexpr int kLongWarps = 4;
+
+__device__ __forceinline__ double2 ldg128(const unsigned char* p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kLongWarps * 32, 2)
+banded_long_kernel(const LongArgs a)
+{
+    constexpr int RPL = kLongRPL, NW = 2, H = 32 * RPL;
+    __shared__ double s_ring[kLongWarps][2][3][32];
+    __shared__ double s_fval[kLongWarps][32];
+
+    const Tile tile = a.tiles[blockIdx.x];
+    const DevBanded* __restrict__ M = reinterpret_cast<const DevBanded*>(tile.model);
+    const int P = M->P, NC = M->NC, acc_col = M->acc_col;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= tile.cnt) return;
+    const int item = tile.first + warp;
+    const int q = a.order[item];
+    const size_t slot = (size_t)(item - a.chunk_base);
+    const int n = a.rlen[q];
+    if (n == 0) {
+        if (lane == 0) a.logp[q] = M->logp_empty;
+        return;
+    }
+    const unsigned char* __restrict__ img = M->image;
+    const unsigned char* __restrict__ img_e = img + (size_t)kImgE * P;
+    const unsigned char* __restrict__ img_v1 = img + (size_t)kImgV1 * P;
+    const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
+    double* __restrict__ vfin = a.vfin + slot * a.vfin_stride;
+    double* __restrict__ carry = a.carry + slot * a.carry_stride;
+    const int n_stripes = (n + H - 1) / H;
+    const int last_word = (n + 15) / 16;
+
+    for (int s = 0; s < n_stripes; ++s) {
+        const int rows = min(H, n - s * H);
+        const int nl = (rows + RPL - 1) / RPL;
+        const bool last_stripe = (s == n_stripes - 1);
+        const int ln = (rows - 1) / RPL, jn = (rows - 1) % RPL;
+        uint32_t symbits;
+        {
+            const int bit = 2 * (s * H + lane * RPL);
+            const int w = bit >> 5;
+            symbits = (w <= last_word) ? (pk[w] >> (bit & 31)) & 0xffffu : 0u;
+        }
+        size_t eoff[RPL];
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) eoff[j] = (size_t)((symbits >> (2 * j)) & 3u) * 16u * P;
+
+        uint32_t* __restrict__ tbw = a.tbw + slot * a.tbw_stride + ((size_t)(s * 32 + lane) * P) * NW;
+        uint16_t* __restrict__ acc_tb = a.acc_tb + slot * a.acc_stride + (size_t)s * H + lane * RPL;
+
+        double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
+        int accarg[RPL];
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; accarg[j] = 0; }
+        double bI = kNegInf, bM = kNegInf, bD = kNegInf;
+
+        if (s > 0) {                           // ring block 0 = carried values of columns 0..31
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s_ring[warp][0][k][lane] = carry[(size_t)k * P + lane];
+        }
+        __syncwarp();
+
+        const int steps = NC + nl - 1;
+#pragma unroll 1
+        for (int t = 0; t < steps; ++t) {
+            if (s > 0 && (t & 31) == 0) {      // prefetch the next 32 carried columns
+                const int col = t + 32 + lane;
+                const int buf = ((t >> 5) + 1) & 1;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s_ring[warp][buf][k][lane] = (col < P) ? carry[(size_t)k * P + col] : kNegInf;
+                __syncwarp();
+            }
+            double uI0 = shfl_up_f64(cI[RPL - 1], 1);
+            double uM0 = shfl_up_f64(cM[RPL - 1], 1);
+            double uD0 = shfl_up_f64(cD[RPL - 1], 1);
+            const int c = t - lane;
+            if (c < 0 || c >= NC || lane >= nl) continue;
+            if (lane == 0 && s > 0) {
+                const int buf = (t >> 5) & 1;
+                uI0 = s_ring[warp][buf][0][t & 31];
+                uM0 = s_ring[warp][buf][1][t & 31];
+                uD0 = s_ring[warp][buf][2][t & 31];
+            }
+            const unsigned char* wp = img + (size_t)c * 80u;
+            const double2 w01 = ldg128(wp), w23 = ldg128(wp + 16), w45 = ldg128(wp + 32);
+            const double2 w67 = ldg128(wp + 48), w89 = ldg128(wp + 64);
+            const double wII = w01.x, wIM = w01.y, wID = w23.x, wMI = w23.y, wMM = w45.x, wMD = w45.y;
+            const double wDI = w67.x, wDM = w67.y, wDD = w89.x, aw = w89.y;
+            const size_t cb = (size_t)c * 16u;
+
+            double nM[RPL], nD[RPL], eIr[RPL];
+            uint32_t word[NW] = {0u, 0u};
+            static_for<0, RPL>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                const double2 e = ldg128(img_e + eoff[j] + cb);
+                eIr[j] = e.x;
+                const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
+                nM[j] = max3_first<6 * (j % 5) + 2, false>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
+                nD[j] = max3_first<6 * (j % 5) + 4, false>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
+            });
+            const bool first_row = (lane == 0 && s == 0);
+            if (first_row) {
+                const double2 f = ldg128(img_v1 + eoff[0] + cb);
+                nM[0] = f.y;
+                eIr[0] = f.x;
+            }
+            if (c == acc_col) {
+#pragma unroll
+                for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
+            }
+            if (aw > kNegInf) {
+#pragma unroll
+                for (int j = 0; j < RPL; ++j) {
+                    const double cand = nD[j] + aw;
+                    if (cand > acc[j]) { acc[j] = cand; accarg[j] = c; }
+                }
+            }
+            double uI = uI0, uM = uM0, uD = uD0;
+            static_for<0, RPL>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                double vI = max3_first<6 * (j % 5), false>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
+                if (j == 0 && first_row) vI = eIr[0];
+                uI = vI; uM = nM[j]; uD = nD[j];
+                cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
+            });
+            bI = uI0; bM = uM0; bD = uD0;
+            reinterpret_cast<uint2*>(tbw)[c] = make_uint2(word[0], word[1]);
+            if (!last_stripe) {
+                if (lane == 31) {              // full stripe: lane 31 owns its last position
+                    carry[c] = cI[RPL - 1]; carry[(size_t)P + c] = cM[RPL - 1]; carry[(size_t)2 * P + c] = cD[RPL - 1];
+                }
+            } else if (lane == ln) {
+                double fI = cI[0], fM = cM[0], fD = cD[0];
+#pragma unroll
+                for (int j = 1; j < RPL; ++j)
+                    if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
+                vfin[c] = fI; vfin[(size_t)P + c] = fM; vfin[(size_t)2 * P + c] = fD;
+            }
+        }
+        if (lane < nl) {
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) acc_tb[j] = (uint16_t)accarg[j];
+        }
+        __syncwarp();
+    }
+
+    // final-only silent states on the last row
+    const int NF = M->NF;
+    int32_t* __restrict__ ftb = a.ftb + slot * 32;
+    for (int f = 0; f < NF; ++f) {
+        const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
+        double best = kNegInf;
+        int arg = 0x7fffffff;
+        for (int k = k0 + lane; k < k1; k += 32) {
+            const int code = M->fin_src[k];
+            const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
+            const double cand = sv + M->fin_w[k];
+            if (cand > best) { best = cand; arg = k; }
+        }
+        warp_argmax_first(best, arg);
+        if (lane == 0) {
+            s_fval[warp][f] = best;
+            ftb[f] = (best > kNegInf) ? M->fin_src[arg] : 0;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) a.logp[q] = s_fval[warp][M->end_final];
+}
+
+// =============================================================================================
 // banded backtrack kernel: one thread per read
 // =============================================================================================
 struct BandedBtArgs {
@@ -580,7 +786,7 @@ struct BandedBtArgs {
     const uint32_t* tbw;
     size_t tbw_stride;
     const uint16_t* acc_tb;
-    int acc_stride;
+    size_t acc_stride;
     const int32_t* ftb;
     const int32_t* item_tile;   // tile index of every work item
     int32_t* path_len;          // [n_out]
@@ -611,11 +817,11 @@ __device__ __forceinline__ void banded_walk(const DevBanded* __restrict__ M, con
         state = -1;
         const int nw = rpl > 5 ? 2 : 1;
         const uint32_t* tbw = a.tbw + slot * a.tbw_stride;
-        const uint16_t* acc_tb = a.acc_tb + slot * (size_t)a.acc_stride;
+        const uint16_t* acc_tb = a.acc_tb + slot * a.acc_stride;
         while (r >= 1) {
             const int s = M->st[sl * M->NC + c];
             emit(s);
-            const int ln = (r - 1) / rpl, j = (r - 1) - ln * rpl;
+            const int ln = (r - 1) / rpl, j = (r - 1) - ln * rpl;   // ln = stripe * 32 + lane
             const uint32_t t = tbw[((size_t)ln * P + c) * nw + j / 5] >> (6 * (j % 5));
             // two bits per slot: bit0 = second candidate beat the first, bit1 = third beat both
             const int kI = (t & 2u) ? 2 : (int)(t & 1u);
@@ -982,13 +1188,14 @@ int upload_model(advhmm_model* mod)
     mod->info.smem_bytes = 0;
     mod->info.max_in_degree = g.max_in_degree;
     const size_t smem_limit = ctx->device >= 0 ? ctx->smem_optin : (size_t)232448;
-    const bool banded_ok = b.valid && (size_t)image_bytes + 4096 <= smem_limit;
-    if (banded_ok) {
+    if (b.valid) {
         mod->info.kind = ADVHMM_KIND_BANDED;
         mod->info.n_columns = b.NC;
         mod->info.n_final_states = (int)b.fin_state.size();
         mod->info.smem_bytes = image_bytes;
-        mod->banded_smem = image_bytes;
+        // 0: the image does not fit in shared memory -> every read of this model takes the
+        // long-read kernel, which streams the tables from global memory
+        mod->banded_smem = ((size_t)image_bytes + 4096 <= smem_limit) ? image_bytes : 0;
     }
     if (ctx->device < 0) return ADVHMM_OK;   // host-only context: analysis only
 
@@ -1023,25 +1230,28 @@ int upload_model(advhmm_model* mod)
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     mod->d_generic = reinterpret_cast<DevGeneric*>(P8(o_dg));
     mod->d_generic_fwd = reinterpret_cast<DevGeneric*>(P8(o_dgf));
-    mod->d_banded = banded_ok ? reinterpret_cast<DevBanded*>(P8(o_db)) : nullptr;
+    mod->d_banded = b.valid ? reinterpret_cast<DevBanded*>(P8(o_db)) : nullptr;
     return ADVHMM_OK;
 }
 
 // =============================================================================================
 // host side: batch planning and launches
 // =============================================================================================
+// work items (result reads) of one kernel family, in launch order
+struct Family {
+    std::vector<int32_t> items;      // result-read ids
+    std::vector<int32_t> model;      // model index of every item
+    int first_item = 0;              // position of the family inside Plan::order
+    int max_len = 0;
+};
+
 struct Plan {
-    int n_reads = 0, n_out = 0, strands = 1;
     std::vector<int64_t> pk_off;        // [n_out]
     int64_t pk_words = 0;
-    // work items grouped by kernel family
-    std::vector<int32_t> order;         // banded items first, then generic items
+    std::vector<int32_t> order;         // short-banded items, then long-banded, then generic
     std::vector<int32_t> item_tile;     // tile of every item
-    std::vector<Tile> tiles;            // banded tiles first
-    int n_banded_items = 0, n_banded_tiles = 0;
-    int max_len_banded = 0, max_len_generic = 0;
-    int max_P = 0, max_banded_smem = 0;
-    int max_m_generic = 0;
+    std::vector<Tile> tiles;
+    int max_P_short = 0, max_smem_short = 0, max_P_long = 0, max_m_generic = 0;
 };
 
 template <typename T> size_t vec_bytes(const std::vector<T>& v) { return v.size() * sizeof(T); }
@@ -1115,10 +1325,10 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     const int n_out = n_reads * strands;
     if (n_out == 0) return ADVHMM_OK;
     if (flags & ADVHMM_FP32) return set_error(ADVHMM_EUNSUPPORTED, "fp32 mode is not available in this build");
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
 
-    // ---- plan ------------------------------------------------------------------------------
+    // ---- plan: packed-read offsets, kernel family of every result read, tiles ----------------
     Plan pl;
-    pl.n_reads = n_reads; pl.n_out = n_out; pl.strands = strands;
     pl.pk_off.resize(n_out);
     int64_t words = 0;
     for (int r = 0; r < n_reads; ++r) {
@@ -1130,89 +1340,78 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         }
     }
     pl.pk_words = words;
-    std::vector<int32_t> generic_items;
-    std::vector<int32_t> generic_item_model;
-    pl.order.reserve(n_out);
-    pl.item_tile.reserve(n_out);
-    // rows per lane follow from the longest read on the banded path; it selects the CTA width
-    int pre_max_len = 0;
+
+    Family fam_short, fam_long, fam_generic;
     bool all_nonpositive = true;
-    for (int gi = 0; gi < n_models; ++gi) {
-        advhmm_model* mod = models[gi];
-        if (!mod || mod->ctx != ctx) return set_error(ADVHMM_EINVAL, "model %d does not belong to this context", gi);
-        if (forward || !mod->d_banded || (flags & ADVHMM_FORCE_GENERIC)) continue;
-        all_nonpositive = all_nonpositive && mod->cm.b.nonpositive;
-        for (int64_t r = std::max<int64_t>(group_off[gi], 0); r < std::min<int64_t>(group_off[gi + 1], n_reads); ++r) {
-            const int len = (int)(seq_off[r + 1] - seq_off[r]);
-            if (len <= 32 * kMaxRPL) pre_max_len = std::max(pre_max_len, len);
-        }
-    }
-    const int pre_rpl = std::max(1, (pre_max_len + 31) / 32);
-    const int wpb = ctx->banded_warps;
-    (void)pre_rpl;
-    ctx->launch_int_compare = ctx->int_compare && all_nonpositive;
-    std::vector<Tile> generic_tiles;
     for (int gi = 0; gi < n_models; ++gi) {
         advhmm_model* mod = models[gi];
         if (!mod || mod->ctx != ctx) return set_error(ADVHMM_EINVAL, "model %d does not belong to this context", gi);
         const int64_t r0 = group_off[gi], r1 = group_off[gi + 1];
         if (r0 < 0 || r1 < r0 || r1 > n_reads) return set_error(ADVHMM_EINVAL, "bad group_off at model %d", gi);
-        const bool banded_model = !forward && mod->d_banded && !(flags & ADVHMM_FORCE_GENERIC);
-        int in_tile = 0;
+        const bool banded = !forward && mod->d_banded && !(flags & ADVHMM_FORCE_GENERIC);
         for (int64_t r = r0; r < r1; ++r) {
             const int len = (int)(seq_off[r + 1] - seq_off[r]);
-            for (int s = 0; s < strands; ++s) {
-                const int32_t q = (int32_t)(r * strands + s);
-                if (banded_model && len <= 32 * kMaxRPL) {
-                    if (in_tile == 0 || in_tile == wpb) {
-                        pl.tiles.push_back(Tile{mod->d_banded, (int32_t)pl.order.size(), 0});
-                        in_tile = 0;
-                    }
-                    pl.tiles.back().cnt = ++in_tile;
-                    pl.item_tile.push_back((int32_t)pl.tiles.size() - 1);
-                    pl.order.push_back(q);
-                    pl.max_len_banded = std::max(pl.max_len_banded, len);
-                    pl.max_P = std::max(pl.max_P, mod->cm.b.NCpad);
-                    pl.max_banded_smem = std::max(pl.max_banded_smem, mod->banded_smem);
+            Family* f = &fam_generic;
+            if (banded) {
+                if (mod->banded_smem > 0 && len <= 32 * kMaxRPL) {
+                    f = &fam_short;
+                    pl.max_P_short = std::max(pl.max_P_short, mod->cm.b.NCpad);
+                    pl.max_smem_short = std::max(pl.max_smem_short, mod->banded_smem);
+                    all_nonpositive = all_nonpositive && mod->cm.b.nonpositive;
                 } else {
-                    generic_items.push_back(q);
-                    generic_item_model.push_back(gi);
-                    pl.max_len_generic = std::max(pl.max_len_generic, len);
-                    pl.max_m_generic = std::max(pl.max_m_generic, mod->cm.g.m);
+                    f = &fam_long;
+                    pl.max_P_long = std::max(pl.max_P_long, mod->cm.b.NCpad);
                 }
+            } else {
+                pl.max_m_generic = std::max(pl.max_m_generic, mod->cm.g.m);
+            }
+            f->max_len = std::max(f->max_len, len);
+            for (int s = 0; s < strands; ++s) {
+                f->items.push_back((int32_t)(r * strands + s));
+                f->model.push_back(gi);
             }
         }
     }
-    pl.n_banded_items = (int)pl.order.size();
-    pl.n_banded_tiles = (int)pl.tiles.size();
+    ctx->launch_int_compare = ctx->int_compare && all_nonpositive;
+
     // generic launch geometry: as many warps per CTA as DP rows fit in shared memory
     int gwarps = kGenericWarpsMax, rows_in_smem = 1;
-    if (!generic_items.empty()) {
+    if (!fam_generic.items.empty()) {
         const size_t per_warp = (size_t)pl.max_m_generic * 2 * sizeof(double);
         const size_t budget = ctx->smem_optin > 8192 ? ctx->smem_optin - 8192 : 0;
         gwarps = (int)std::min<size_t>(kGenericWarpsMax, per_warp ? budget / per_warp : kGenericWarpsMax);
         if (gwarps < 1) { gwarps = 4; rows_in_smem = 0; }
+    }
+    pl.order.reserve(n_out);
+    pl.item_tile.reserve(n_out);
+    auto make_tiles = [&](Family& f, int per_tile, int kind) {
+        f.first_item = (int)pl.order.size();
         int in_tile = 0, last_model = -1;
-        for (size_t i = 0; i < generic_items.size(); ++i) {
-            const int gi = generic_item_model[i];
-            if (in_tile == 0 || in_tile == gwarps || gi != last_model) {
-                const void* dm = forward ? (const void*)models[gi]->d_generic_fwd : (const void*)models[gi]->d_generic;
+        for (size_t i = 0; i < f.items.size(); ++i) {
+            const int gi = f.model[i];
+            if (in_tile == 0 || in_tile == per_tile || gi != last_model) {
+                const void* dm = kind == 2 ? (forward ? (const void*)models[gi]->d_generic_fwd
+                                                      : (const void*)models[gi]->d_generic)
+                                           : (const void*)models[gi]->d_banded;
                 pl.tiles.push_back(Tile{dm, (int32_t)pl.order.size(), 0});
                 in_tile = 0;
             }
             last_model = gi;
             pl.tiles.back().cnt = ++in_tile;
             pl.item_tile.push_back((int32_t)pl.tiles.size() - 1);
-            pl.order.push_back(generic_items[i]);
+            pl.order.push_back(f.items[i]);
         }
-    }
-    const int n_generic_items = (int)pl.order.size() - pl.n_banded_items;
+    };
+    make_tiles(fam_short, ctx->banded_warps, 0);
+    make_tiles(fam_long, kLongWarps, 1);
+    make_tiles(fam_generic, gwarps, 2);
+    const int n_short = (int)fam_short.items.size(), n_long = (int)fam_long.items.size();
+    const int n_generic = (int)fam_generic.items.size();
 
     // ---- metadata upload (pinned staging, one H2D) -----------------------------------------
     const size_t b_seq_off = (size_t)(n_reads + 1) * sizeof(int64_t);
     const size_t b_pk_off = vec_bytes(pl.pk_off), b_order = vec_bytes(pl.order);
     const size_t b_item_tile = vec_bytes(pl.item_tile), b_tiles = vec_bytes(pl.tiles);
-    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t o_seq_off = 0, o_pk_off = o_seq_off + al(b_seq_off), o_order = o_pk_off + al(b_pk_off);
     const size_t o_item_tile = o_order + al(b_order), o_tiles = o_item_tile + al(b_item_tile);
     const size_t meta_bytes = o_tiles + al(b_tiles);
@@ -1249,35 +1448,40 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     }
     if (want_path) CU_TRY(cudaMemsetAsync(out.cursor, 0, sizeof(unsigned long long), ctx->stream));
 
-    // ---- workspace: sized once for both kernel families, chunks end on tile boundaries -------
-    const int rpl = std::max(1, (pl.max_len_banded + 31) / 32);
-    const size_t P = (size_t)pl.max_P;
-    const size_t word_bytes = rpl > 5 ? 8 : 4;
-    const size_t b_per_item = pl.n_banded_items
-        ? 32 * P * word_bytes + 3 * P * sizeof(double) + (size_t)32 * rpl * 2 + 32 * 4 : 0;
+    // ---- workspace: sized once for all families (they run one after the other on the stream),
+    //      chunks end on tile boundaries --------------------------------------------------------
+    const int rpl = std::max(1, (fam_short.max_len + 31) / 32);
+    const size_t Ps = (size_t)pl.max_P_short, Pl = (size_t)pl.max_P_long;
+    const size_t nw_short = rpl > 5 ? 2 : 1;
+    const size_t s_per_item = n_short ? 32 * Ps * nw_short * 4 + 3 * Ps * 8 + (size_t)32 * rpl * 2 + 32 * 4 : 0;
+    const size_t stripes_max = n_long ? ((size_t)std::max(fam_long.max_len, 1) + 32 * kLongRPL - 1) / (32 * kLongRPL) : 0;
+    const size_t l_tbw_words = stripes_max * 32 * Pl * 2;
+    const size_t l_acc = stripes_max * 32 * kLongRPL;
+    const size_t l_per_item = n_long ? l_tbw_words * 4 + 6 * Pl * 8 + l_acc * 2 + 32 * 4 : 0;
     const size_t gm = (size_t)pl.max_m_generic;
-    const size_t g_tb_per = (want_path && n_generic_items)
-        ? (size_t)std::max(pl.max_len_generic, 1) * gm * sizeof(uint16_t) : 0;
-    const size_t g_rows_per = (n_generic_items && !rows_in_smem) ? 2 * gm * sizeof(double) : 0;
-    const size_t g_per_item = n_generic_items ? g_tb_per + g_rows_per + 8 : 0;
-    size_t b_chunk = 0, g_chunk = 0;
-    if (pl.n_banded_items) {
-        b_chunk = std::max<size_t>(ctx->workspace_budget / b_per_item, (size_t)kBandedWarpsMax * ctx->sm_count);
-        b_chunk = std::min<size_t>(b_chunk, (size_t)pl.n_banded_items);
-    }
-    if (n_generic_items) {
-        g_chunk = std::max<size_t>(ctx->workspace_budget / g_per_item, (size_t)gwarps);
-        g_chunk = std::min<size_t>(g_chunk, (size_t)n_generic_items);
-    }
-    // banded layout
-    const size_t o_tbw = 0, o_vfin = al(b_chunk * 32 * P * word_bytes);
-    const size_t o_acc = o_vfin + al(b_chunk * 3 * P * sizeof(double));
-    const size_t o_ftb = o_acc + al(b_chunk * 32 * rpl * 2);
-    const size_t b_bytes = o_ftb + al(b_chunk * 32 * 4);
-    // generic layout (shares the buffer: the two families run one after the other on the stream)
-    const size_t o_gtb = 0, o_grows = al(g_chunk * g_tb_per);
-    const size_t g_bytes = o_grows + al(g_chunk * g_rows_per);
-    const size_t o_end = std::max(b_bytes, g_bytes);           // end_state[n_out], whole batch
+    const size_t g_tb_per = (want_path && n_generic) ? (size_t)std::max(fam_generic.max_len, 1) * gm * sizeof(uint16_t) : 0;
+    const size_t g_rows_per = (n_generic && !rows_in_smem) ? 2 * gm * sizeof(double) : 0;
+    const size_t g_per_item = n_generic ? g_tb_per + g_rows_per + 8 : 0;
+    auto chunk_of = [&](size_t per_item, int n_items, size_t floor_items) {
+        if (!n_items) return (size_t)0;
+        size_t c = std::max<size_t>(ctx->workspace_budget / per_item, floor_items);
+        return std::min<size_t>(c, (size_t)n_items);
+    };
+    const size_t s_chunk = chunk_of(s_per_item, n_short, (size_t)kBandedWarpsMax * ctx->sm_count);
+    const size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)kLongWarps);
+    const size_t g_chunk = chunk_of(g_per_item, n_generic, (size_t)gwarps);
+    // short layout
+    const size_t so_tbw = 0, so_vfin = al(s_chunk * 32 * Ps * nw_short * 4);
+    const size_t so_acc = so_vfin + al(s_chunk * 3 * Ps * 8), so_ftb = so_acc + al(s_chunk * 32 * rpl * 2);
+    const size_t s_bytes = so_ftb + al(s_chunk * 32 * 4);
+    // long layout
+    const size_t lo_tbw = 0, lo_vfin = al(l_chunk * l_tbw_words * 4), lo_carry = lo_vfin + al(l_chunk * 3 * Pl * 8);
+    const size_t lo_acc = lo_carry + al(l_chunk * 3 * Pl * 8), lo_ftb = lo_acc + al(l_chunk * l_acc * 2);
+    const size_t l_bytes = lo_ftb + al(l_chunk * 32 * 4);
+    // generic layout
+    const size_t go_tb = 0, go_rows = al(g_chunk * g_tb_per);
+    const size_t g_bytes = go_rows + al(g_chunk * g_rows_per);
+    const size_t o_end = std::max(s_bytes, std::max(l_bytes, g_bytes));   // end_state[n_out], whole batch
     CU_TRY(ctx->d_work.ensure(o_end + al((size_t)n_out * sizeof(int32_t))));
     unsigned char* w = ctx->d_work.as<unsigned char>();
 
@@ -1286,66 +1490,93 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         int hi = (int)std::min<size_t>((size_t)end, (size_t)lo + cap);
         if (hi < end)
             while (hi > lo && pl.item_tile[hi] == pl.item_tile[hi - 1]) --hi;
-        if (hi == lo) {   // a single tile larger than cap cannot happen (cap >= warps per CTA)
+        if (hi == lo) {
             hi = lo + 1;
             while (hi < end && pl.item_tile[hi] == pl.item_tile[hi - 1]) ++hi;
         }
         return hi;
     };
+    auto launch_backtrack = [&](int lo, int items, int bt_rpl, const uint32_t* tbw, size_t tbw_stride,
+                                const uint16_t* acc, size_t acc_stride, const int32_t* ftb) -> int {
+        BandedBtArgs ba{};
+        ba.tiles = d_tiles; ba.order = d_order; ba.chunk_base = lo; ba.n_items = items; ba.rpl = bt_rpl;
+        ba.pk = d_pk; ba.pk_off = d_pk_off; ba.rlen = d_rlen; ba.logp = out.logp;
+        ba.tbw = tbw; ba.tbw_stride = tbw_stride; ba.acc_tb = acc; ba.acc_stride = acc_stride; ba.ftb = ftb;
+        ba.item_tile = d_item_tile;
+        ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = out.path;
+        ba.path_cap = out.path_cap; ba.cursor = out.cursor;
+        {
+            ProfScope prof(ctx, 1);
+            banded_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
+        }
+        CU_TRY(cudaGetLastError());
+        ctx->launches++;
+        return ADVHMM_OK;
+    };
 
-    // ---- banded reads -----------------------------------------------------------------------
-    for (int lo = 0; lo < pl.n_banded_items;) {
-        const int hi = next_chunk(lo, pl.n_banded_items, b_chunk);
-        const int items = hi - lo;
+    // ---- short banded reads (the Illumina path) ---------------------------------------------
+    for (int lo = fam_short.first_item, end = lo + n_short; lo < end;) {
+        const int hi = next_chunk(lo, end, s_chunk);
         const int tile0 = pl.item_tile[lo], tile1 = pl.item_tile[hi - 1] + 1;
         BandedArgs fa{};
         fa.tiles = d_tiles + tile0; fa.order = d_order; fa.chunk_base = lo;
         fa.pk = d_pk; fa.pk_off = d_pk_off; fa.rlen = d_rlen; fa.logp = out.logp;
-        fa.tbw = reinterpret_cast<uint32_t*>(w + o_tbw); fa.tbw_stride = 32 * P * (word_bytes / 4);
-        fa.acc_tb = reinterpret_cast<uint16_t*>(w + o_acc); fa.acc_stride = 32 * rpl;
-        fa.vfin = reinterpret_cast<double*>(w + o_vfin); fa.vfin_stride = 3 * P;
-        fa.ftb = reinterpret_cast<int32_t*>(w + o_ftb);
-        int rc = launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_banded_smem, fa);
+        fa.tbw = reinterpret_cast<uint32_t*>(w + so_tbw); fa.tbw_stride = 32 * Ps * nw_short;
+        fa.acc_tb = reinterpret_cast<uint16_t*>(w + so_acc); fa.acc_stride = 32 * rpl;
+        fa.vfin = reinterpret_cast<double*>(w + so_vfin); fa.vfin_stride = 3 * Ps;
+        fa.ftb = reinterpret_cast<int32_t*>(w + so_ftb);
+        int rc = launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa);
         if (rc) return rc;
         if (want_path) {
-            BandedBtArgs ba{};
-            ba.tiles = d_tiles; ba.order = d_order; ba.chunk_base = lo; ba.n_items = items; ba.rpl = rpl;
-            ba.pk = d_pk; ba.pk_off = d_pk_off; ba.rlen = d_rlen; ba.logp = out.logp;
-            ba.tbw = reinterpret_cast<const uint32_t*>(w + o_tbw); ba.tbw_stride = 32 * P * (word_bytes / 4);
-            ba.acc_tb = reinterpret_cast<const uint16_t*>(w + o_acc); ba.acc_stride = 32 * rpl;
-            ba.ftb = reinterpret_cast<const int32_t*>(w + o_ftb);
-            ba.item_tile = d_item_tile;
-            ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = out.path;
-            ba.path_cap = out.path_cap; ba.cursor = out.cursor;
-            {
-                ProfScope prof(ctx, 1);
-                banded_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
-            }
-            CU_TRY(cudaGetLastError());
-            ctx->launches++;
+            rc = launch_backtrack(lo, hi - lo, rpl, fa.tbw, fa.tbw_stride, fa.acc_tb, (size_t)fa.acc_stride, fa.ftb);
+            if (rc) return rc;
         }
         lo = hi;
     }
 
-    // ---- everything else: generic kernel ----------------------------------------------------
-    if (n_generic_items > 0) {
+    // ---- long banded reads / models too large for shared memory ------------------------------
+    for (int lo = fam_long.first_item, end = lo + n_long; lo < end;) {
+        const int hi = next_chunk(lo, end, l_chunk);
+        const int tile0 = pl.item_tile[lo], tile1 = pl.item_tile[hi - 1] + 1;
+        LongArgs la{};
+        la.tiles = d_tiles + tile0; la.order = d_order; la.chunk_base = lo;
+        la.pk = d_pk; la.pk_off = d_pk_off; la.rlen = d_rlen; la.logp = out.logp;
+        la.tbw = reinterpret_cast<uint32_t*>(w + lo_tbw); la.tbw_stride = l_tbw_words;
+        la.acc_tb = reinterpret_cast<uint16_t*>(w + lo_acc); la.acc_stride = l_acc;
+        la.vfin = reinterpret_cast<double*>(w + lo_vfin); la.vfin_stride = 3 * Pl;
+        la.carry = reinterpret_cast<double*>(w + lo_carry); la.carry_stride = 3 * Pl;
+        la.ftb = reinterpret_cast<int32_t*>(w + lo_ftb);
+        {
+            ProfScope prof(ctx, 0);
+            banded_long_kernel<<<tile1 - tile0, kLongWarps * 32, 0, ctx->stream>>>(la);
+        }
+        CU_TRY(cudaGetLastError());
+        ctx->launches++;
+        if (want_path) {
+            int rc = launch_backtrack(lo, hi - lo, kLongRPL, la.tbw, la.tbw_stride, la.acc_tb, la.acc_stride, la.ftb);
+            if (rc) return rc;
+        }
+        lo = hi;
+    }
+
+    // ---- everything else: generic kernel ------------------------------------------------------
+    if (n_generic > 0) {
         const int smem = rows_in_smem ? (int)(gwarps * 2 * gm * sizeof(double)) : 0;
         if (smem > 48 * 1024 && smem > ctx->generic_smem_set) {
             CU_TRY(cudaFuncSetAttribute(generic_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             CU_TRY(cudaFuncSetAttribute(generic_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             ctx->generic_smem_set = smem;
         }
-        const int gend = (int)pl.order.size();
-        for (int lo = pl.n_banded_items; lo < gend;) {
-            const int hi = next_chunk(lo, gend, g_chunk);
+        for (int lo = fam_generic.first_item, end = lo + n_generic; lo < end;) {
+            const int hi = next_chunk(lo, end, g_chunk);
             const int items = hi - lo;
             const int tile0 = pl.item_tile[lo], tile1 = pl.item_tile[hi - 1] + 1;
             GenericArgs ga{};
             ga.tiles = d_tiles + tile0; ga.order = d_order; ga.chunk_base = lo;
             ga.pk = d_pk; ga.pk_off = d_pk_off; ga.rlen = d_rlen; ga.logp = out.logp;
             ga.end_state = reinterpret_cast<int32_t*>(w + o_end);
-            ga.tb = reinterpret_cast<uint16_t*>(w + o_gtb); ga.tb_stride = g_tb_per / sizeof(uint16_t);
-            ga.rows = reinterpret_cast<double*>(w + o_grows); ga.rows_stride = 2 * gm;
+            ga.tb = reinterpret_cast<uint16_t*>(w + go_tb); ga.tb_stride = g_tb_per / sizeof(uint16_t);
+            ga.rows = reinterpret_cast<double*>(w + go_rows); ga.rows_stride = 2 * gm;
             ga.warps = gwarps; ga.rows_in_smem = rows_in_smem;
             if (forward) generic_fill_kernel<true><<<tile1 - tile0, gwarps * 32, smem, ctx->stream>>>(ga);
             else generic_fill_kernel<false><<<tile1 - tile0, gwarps * 32, smem, ctx->stream>>>(ga);

@@ -247,6 +247,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback of the hot path")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner to stdout; the contract is ONE JSON line on stdout
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

@@ -104,18 +104,50 @@ def test_many_loci_one_call(ctx):
         m.close()
 
 
-def test_long_reads_take_the_generic_kernel(ctx, golden_config1):
-    """Reads longer than the banded kernel's 320 positions are routed to the generic kernel."""
+def test_reads_longer_than_one_stripe(ctx, golden_config1):
+    """Reads longer than 320 positions leave the 150 bp kernel for the striped long-read kernel
+    (several stripes of 256 positions, carried through global memory)."""
     g = golden_config1
     from advntr_b200 import synth
     loc = synth.config1_locus()
     rng = random.Random(4)
-    reads = [loc.sequence[:400], loc.sequence[50:450], synth.rand_dna(rng, 333)] + g.reads[:5]
+    reads = [loc.sequence[:400], loc.sequence[50:450], synth.rand_dna(rng, 333), loc.sequence,
+             loc.left + loc.pattern * 25 + loc.right, synth.rand_dna(rng, 700), loc.sequence[:321],
+             loc.sequence[:256 + 150], loc.sequence[:512]] + g.reads[:5]
     codes = [oracle.encode(r) for r in reads]
     lp, paths = oracle.OracleModel(g.baked).viterbi(codes)
-    _, res = _decode(ctx, g.baked, codes)
+    for force in (False, True):
+        _, res = _decode(ctx, g.baked, codes, force_generic=force)
+        assert same_bits(res.logp, lp)
+        assert_paths_equal([res.path(i) for i in range(len(res))], paths)
+
+
+def test_pacbio_like_model_and_reads(ctx):
+    """BASELINE config 3, scaled down: 60 bp repeat unit x 16 unrolled copies, 100 bp flanks,
+    error rate 0.3 (advntr_commands.py:66-69); the model's tables (3,600 states, 253 KB) do not
+    fit in shared memory, reads are ~1 kb with CLR-like errors."""
+    from advntr_b200 import engine, read_matcher, synth
+    rng = random.Random(33)
+    ru = synth.rand_dna(rng, 60)
+    left, right = synth.rand_dna(rng, 100), synth.rand_dna(rng, 100)
+    model = read_matcher.get_read_matcher_model(left, right, [ru], 16, error_rate=0.3)
+    dm = engine.DeviceModel(ctx, model.baked)
+    assert dm.kind == "banded" and dm.info.smem_bytes > 227 * 1024
+    reads = []
+    for copies in (3, 9, 16, 12, 7):
+        true = left + ru * copies + right
+        reads.append(synth.sequencing_errors(rng, true, 0.02, 0.05, 0.05))
+    reads += [reads[0][:300], reads[1][:150], ""]
+    codes = [oracle.encode(r) for r in reads]
+    lp, paths = oracle.OracleModel(model.baked).viterbi(codes)
+    res = dm.viterbi(codes)
+    dm.close()
     assert same_bits(res.logp, lp)
     assert_paths_equal([res.path(i) for i in range(len(res))], paths)
+    from advntr_b200 import path_utils
+    st = model.states
+    counts = [path_utils.get_number_of_repeats_in_vpath([(int(k), st[k]) for k in res.path(i)]) for i in range(5)]
+    assert counts == [3, 9, 16, 12, 7]
 
 
 def test_non_profile_model_on_device(ctx):
