@@ -1732,7 +1732,9 @@ int advhmm_context_create(int device, void* stream, advhmm_context** out)
         else { CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->owns_stream = true; }
         size_t free_b = 0, total_b = 0;
         CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-        ctx->workspace_budget = std::min<size_t>((size_t)6 << 30, free_b / 4);
+        // traceback workspace: long reads need ~40 MB each to keep every SM busy, so by default
+        // half of the free device memory (capped at 96 GB) may be used; ADVHMM_WORKSPACE_MB overrides
+        ctx->workspace_budget = std::min<size_t>((size_t)96 << 30, free_b / 2);
         const char* env = getenv("ADVHMM_WORKSPACE_MB");
         if (env && atoll(env) > 0) ctx->workspace_budget = (size_t)atoll(env) << 20;
         env = getenv("ADVHMM_ICMP");

@@ -411,6 +411,40 @@ class HiddenMarkovModel(object):
         model.bake(verbose=verbose, merge=merge)
         return model
 
+    def sparse_transition_matrix(self):
+        """The non-zero cells of ``dense_transition_matrix()`` as ``{(i, j): probability}``.
+        Same values (``numpy.exp`` of the stored logs), without the O(m^2) array."""
+        b = self.baked
+        rows = np.repeat(np.arange(b["n_states"]), np.diff(b["out_off"]))
+        probs = np.exp(b["out_logp"])
+        return {(int(i), int(j)): p for i, j, p in zip(rows, b["out_dst"], probs) if p != 0}
+
+    @classmethod
+    def from_sparse(cls, cells, distributions, starts, ends=None, state_names=None, name=None,
+                    verbose=False, merge="All"):
+        """``from_matrix`` for a matrix given as ``{(i, j): probability}``: identical model (the
+        cells are walked row-major like the dense loop, hmm.pyx:3226-3229)."""
+        model = cls(name=name)
+        n = len(distributions)
+        names = state_names or ["s{}".format(i) for i in range(n)]
+        states = [State(d, name=nm) for nm, d in zip(names, distributions)]
+        for s in states:
+            model.add_state(s)
+        for i, p in enumerate(starts):
+            if p != 0:
+                model.add_transition(model.start, states[i], p)
+        for (i, j) in sorted(cells):
+            p = cells[(i, j)]
+            if p != 0:
+                model.add_transition(states[i], states[j], p)
+        if ends is not None:
+            tail = states[n - 1] if n else None      # see from_matrix: always the LAST state
+            for p in ends:
+                if p != 0:
+                    model.add_transition(tail, model.end, p)
+        model.bake(verbose=verbose, merge=merge)
+        return model
+
     # ------------------------------------------------------------------ decoding
     def _release_engine(self):
         if self._engine is not None:

@@ -294,6 +294,8 @@ def get_variable_number_of_repeats_matcher_hmm(patterns, copies=1, error_rate=DE
     pom = pom or _default_backend
     State = pom.State
     base = get_constant_number_of_repeats_matcher_hmm(patterns, copies, error_rate, profile, pom)
+    if hasattr(base, "sparse_transition_matrix"):
+        return _variable_repeats_sparse(base, pom)
     mat = base.dense_transition_matrix()
     m = len(mat)
     states = list(base.states)
@@ -325,6 +327,44 @@ def get_variable_number_of_repeats_matcher_hmm(patterns, copies=1, error_rate=DE
     return out
 
 
+def _last_in_row(cells, i):
+    cols = [j for (r, j) in cells if r == i]
+    return max(cols) if cols else None
+
+
+def _variable_repeats_sparse(base, pom):
+    """Same edits as the dense branch of get_variable_number_of_repeats_matcher_hmm on the
+    non-zero cells only (O(E) instead of O(m^2); bit-identical result)."""
+    cells = base.sparse_transition_matrix()
+    m = len(base.states)
+    states = list(base.states)
+    states.append(pom.State(None, name="start_repeating_pattern_match"))
+    states.append(pom.State(None, name="end_repeating_pattern_match"))
+    enter, leave = m, m + 1
+    by_row = {}
+    for (i, j) in cells:
+        if i not in by_row or j > by_row[i]:
+            by_row[i] = j
+    first_unit = by_row[base.start_index]
+    del cells[(base.start_index, first_unit)]
+    cells[(base.start_index, enter)] = 1
+    cells[(enter, first_unit)] = 1
+    for i, st in enumerate(states):
+        if st.name.startswith("unit_end"):
+            cells[(i, by_row[i])] = 0.5
+            cells[(i, leave)] = 0.5
+    cells[(leave, base.end_index)] = 1
+    starts = np.zeros(m + 2)
+    starts[base.start_index] = 1.0
+    ends = np.zeros(m + 2)
+    ends[base.end_index] = 1.0
+    out = pom.HiddenMarkovModel.from_sparse(cells, [s.distribution for s in states], starts, ends,
+                                            name="Repeat Matcher HMM Model",
+                                            state_names=[s.name for s in states], merge=None)
+    out.bake(merge=None)
+    return out
+
+
 def get_read_matcher_model(left_flanking_region, right_flanking_region, patterns, copies=1,
                            vpaths=None, error_rate=DEFAULT_MAX_ERROR_RATE, profile=None, pom=None):
     """The model every read of a locus is decoded against (``hmm_utils.py:553-595``)."""
@@ -337,8 +377,10 @@ def get_read_matcher_model(left_flanking_region, right_flanking_region, patterns
     hmm.concatenate(get_prefix_matcher_hmm(right_flanking_region, error_rate, pom))
     hmm.bake(merge=None)
 
-    mat = hmm.dense_transition_matrix()
     names = [s.name for s in hmm.states]
+    if hasattr(hmm, "sparse_transition_matrix"):
+        return _read_matcher_sparse(hmm, names, pom)
+    mat = hmm.dense_transition_matrix()
     first_copy, repeat_matches, entry = [], [], None
     for i, nm in enumerate(names):
         tail = nm.split("_")[-1]
@@ -366,6 +408,38 @@ def get_read_matcher_model(left_flanking_region, right_flanking_region, patterns
     ends[hmm.end_index] = 1.0
     out = pom.HiddenMarkovModel.from_matrix(mat, [s.distribution for s in hmm.states], starts, ends,
                                         name="Read Matcher", state_names=names, merge=None)
+    out.bake(merge=None)
+    return out
+
+
+def _read_matcher_sparse(hmm, names, pom):
+    """The final edit of get_read_matcher_model (hmm_utils.py:561-594) on the non-zero cells."""
+    cells = hmm.sparse_transition_matrix()
+    first_copy, repeat_matches, entry = [], set(), None
+    for i, nm in enumerate(names):
+        tail = nm.split("_")[-1]
+        if nm[0] == "M" and tail == "0":
+            first_copy.append(i)
+        if nm[0] == "M" and tail not in ("prefix", "suffix"):
+            repeat_matches.add(i)
+        if nm == "suffix_start_suffix":
+            entry = i
+    cells[(hmm.start_index, entry)] = 0.3
+    for i in first_copy:
+        cells[(hmm.start_index, i)] = 0.7 / len(first_copy)
+    to_end = 0.7 / len(repeat_matches)
+    scale = 1 + to_end
+    for key in list(cells):
+        if key[0] in repeat_matches:
+            cells[key] = cells[key] / scale
+    for i in repeat_matches:
+        cells[(i, hmm.end_index)] = to_end / scale
+    starts = np.zeros(len(names))
+    starts[hmm.start_index] = 1.0
+    ends = np.zeros(len(names))
+    ends[hmm.end_index] = 1.0
+    out = pom.HiddenMarkovModel.from_sparse(cells, [s.distribution for s in hmm.states], starts, ends,
+                                            name="Read Matcher", state_names=names, merge=None)
     out.bake(merge=None)
     return out
 
