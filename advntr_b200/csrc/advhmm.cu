@@ -126,6 +126,14 @@ struct DevBanded {
     const int32_t* fin_src;
     const double* fin_w;
     const int32_t* tb0;           // [m]
+    // fp32 twin (ADVHMM_FP32): float image (112 bytes per column) and the host-evaluated tables
+    // re-evaluated in float arithmetic
+    const unsigned char* image_f;
+    int image_f_bytes, pad1;
+    float logp_empty_f, pad2;
+    const int32_t* tb1_f;
+    const int32_t* tb0_f;
+    const float* fin_w_f;
 };
 
 struct Tile {
@@ -160,6 +168,7 @@ struct advhmm_context {
     bool int_compare = false;    // integer-pipe compares (ADVHMM_ICMP=1); needs all tables <= 0
     bool launch_int_compare = false;   // ... and every model of the current batch qualifies
     int generic_smem_set = 0;
+    int banded_f32_smem_set[kMaxRPL + 1] = {0};
     std::mutex mu;
 };
 
@@ -565,6 +574,204 @@ banded_fill_kernel(const BandedArgs a)
 }
 
 // =============================================================================================
+// fp32 variant of the banded fill kernel (optional mode, ADVHMM_FP32): same schedule and
+// operation order with float tables / float arithmetic.  Image: 112 bytes per column
+//   [0, 48P)    w12[c][12] floats: the ten weights of the fp64 image + 2 pad
+//   [48P, 80P)  e2[sym][c][2] floats        [80P, 112P)  v1[sym][c][2] floats
+// =============================================================================================
+constexpr int kImgFE = 48, kImgFV1 = 80, kImgFBytesPerCol = 112;
+
+__device__ __forceinline__ float4 lds128f(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds64f(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
+template <int SH>
+__device__ __forceinline__ float max3_first_f32(float a0, float a1, float a2, uint32_t& bits)
+{
+    float m;
+    asm("{\n\t"
+        ".reg .pred p1, p2;\n\t"
+        ".reg .f32 t;\n\t"
+        "setp.gt.f32 p1, %3, %2;\n\t"
+        "selp.f32 t, %3, %2, p1;\n\t"
+        "@p1 or.b32 %1, %1, %5;\n\t"
+        "setp.gt.f32 p2, %4, t;\n\t"
+        "selp.f32 %0, %4, t, p2;\n\t"
+        "@p2 or.b32 %1, %1, %6;\n\t"
+        "}"
+        : "=f"(m), "+r"(bits)
+        : "f"(a0), "f"(a1), "f"(a2), "n"(1u << SH), "n"(2u << SH));
+    return m;
+}
+
+template <int RPL>
+__global__ void __launch_bounds__(8 * 32, 2)
+banded_fill_f32_kernel(const BandedArgs a)
+{
+    constexpr int WPB = 8, NW = RPL > 5 ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ float s_fval[WPB][32];
+    const float kNI = -__int_as_float(0x7f800000);
+
+    const Tile tile = a.tiles[blockIdx.x];
+    const DevBanded* __restrict__ M = reinterpret_cast<const DevBanded*>(tile.model);
+    const int P = M->P, NC = M->NC, acc_col = M->acc_col;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)M->image_f_bytes;
+        mbar_expect_tx(&s_bar, bytes);
+#pragma unroll 1
+        for (uint32_t o = 0; o < bytes; o += 65536u)
+            tma_bulk_g2s(smem_raw + o, M->image_f + o, min(65536u, bytes - o), &s_bar);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    mbar_wait(&s_bar, 0);
+    if (warp >= tile.cnt) return;
+    const int item = tile.first + warp;
+    const int q = a.order[item];
+    const size_t slot = (size_t)(item - a.chunk_base);
+    const int n = a.rlen[q];
+    if (n == 0) {
+        if (lane == 0) a.logp[q] = (double)M->logp_empty_f;
+        return;
+    }
+    const int nl = (n + RPL - 1) / RPL;
+    const int ln = (n - 1) / RPL, jn = (n - 1) % RPL;
+    const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
+    uint32_t symbits;
+    {
+        const int bit = 2 * lane * RPL;
+        const int w = bit >> 5, sh = bit & 31;
+        const int last_word = (n + 15) / 16;
+        const uint32_t lo = (w <= last_word) ? pk[w] : 0u;
+        const uint32_t hi = (w + 1 <= last_word) ? pk[w + 1] : 0u;
+        symbits = __funnelshift_r(lo, hi, sh);
+    }
+    uint32_t* tbw_t = a.tbw + slot * a.tbw_stride + (size_t)lane * P * NW - (ptrdiff_t)lane * NW;
+    uint16_t* __restrict__ acc_tb = a.acc_tb + slot * (size_t)a.acc_stride + lane * RPL;
+    float* __restrict__ vfin = reinterpret_cast<float*>(a.vfin + slot * a.vfin_stride);
+    float* vfin_t = vfin - lane;
+    const uint32_t s_base = smem_u32(smem_raw);
+    uint32_t w_t = s_base - (uint32_t)lane * 48u;
+    uint32_t e_t[RPL];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+        e_t[j] = s_base + (uint32_t)kImgFE * P + ((symbits >> (2 * j)) & 3u) * (uint32_t)(8 * P) - (uint32_t)lane * 8u;
+        asm volatile("" : "+r"(e_t[j]));
+    }
+    asm volatile("" : "+l"(tbw_t), "+l"(vfin_t), "+r"(w_t));
+    const uint32_t v1_delta = (uint32_t)(kImgFV1 - kImgFE) * P;
+
+    float cI[RPL], cM[RPL], cD[RPL], acc[RPL];
+    int accarg[RPL];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNI; accarg[j] = 0; }
+    float bI = kNI, bM = kNI, bD = kNI;
+
+    const int steps = NC + nl - 1;
+#pragma unroll 1
+    for (int t = 0; t < steps; ++t) {
+        const float uI0 = __shfl_up_sync(0xffffffffu, cI[RPL - 1], 1);
+        const float uM0 = __shfl_up_sync(0xffffffffu, cM[RPL - 1], 1);
+        const float uD0 = __shfl_up_sync(0xffffffffu, cD[RPL - 1], 1);
+        const int c = t - lane;
+        if (c < 0 || c >= NC || lane >= nl) continue;
+        const uint32_t wa = w_t + (uint32_t)t * 48u;
+        const float4 w0 = lds128f(wa), w1 = lds128f(wa + 16), w2 = lds128f(wa + 32);
+        const float wII = w0.x, wIM = w0.y, wID = w0.z, wMI = w0.w, wMM = w1.x, wMD = w1.y;
+        const float wDI = w1.z, wDM = w1.w, wDD = w2.x, aw = w2.y;
+        const uint32_t cb = (uint32_t)t * 8u;
+        float nM[RPL], nD[RPL], eIr[RPL];
+        uint32_t word[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) word[k] = 0;
+        static_for<0, RPL>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            const float2 e = lds64f(e_t[j] + cb);
+            eIr[j] = e.x;
+            const float oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
+            nM[j] = max3_first_f32<6 * (j % 5) + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
+            nD[j] = max3_first_f32<6 * (j % 5) + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
+        });
+        if (lane == 0) {
+            const float2 f = lds64f(e_t[0] + v1_delta + cb);
+            nM[0] = f.y;
+            eIr[0] = f.x;
+        }
+        if (c == acc_col) {
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
+        }
+        if (aw > kNI) {
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                const float cand = nD[j] + aw;
+                if (cand > acc[j]) { acc[j] = cand; accarg[j] = c; }
+            }
+        }
+        float uI = uI0, uM = uM0, uD = uD0;
+        static_for<0, RPL>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            float vI = max3_first_f32<6 * (j % 5)>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
+            if (j == 0 && lane == 0) vI = eIr[0];
+            uI = vI; uM = nM[j]; uD = nD[j];
+            cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
+        });
+        bI = uI0; bM = uM0; bD = uD0;
+        if (NW == 1) tbw_t[t] = word[0];
+        else reinterpret_cast<uint2*>(tbw_t)[t] = make_uint2(word[0], word[NW - 1]);
+        if (lane == ln) {
+            float fI = cI[0], fM = cM[0], fD = cD[0];
+#pragma unroll
+            for (int j = 1; j < RPL; ++j)
+                if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
+            vfin_t[t] = fI; vfin_t[P + t] = fM; vfin_t[2 * P + t] = fD;
+        }
+    }
+    if (lane < nl) {
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) acc_tb[j] = (uint16_t)accarg[j];
+    }
+    __syncwarp();
+    const int NF = M->NF;
+    int32_t* __restrict__ ftb = a.ftb + slot * 32;
+    for (int f = 0; f < NF; ++f) {
+        const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
+        float best = kNI;
+        int arg = 0x7fffffff;
+        for (int k = k0 + lane; k < k1; k += 32) {
+            const int code = M->fin_src[k];
+            const float sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
+            const float cand = sv + M->fin_w_f[k];
+            if (cand > best) { best = cand; arg = k; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, arg, off);
+            if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+        }
+        if (lane == 0) {
+            s_fval[warp][f] = best;
+            ftb[f] = (best > kNI) ? M->fin_src[arg] : 0;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) a.logp[q] = (double)s_fval[warp][M->end_final];
+}
+
+// =============================================================================================
 // banded fill kernel for long reads / large models (PacBio-like, BASELINE config 3)
 //
 // Same recurrence, tables and traceback encoding as banded_fill_kernel, but
@@ -779,6 +986,7 @@ struct BandedBtArgs {
     int32_t chunk_base;
     int32_t n_items;            // work items in this chunk
     int32_t rpl;                // RPL the fill kernel ran with
+    int32_t fp32;               // fill ran in fp32: use the float-evaluated predecessor tables
     const uint32_t* pk;
     const int64_t* pk_off;
     const int32_t* rlen;
@@ -831,7 +1039,7 @@ __device__ __forceinline__ void banded_walk(const DevBanded* __restrict__ M, con
                 if (c == M->acc_col) c = acc_tb[r - 1];
                 else { sl = kD; c -= 1; }
             } else if (r == 1) {
-                state = M->tb1[sym0 * M->S + s];
+                state = (a.fp32 ? M->tb1_f : M->tb1)[sym0 * M->S + s];
                 r = 0;
             } else if (sl == SLOT_M) { sl = kM; c -= 1; r -= 1; }
             else { sl = kI; r -= 1; }
@@ -839,7 +1047,8 @@ __device__ __forceinline__ void banded_walk(const DevBanded* __restrict__ M, con
     }
     // row 0: silent closure back to the start state
     int guard = M->m + 1;
-    while (state != M->start && state >= 0 && guard-- > 0) { emit(state); state = M->tb0[state]; }
+    const int32_t* __restrict__ tb0 = a.fp32 ? M->tb0_f : M->tb0;
+    while (state != M->start && state >= 0 && guard-- > 0) { emit(state); state = tb0[state]; }
     emit(state);
 }
 
@@ -1153,7 +1362,8 @@ int upload_model(advhmm_model* mod)
     const size_t o_f0 = bb.add(f0);
     // banded tables
     size_t o_image = 0, o_st = 0, o_tb1 = 0, o_acc = 0, o_fs = 0, o_fo = 0, o_fsrc = 0, o_fw = 0;
-    int image_bytes = 0;
+    size_t o_image_f = 0, o_tb1f = 0, o_tb0f = 0, o_fwf = 0;
+    int image_bytes = 0, image_f_bytes = 0;
     if (b.valid) {
         const size_t P = b.NCpad;
         std::vector<unsigned char> image((size_t)kImgBytesPerCol * P, 0);
@@ -1175,6 +1385,23 @@ int upload_model(advhmm_model* mod)
         for (int t = 0; t < 3; ++t) memcpy(st.data() + (size_t)t * b.NC, b.st[t].data(), sizeof(int32_t) * b.NC);
         o_st = bb.add(st); o_tb1 = bb.add(b.tb1); o_acc = bb.add(b.acc_src_col);
         o_fs = bb.add(b.fin_state); o_fo = bb.add(b.fin_off); o_fsrc = bb.add(b.fin_src); o_fw = bb.add(b.fin_w);
+        // fp32 twin
+        const BandedF32& f = mod->cm.f;
+        std::vector<unsigned char> imf((size_t)kImgFBytesPerCol * P, 0);
+        float* w12 = reinterpret_cast<float*>(imf.data());
+        float* e2f = reinterpret_cast<float*>(imf.data() + (size_t)kImgFE * P);
+        float* v1f = reinterpret_cast<float*>(imf.data() + (size_t)kImgFV1 * P);
+        for (size_t c = 0; c < P; ++c) {
+            for (int k = 0; k < 9; ++k) w12[c * 12 + k] = f.w[(size_t)k * P + c];
+            w12[c * 12 + 9] = f.accw[c];
+            for (int x = 0; x < 4; ++x)
+                for (int sl = 0; sl < 2; ++sl) {
+                    e2f[((size_t)x * P + c) * 2 + sl] = f.e[((size_t)sl * 4 + x) * P + c];
+                    v1f[((size_t)x * P + c) * 2 + sl] = f.v1[((size_t)sl * 4 + x) * P + c];
+                }
+        }
+        image_f_bytes = (int)imf.size();
+        o_image_f = bb.add(imf); o_tb1f = bb.add(f.tb1); o_tb0f = bb.add(f.tb0); o_fwf = bb.add(f.fin_w);
     }
     const size_t o_dg = bb.add(nullptr, sizeof(DevGeneric));
     const size_t o_dgf = bb.add(nullptr, sizeof(DevGeneric));
@@ -1224,6 +1451,10 @@ int upload_model(advhmm_model* mod)
         db.acc_src_col = (const int32_t*)P8(o_acc); db.fin_state = (const int32_t*)P8(o_fs);
         db.fin_off = (const int32_t*)P8(o_fo); db.fin_src = (const int32_t*)P8(o_fsrc);
         db.fin_w = (const double*)P8(o_fw); db.tb0 = (const int32_t*)P8(o_tb0);
+        db.image_f = P8(o_image_f); db.image_f_bytes = image_f_bytes;
+        db.logp_empty_f = mod->cm.f.v0[g.end];
+        db.tb1_f = (const int32_t*)P8(o_tb1f); db.tb0_f = (const int32_t*)P8(o_tb0f);
+        db.fin_w_f = (const float*)P8(o_fwf);
         memcpy(bb.bytes.data() + o_db, &db, sizeof db);
     }
     CU_TRY(cudaMemcpyAsync(base, bb.bytes.data(), bb.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1309,6 +1540,30 @@ int launch_banded_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const 
     return ADVHMM_OK;
 }
 
+int launch_banded_f32_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const BandedArgs& args)
+{
+    ProfScope prof(ctx, 0);
+    // the fp32 image is smaller than the fp64 one, so the fp64 size is a safe dynamic-smem request
+#define ADV_CASE(R)                                                                                   \
+    case R:                                                                                           \
+        if (smem > ctx->banded_f32_smem_set[R]) {                                                     \
+            CU_TRY(cudaFuncSetAttribute(banded_fill_f32_kernel<R>,                                    \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
+            ctx->banded_f32_smem_set[R] = smem;                                                       \
+        }                                                                                             \
+        banded_fill_f32_kernel<R><<<grid, 8 * 32, smem, ctx->stream>>>(args);                         \
+        break;
+    switch (rpl) {
+        ADV_CASE(1) ADV_CASE(2) ADV_CASE(3) ADV_CASE(4) ADV_CASE(5)
+        ADV_CASE(6) ADV_CASE(7) ADV_CASE(8) ADV_CASE(9) ADV_CASE(10)
+        default: return set_error(ADVHMM_EINVAL, "unsupported rows-per-lane %d", rpl);
+    }
+#undef ADV_CASE
+    CU_TRY(cudaGetLastError());
+    ctx->launches++;
+    return ADVHMM_OK;
+}
+
 struct OutPtrs {
     double* logp; int32_t* path_len; int64_t* path_off; int32_t* path; int64_t path_cap;
     unsigned long long* cursor;
@@ -1324,7 +1579,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     const int strands = (flags & ADVHMM_BOTH_STRANDS) ? 2 : 1;
     const int n_out = n_reads * strands;
     if (n_out == 0) return ADVHMM_OK;
-    if (flags & ADVHMM_FP32) return set_error(ADVHMM_EUNSUPPORTED, "fp32 mode is not available in this build");
+    const bool fp32 = (flags & ADVHMM_FP32) != 0;
+    if (fp32 && forward) return set_error(ADVHMM_EUNSUPPORTED, "fp32 mode exists for Viterbi only");
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
 
     // ---- plan: packed-read offsets, kernel family of every result read, tiles ----------------
@@ -1373,6 +1629,9 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         }
     }
     ctx->launch_int_compare = ctx->int_compare && all_nonpositive;
+    if (fp32 && (!fam_long.items.empty() || !fam_generic.items.empty()))
+        return set_error(ADVHMM_EUNSUPPORTED, "fp32 mode is implemented for the short-read banded kernel only "
+                                              "(profile-shaped model, reads <= %d bases)", 32 * kMaxRPL);
 
     // generic launch geometry: as many warps per CTA as DP rows fit in shared memory
     int gwarps = kGenericWarpsMax, rows_in_smem = 1;
@@ -1500,6 +1759,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
                                 const uint16_t* acc, size_t acc_stride, const int32_t* ftb) -> int {
         BandedBtArgs ba{};
         ba.tiles = d_tiles; ba.order = d_order; ba.chunk_base = lo; ba.n_items = items; ba.rpl = bt_rpl;
+        ba.fp32 = fp32 ? 1 : 0;
         ba.pk = d_pk; ba.pk_off = d_pk_off; ba.rlen = d_rlen; ba.logp = out.logp;
         ba.tbw = tbw; ba.tbw_stride = tbw_stride; ba.acc_tb = acc; ba.acc_stride = acc_stride; ba.ftb = ftb;
         ba.item_tile = d_item_tile;
@@ -1525,7 +1785,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         fa.acc_tb = reinterpret_cast<uint16_t*>(w + so_acc); fa.acc_stride = 32 * rpl;
         fa.vfin = reinterpret_cast<double*>(w + so_vfin); fa.vfin_stride = 3 * Ps;
         fa.ftb = reinterpret_cast<int32_t*>(w + so_ftb);
-        int rc = launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa);
+        int rc = fp32 ? launch_banded_f32_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa)
+                      : launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa);
         if (rc) return rc;
         if (want_path) {
             rc = launch_backtrack(lo, hi - lo, rpl, fa.tbw, fa.tbw_stride, fa.acc_tb, (size_t)fa.acc_stride, fa.ftb);

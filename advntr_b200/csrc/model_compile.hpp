@@ -80,9 +80,24 @@ struct BandedTables {
     bool nonpositive = false;        // every table entry <= 0: DP values can be ordered as integers
 };
 
+// fp32 twin of the banded tables (ADVHMM_FP32): every table rounded to float once, and the two
+// host-evaluated pieces (row-0 closure, first-row tables) re-evaluated in float arithmetic with
+// the same operation order, so the device fp32 DP equals a float restatement of the reference.
+struct BandedF32 {
+    std::vector<float>   w;          // [9*NCpad]  as BandedTables::w
+    std::vector<float>   accw;       // [NCpad]
+    std::vector<float>   e;          // [2*K*NCpad]
+    std::vector<float>   v1;         // [2*K*NCpad]
+    std::vector<int32_t> tb1;        // [K*S]
+    std::vector<float>   v0;         // [m]  row-0 values in float
+    std::vector<int32_t> tb0;        // [m]
+    std::vector<float>   fin_w;
+};
+
 struct CompiledModel {
     GenericTables g;
     BandedTables b;
+    BandedF32 f;
 };
 
 namespace detail {
@@ -339,10 +354,47 @@ inline void build_banded(const GenericTables& g, BandedTables& b)
 
 }  // namespace detail
 
+namespace detail {
+inline void build_banded_f32(const GenericTables& g, const BandedTables& b, BandedF32& f)
+{
+    const int m = g.m, S = g.S, K = g.K;
+    const size_t P = (size_t)b.NCpad;
+    auto cast = [](const std::vector<double>& v) { return std::vector<float>(v.begin(), v.end()); };
+    f.w = cast(b.w); f.accw = cast(b.accw); f.e = cast(b.e); f.fin_w = cast(b.fin_w);
+    const float ninf = -std::numeric_limits<float>::infinity();
+    f.v0.assign(m, ninf);
+    f.tb0.assign(m, -1);
+    f.v0[g.start] = 0.0f;
+    for (int l = S; l < m; ++l) {
+        if (l == g.start) continue;
+        for (int k = g.in_off[l]; k < g.in_off[l + 1]; ++k) {
+            const int ki = g.in_src[k];
+            if (ki < S) continue;
+            const float cand = f.v0[ki] + (float)g.in_w[k];
+            if (cand > f.v0[l]) { f.v0[l] = cand; f.tb0[l] = ki; }
+        }
+    }
+    f.v1.assign(2 * K * P, ninf);
+    f.tb1.assign((size_t)K * S, -1);
+    for (int l = 0; l < S; ++l)
+        for (int x = 0; x < K; ++x) {
+            float best = ninf; int arg = -1;
+            const float e = (float)g.emis[(size_t)l * K + x];
+            for (int k = g.in_off[l]; k < g.in_off[l + 1]; ++k) {
+                const float cand = (f.v0[g.in_src[k]] + (float)g.in_w[k]) + e;
+                if (cand > best) { best = cand; arg = g.in_src[k]; }
+            }
+            f.v1[((size_t)(b.slot_of[l] == SLOT_I ? 0 : 1) * K + x) * P + b.col_of[l]] = best;
+            f.tb1[(size_t)x * S + l] = arg;
+        }
+}
+}  // namespace detail
+
 inline bool compile_model(const advhmm_model_desc& d, CompiledModel& out, std::string& err)
 {
     if (!detail::build_generic(d, out.g, err)) return false;
     detail::build_banded(out.g, out.b);
+    if (out.b.valid) detail::build_banded_f32(out.g, out.b, out.f);
     return true;
 }
 

@@ -168,20 +168,21 @@ class Context(object):
 
     # -- many loci in one call -----------------------------------------------------------
     def viterbi_multi(self, models, groups, both_strands=False, want_path=True,
-                      force_generic=False, path_cap=None):
+                      force_generic=False, path_cap=None, precision="fp64"):
         """``groups[g]`` = list of uint8 code arrays decoded against ``models[g]``."""
         flat_codes = [c for grp in groups for c in grp]
         goff = np.zeros(len(groups) + 1, dtype=np.int64)
         np.cumsum([len(g) for g in groups], out=goff[1:])
         seqs, off = pack_reads(flat_codes)
-        return self._run(models, goff, seqs, off, both_strands, want_path, force_generic, path_cap)
+        return self._run(models, goff, seqs, off, both_strands, want_path, force_generic, path_cap,
+                         fp32=(precision == "fp32"))
 
-    def _run(self, models, goff, seqs, off, both_strands, want_path, force_generic, path_cap):
+    def _run(self, models, goff, seqs, off, both_strands, want_path, force_generic, path_cap, fp32=False):
         R = len(off) - 1
         strands = 2 if both_strands else 1
         n_out = R * strands
         flags = (WANT_PATH if want_path else 0) | (BOTH_STRANDS if both_strands else 0) | \
-                (FORCE_GENERIC if force_generic else 0)
+                (FORCE_GENERIC if force_generic else 0) | (FP32 if fp32 else 0)
         handles = (C.c_void_p * len(models))(*[m._h for m in models])
         logp = np.empty(n_out, dtype=np.float64)
         plen = np.full(n_out, -1, dtype=np.int32)
@@ -267,11 +268,12 @@ class DeviceModel(object):
 
     def viterbi(self, codes, both_strands=False, want_path=True, precision="fp64",
                 force_generic=False, path_cap=None):
-        if precision != "fp64":
-            raise EngineError(EUNSUPPORTED, "only fp64 is available in this build")
+        if precision not in ("fp64", "fp32"):
+            raise EngineError(EUNSUPPORTED, "precision must be 'fp64' (default, bit-exact) or 'fp32'")
         seqs, off = pack_reads(codes)
         goff = np.array([0, len(codes)], dtype=np.int64)
-        return self.ctx._run([self], goff, seqs, off, both_strands, want_path, force_generic, path_cap)
+        return self.ctx._run([self], goff, seqs, off, both_strands, want_path, force_generic, path_cap,
+                             fp32=(precision == "fp32"))
 
     def log_probability(self, codes):
         seqs, off = pack_reads(codes)

@@ -131,6 +131,90 @@ double oracle_viterbi(const oracle_model* M, const uint8_t* seq, int32_t n,
     return logp;
 }
 
+/* fp32 twin of oracle_viterbi: the same recurrence with every table rounded to float once and
+ * all arithmetic in float (same operation order).  Checker of the engine's optional ADVHMM_FP32
+ * mode; the reference itself has no fp32 path. */
+double oracle_viterbi_f32(const oracle_model* M, const uint8_t* seq, int32_t n,
+                          int32_t* path, int32_t* path_len)
+{
+    const int m = M->n_states, S = M->silent_start, K = M->n_symbols;
+    const int32_t* off = M->in_off;
+    const int32_t* src = M->in_src;
+    const int E = off[m];
+    float* w = (float*)malloc(sizeof(float) * (size_t)(E > 0 ? E : 1));
+    float* em = (float*)malloc(sizeof(float) * (size_t)(S * K > 0 ? S * K : 1));
+    size_t cells = (size_t)(n + 1) * (size_t)m;
+    float* v = (float*)calloc(cells, sizeof(float));
+    int32_t* tbx = (int32_t*)calloc(cells, sizeof(int32_t));
+    int32_t* tby = (int32_t*)calloc(cells, sizeof(int32_t));
+    int i, l, k;
+    for (k = 0; k < E; ++k) w[k] = (float)M->in_logp[k];
+    for (k = 0; k < S * K; ++k) em[k] = (float)M->emis[k];
+    *path_len = -1;
+    for (l = 0; l < m; ++l) v[l] = -INFINITY;
+    v[M->start_index] = 0.0f;
+    for (l = S; l < m; ++l) {
+        if (l == M->start_index) continue;
+        for (k = off[l]; k < off[l + 1]; ++k) {
+            int ki = src[k];
+            if (ki < S || ki >= l) continue;
+            float cand = v[ki] + w[k];
+            if (cand > v[l]) { v[l] = cand; tbx[l] = 0; tby[l] = ki; }
+        }
+    }
+    for (i = 0; i < n; ++i) {
+        const float* prev = v + (size_t)i * m;
+        float* cur = v + (size_t)(i + 1) * m;
+        int32_t* cx = tbx + (size_t)(i + 1) * m;
+        int32_t* cy = tby + (size_t)(i + 1) * m;
+        int sym = seq[i];
+        for (l = 0; l < S; ++l) {
+            float e = em[(size_t)l * K + sym];
+            cur[l] = -INFINITY;
+            for (k = off[l]; k < off[l + 1]; ++k) {
+                float t = prev[src[k]] + w[k];
+                float cand = t + e;
+                if (cand > cur[l]) { cur[l] = cand; cx[l] = i; cy[l] = src[k]; }
+            }
+        }
+        for (l = S; l < m; ++l) {
+            cur[l] = -INFINITY;
+            for (k = off[l]; k < off[l + 1]; ++k) {
+                int ki = src[k];
+                if (ki >= S) continue;
+                float cand = cur[ki] + w[k];
+                if (cand > cur[l]) { cur[l] = cand; cx[l] = i + 1; cy[l] = ki; }
+            }
+        }
+        for (l = S; l < m; ++l) {
+            for (k = off[l]; k < off[l + 1]; ++k) {
+                int ki = src[k];
+                if (ki < S || ki >= l) continue;
+                float cand = cur[ki] + w[k];
+                if (cand > cur[l]) { cur[l] = cand; cx[l] = i + 1; cy[l] = ki; }
+            }
+        }
+    }
+    float logp = v[(size_t)n * m + M->end_index];
+    int end = M->end_index;
+    if (logp != -INFINITY) {
+        int px = n, py = end, len = 0;
+        while (px != 0 || py != M->start_index) {
+            path[len++] = py;
+            size_t c = (size_t)px * m + py;
+            px = tbx[c];
+            py = tby[c];
+        }
+        path[len++] = py;
+        for (i = 0; i < len / 2; ++i) {
+            int32_t t = path[i]; path[i] = path[len - 1 - i]; path[len - 1 - i] = t;
+        }
+        *path_len = len;
+    }
+    free(v); free(tbx); free(tby); free(w); free(em);
+    return (double)logp;
+}
+
 /* utils.pyx:72-90 (pair_lse) */
 static double pair_lse(double x, double y)
 {
@@ -212,6 +296,23 @@ void oracle_viterbi_batch(const oracle_model* M, const uint8_t* seqs, const int6
         int32_t* p = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n + M->n_states));
         int32_t len;
         logp[r] = oracle_viterbi(M, seqs + seq_off[r], n, p, &len);
+        path_len[r] = len;
+        if (paths && len > 0)
+            memcpy(paths + (size_t)r * path_stride, p,
+                   sizeof(int32_t) * (size_t)(len < path_stride ? len : path_stride));
+        free(p);
+    }
+}
+
+void oracle_viterbi_f32_batch(const oracle_model* M, const uint8_t* seqs, const int64_t* seq_off,
+                              int32_t n_reads, double* logp, int32_t* path_len,
+                              int32_t* paths, int64_t path_stride)
+{
+    for (int r = 0; r < n_reads; ++r) {
+        int32_t n = (int32_t)(seq_off[r + 1] - seq_off[r]);
+        int32_t* p = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n + M->n_states));
+        int32_t len;
+        logp[r] = oracle_viterbi_f32(M, seqs + seq_off[r], n, p, &len);
         path_len[r] = len;
         if (paths && len > 0)
             memcpy(paths + (size_t)r * path_stride, p,

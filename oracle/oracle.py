@@ -39,6 +39,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         _lib.oracle_viterbi_batch.restype = None
+        _lib.oracle_viterbi_f32_batch.restype = None
         _lib.oracle_log_probability_batch.restype = None
     return _lib
 
@@ -66,15 +67,17 @@ class OracleModel(object):
                 if len(codes) and off[-1] else np.zeros(1, dtype=np.uint8))
         return np.ascontiguousarray(flat), off
 
-    def viterbi(self, codes):
-        """codes: list of uint8 arrays.  Returns (logp[R], [path arrays or None])."""
+    def viterbi(self, codes, fp32=False):
+        """codes: list of uint8 arrays.  Returns (logp[R], [path arrays or None]).  ``fp32``: the
+        float restatement (checker of the engine's optional fp32 mode)."""
         flat, off = self._pack(codes)
         R = len(codes)
         stride = int((off[1:] - off[:-1]).max() if R else 0) + self.n_states
         logp = np.empty(R, dtype=np.float64)
         plen = np.empty(R, dtype=np.int32)
         paths = np.empty((R, stride), dtype=np.int32)
-        lib().oracle_viterbi_batch(C.byref(self.c), C.c_void_p(flat.ctypes.data),
+        fn = lib().oracle_viterbi_f32_batch if fp32 else lib().oracle_viterbi_batch
+        fn(C.byref(self.c), C.c_void_p(flat.ctypes.data),
                                    C.c_void_p(off.ctypes.data), C.c_int32(R),
                                    C.c_void_p(logp.ctypes.data), C.c_void_p(plen.ctypes.data),
                                    C.c_void_p(paths.ctypes.data), C.c_int64(stride))

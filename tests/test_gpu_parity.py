@@ -196,3 +196,32 @@ def test_drop_in_surface(ctx):
         pom.HiddenMarkovModel("x").viterbi("A")
     res = model.viterbi_batch(g.reads[:30])
     assert same_bits(res.logp, g.logp[:30])
+
+
+def test_fp32_mode(ctx, golden):
+    """Optional fp32 mode (ADVHMM_FP32): the device result equals a float restatement of the
+    reference recurrence bit for bit; against the fp64 reference the stated tolerance is
+    |dlogp| <= 2e-5 * |logp| + 2e-5, and repeat counts agree on >= 97 % of the reads (ties
+    that fp64 separates can fall differently in fp32)."""
+    from advntr_b200 import engine, path_utils
+    codes = golden.codes()
+    dm = engine.DeviceModel(ctx, golden.baked)
+    res = dm.viterbi(codes, precision="fp32")
+    dm.close()
+    lp32, paths32 = oracle.OracleModel(golden.baked).viterbi(codes, fp32=True)
+    assert same_bits(res.logp, lp32)
+    assert_paths_equal([res.path(i) for i in range(len(res))], paths32, golden.name + " fp32")
+    finite = np.isfinite(golden.logp)
+    assert np.all(np.abs(res.logp[finite] - golden.logp[finite]) <= 2e-5 * np.abs(golden.logp[finite]) + 2e-5)
+
+    class _S(object):
+        def __init__(self, name):
+            self.name = name
+    same = total = 0
+    for i in range(len(codes)):
+        if golden.ru_count[i] < 0:
+            continue
+        vp = [(int(k), _S(golden.names[k])) for k in res.path(i)]
+        same += int(path_utils.get_number_of_repeats_in_vpath(vp) == golden.ru_count[i])
+        total += 1
+    assert same >= 0.97 * total, "RU-count concordance %d/%d" % (same, total)

@@ -22,7 +22,7 @@ d_total = torch.zeros(1, dtype=torch.int64, device="cuda")
 def step(flags):
     engine._check(lib.advhmm_viterbi_multi(ctx._h, handles, len(models), goff.ctypes.data, d_seqs.data_ptr(), off.ctypes.data, R,
         flags, d_logp.data_ptr(), d_plen.data_ptr(), d_poff.data_ptr(), d_path.data_ptr(), cap, d_total.data_ptr()))
-F = engine.WANT_PATH | engine.DEVICE_BUFFERS
+F = engine.WANT_PATH | engine.DEVICE_BUFFERS | (engine.FP32 if os.environ.get('ADVHMM_PRECISION') == 'fp32' else 0)
 for _ in range(2): step(F)
 torch.cuda.synchronize()
 ref = d_logp.clone()
@@ -33,6 +33,6 @@ for _ in range(steps): step(F)
 e1.record(stream); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 fm, fn, bm, bn = ctx.profile_read()
-print("WPB=%s ICMP=%s loci=%d reads=%d: step %.2f ms (%.2f Mreads/s, %.0f GCUPS) fill %.2f ms/step (%d launches) backtrack %.2f ms/step | logp checksum %r" % (
-    os.environ.get("ADVHMM_WPB", "8"), os.environ.get("ADVHMM_ICMP", "0"), n_loci, R, ms, R / ms / 1e3, wl["cells"] / ms / 1e6,
+print("prec=%s WPB=%s ICMP=%s loci=%d reads=%d: step %.2f ms (%.2f Mreads/s, %.0f GCUPS) fill %.2f ms/step (%d launches) backtrack %.2f ms/step | logp checksum %r" % (
+    os.environ.get("ADVHMM_PRECISION", "fp64"), os.environ.get("ADVHMM_WPB", "8"), os.environ.get("ADVHMM_ICMP", "0"), n_loci, R, ms, R / ms / 1e3, wl["cells"] / ms / 1e6,
     fm / steps, fn // steps, bm / steps, float(d_logp.sum().item())))
