@@ -111,6 +111,7 @@ struct DevGeneric {
     const int32_t* tb0;
     const int32_t* lvl_off;
     const int32_t* lvl_state;
+    const uint8_t* classes;       // [m] state class bytes for the on-device path reducers
 };
 
 struct DevBanded {
@@ -134,6 +135,7 @@ struct DevBanded {
     const int32_t* tb1_f;
     const int32_t* tb0_f;
     const float* fin_w_f;
+    const uint8_t* classes;       // [m]
 };
 
 struct Tile {
@@ -179,6 +181,7 @@ struct advhmm_model {
     DevGeneric* d_generic = nullptr;
     DevGeneric* d_generic_fwd = nullptr;   // same tables, row 0 closed with pair_lse (forward)
     DevBanded* d_banded = nullptr;
+    uint8_t* d_classes = nullptr;  // [n_states] state class bytes (zero until set_state_classes)
     int banded_smem = 0;         // image bytes (0: not banded / does not fit)
     advhmm_model_info info{};
 };
@@ -978,6 +981,53 @@ banded_long_kernel(const LongArgs a)
 }
 
 // =============================================================================================
+// on-device path reducers (hmm_utils.py:155-286): what adVNTR derives from a state path, computed
+// while the backtrack walks it (from the end of the read to its start)
+// =============================================================================================
+struct PathReducer {
+    const uint8_t* __restrict__ cls;
+    const uint32_t* __restrict__ pk;
+    int n, rem = 0;                      // read length; emitting states seen so far (from the end)
+    int n_match = 0, repeat_bp = 0, left_bp = 0, right_bp = 0, left_hits = 0, right_hits = 0;
+    int starts = 0, ends = 0, first_start = -1, last_start = -1, first_end = -1, last_end = -1;
+
+    __device__ __forceinline__ PathReducer(const uint8_t* c, const uint32_t* p, int len) : cls(c), pk(p), n(len) {}
+
+    __device__ __forceinline__ void visit(int state)
+    {
+        const int c = cls[state];
+        const int kind = c & 7, part = (c >> 3) & 3;
+        if (kind == 1 || kind == 2) {                       // M or I: emits read base n - rem - 1
+            if (kind == 1) {
+                ++n_match;
+                if (part == 1 || part == 2) {
+                    const int hit = packed_sym(pk, n - rem - 1) == ((c >> 5) & 3);
+                    if (part == 1) left_hits += hit; else right_hits += hit;
+                }
+            }
+            if (part == 1) ++left_bp; else if (part == 2) ++right_bp; else ++repeat_bp;
+            ++rem;
+        } else if (kind == 4) {                             // unit_start: >= 3 bases still to come
+            if (rem >= 3) { ++starts; const int bp = n - rem; if (last_start < 0) last_start = bp; first_start = bp; }
+        } else if (kind == 5) {                             // unit_end: >= 3 bases consumed
+            const int bp = n - rem;
+            if (bp >= 3) { ++ends; if (last_end < 0) last_end = bp; first_end = bp; }
+        }
+    }
+    __device__ __forceinline__ void store(advhmm_read_summary* out) const
+    {
+        int delta = 0;
+        if (first_start >= 0 && first_end >= 0 && first_end < first_start && last_start > last_end) delta = 1;
+        advhmm_read_summary s;
+        s.repeats = max(starts, ends) + delta;
+        s.n_match = n_match; s.repeat_bp = repeat_bp; s.left_bp = left_bp; s.right_bp = right_bp;
+        s.left_hits = left_hits; s.right_hits = right_hits;
+        s.unit_starts_ends = starts | (ends << 16);
+        *out = s;
+    }
+};
+
+// =============================================================================================
 // banded backtrack kernel: one thread per read
 // =============================================================================================
 struct BandedBtArgs {
@@ -999,9 +1049,10 @@ struct BandedBtArgs {
     const int32_t* item_tile;   // tile index of every work item
     int32_t* path_len;          // [n_out]
     int64_t* path_off;          // [n_out]
-    int32_t* path;
+    int32_t* path;              // NULL: no paths wanted (summaries only)
     int64_t path_cap;
     unsigned long long* cursor; // total path entries
+    advhmm_read_summary* summaries;   // NULL or [n_out]
 };
 
 template <typename Emit>
@@ -1069,8 +1120,24 @@ __global__ void __launch_bounds__(128) banded_backtrack_kernel(const BandedBtArg
         possible = a.logp[q] > kNegInf;
         if (possible) {
             if (n > 0) sym0 = packed_sym(a.pk + a.pk_off[q], 0);
-            banded_walk(M, a, slot, n, sym0, [&](int) { ++len; });
+            if (a.summaries) {
+                // the walk starts at the model's end state and finishes at its start state; like
+                // the reference's vpath[1:-1] both are silent "other" states and reduce to nothing
+                PathReducer red(M->classes, a.pk + a.pk_off[q], n);
+                banded_walk(M, a, slot, n, sym0, [&](int s) { ++len; red.visit(s); });
+                red.store(a.summaries + q);
+            } else {
+                banded_walk(M, a, slot, n, sym0, [&](int) { ++len; });
+            }
+        } else if (a.summaries) {
+            advhmm_read_summary z = {};
+            z.repeats = -1;
+            a.summaries[q] = z;
         }
+    }
+    if (!a.path) {                       // summaries only
+        if (active) { a.path_len[q] = possible ? len : -1; a.path_off[q] = 0; }
+        return;
     }
     // warp-aggregated allocation of output space
     const unsigned lane = threadIdx.x & 31;
@@ -1249,6 +1316,9 @@ struct GenericBtArgs {
     int32_t* path;
     int64_t path_cap;
     unsigned long long* cursor;
+    const uint32_t* pk;
+    const int64_t* pk_off;
+    advhmm_read_summary* summaries;
 };
 
 template <typename Emit>
@@ -1284,7 +1354,23 @@ __global__ void __launch_bounds__(128) generic_backtrack_kernel(const GenericBtA
         tb = a.tb + (size_t)i * a.tb_stride;
         end = a.end_state[q];
         possible = a.logp[q] > kNegInf && end >= 0;
-        if (possible) generic_walk(G, tb, n, end, [&](int) { ++len; });
+        if (possible) {
+            if (a.summaries) {
+                PathReducer red(G->classes, a.pk + a.pk_off[q], n);
+                generic_walk(G, tb, n, end, [&](int s) { ++len; red.visit(s); });
+                red.store(a.summaries + q);
+            } else {
+                generic_walk(G, tb, n, end, [&](int) { ++len; });
+            }
+        } else if (a.summaries) {
+            advhmm_read_summary z = {};
+            z.repeats = -1;
+            a.summaries[q] = z;
+        }
+    }
+    if (!a.path) {
+        if (active) { a.path_len[q] = possible ? len : -1; a.path_off[q] = 0; }
+        return;
     }
     const unsigned lane = threadIdx.x & 31;
     int incl = len;
@@ -1403,6 +1489,8 @@ int upload_model(advhmm_model* mod)
         image_f_bytes = (int)imf.size();
         o_image_f = bb.add(imf); o_tb1f = bb.add(f.tb1); o_tb0f = bb.add(f.tb0); o_fwf = bb.add(f.fin_w);
     }
+    const std::vector<uint8_t> zero_classes((size_t)g.m, 0);
+    const size_t o_cls = bb.add(zero_classes);
     const size_t o_dg = bb.add(nullptr, sizeof(DevGeneric));
     const size_t o_dgf = bb.add(nullptr, sizeof(DevGeneric));
     const size_t o_db = bb.add(nullptr, sizeof(DevBanded));
@@ -1437,6 +1525,8 @@ int upload_model(advhmm_model* mod)
     dg.in_w = (const double*)P8(o_in_w); dg.emis = (const double*)P8(o_emis);
     dg.v0 = (const double*)P8(o_v0); dg.tb0 = (const int32_t*)P8(o_tb0);
     dg.lvl_off = (const int32_t*)P8(o_lvl_off); dg.lvl_state = (const int32_t*)P8(o_lvl_state);
+    dg.classes = (const uint8_t*)P8(o_cls);
+    mod->d_classes = (uint8_t*)P8(o_cls);
     memcpy(bb.bytes.data() + o_dg, &dg, sizeof dg);
     DevGeneric dgf = dg;
     dgf.v0 = (const double*)P8(o_f0);
@@ -1455,6 +1545,7 @@ int upload_model(advhmm_model* mod)
         db.logp_empty_f = mod->cm.f.v0[g.end];
         db.tb1_f = (const int32_t*)P8(o_tb1f); db.tb0_f = (const int32_t*)P8(o_tb0f);
         db.fin_w_f = (const float*)P8(o_fwf);
+        db.classes = (const uint8_t*)P8(o_cls);
         memcpy(bb.bytes.data() + o_db, &db, sizeof db);
     }
     CU_TRY(cudaMemcpyAsync(base, bb.bytes.data(), bb.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1567,6 +1658,7 @@ int launch_banded_f32_chunk(advhmm_context* ctx, int rpl, int grid, int smem, co
 struct OutPtrs {
     double* logp; int32_t* path_len; int64_t* path_off; int32_t* path; int64_t path_cap;
     unsigned long long* cursor;
+    advhmm_read_summary* summaries;   // NULL unless ADVHMM_WANT_SUMMARY
 };
 
 // Runs the whole batch on the context's stream.  All pointers in `out` and d_seqs are device
@@ -1576,6 +1668,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
               const OutPtrs& out, bool forward, int32_t* d_bad)
 {
     const bool want_path = (flags & ADVHMM_WANT_PATH) && !forward;
+    const bool want_walk = want_path || (out.summaries && !forward);   // backtrack kernel needed
     const int strands = (flags & ADVHMM_BOTH_STRANDS) ? 2 : 1;
     const int n_out = n_reads * strands;
     if (n_out == 0) return ADVHMM_OK;
@@ -1718,7 +1811,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     const size_t l_acc = stripes_max * 32 * kLongRPL;
     const size_t l_per_item = n_long ? l_tbw_words * 4 + 6 * Pl * 8 + l_acc * 2 + 32 * 4 : 0;
     const size_t gm = (size_t)pl.max_m_generic;
-    const size_t g_tb_per = (want_path && n_generic) ? (size_t)std::max(fam_generic.max_len, 1) * gm * sizeof(uint16_t) : 0;
+    const size_t g_tb_per = (want_walk && n_generic) ? (size_t)std::max(fam_generic.max_len, 1) * gm * sizeof(uint16_t) : 0;
     const size_t g_rows_per = (n_generic && !rows_in_smem) ? 2 * gm * sizeof(double) : 0;
     const size_t g_per_item = n_generic ? g_tb_per + g_rows_per + 8 : 0;
     auto chunk_of = [&](size_t per_item, int n_items, size_t floor_items) {
@@ -1763,8 +1856,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         ba.pk = d_pk; ba.pk_off = d_pk_off; ba.rlen = d_rlen; ba.logp = out.logp;
         ba.tbw = tbw; ba.tbw_stride = tbw_stride; ba.acc_tb = acc; ba.acc_stride = acc_stride; ba.ftb = ftb;
         ba.item_tile = d_item_tile;
-        ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = out.path;
-        ba.path_cap = out.path_cap; ba.cursor = out.cursor;
+        ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = want_path ? out.path : nullptr;
+        ba.path_cap = out.path_cap; ba.cursor = out.cursor; ba.summaries = out.summaries;
         {
             ProfScope prof(ctx, 1);
             banded_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
@@ -1788,7 +1881,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         int rc = fp32 ? launch_banded_f32_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa)
                       : launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa);
         if (rc) return rc;
-        if (want_path) {
+        if (want_walk) {
             rc = launch_backtrack(lo, hi - lo, rpl, fa.tbw, fa.tbw_stride, fa.acc_tb, (size_t)fa.acc_stride, fa.ftb);
             if (rc) return rc;
         }
@@ -1813,7 +1906,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         }
         CU_TRY(cudaGetLastError());
         ctx->launches++;
-        if (want_path) {
+        if (want_walk) {
             int rc = launch_backtrack(lo, hi - lo, kLongRPL, la.tbw, la.tbw_stride, la.acc_tb, la.acc_stride, la.ftb);
             if (rc) return rc;
         }
@@ -1843,13 +1936,14 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
             else generic_fill_kernel<false><<<tile1 - tile0, gwarps * 32, smem, ctx->stream>>>(ga);
             CU_TRY(cudaGetLastError());
             ctx->launches++;
-            if (want_path) {
+            if (want_walk) {
                 GenericBtArgs ba{};
                 ba.tiles = d_tiles; ba.order = d_order; ba.chunk_base = lo; ba.n_items = items;
                 ba.rlen = d_rlen; ba.logp = out.logp; ba.end_state = ga.end_state;
                 ba.tb = ga.tb; ba.tb_stride = ga.tb_stride; ba.item_tile = d_item_tile;
-                ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = out.path;
+                ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = want_path ? out.path : nullptr;
                 ba.path_cap = out.path_cap; ba.cursor = out.cursor;
+                ba.pk = d_pk; ba.pk_off = d_pk_off; ba.summaries = out.summaries;
                 generic_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
                 CU_TRY(cudaGetLastError());
                 ctx->launches++;
@@ -1864,14 +1958,16 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
 int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, const int64_t* group_off,
              const uint8_t* seqs, const int64_t* seq_off, int n_reads, uint32_t flags, bool forward,
              double* logp, int32_t* path_len, int64_t* path_off, int32_t* path, int64_t path_cap,
-             int64_t* path_total)
+             int64_t* path_total, advhmm_read_summary* summaries = nullptr)
 {
     if (!ctx || ctx->device < 0) return set_error(ADVHMM_ECUDA, "this context has no CUDA device (host-only analysis context)");
     if (n_reads < 0 || !seq_off || (n_reads > 0 && (!logp || !models || n_models <= 0)))
         return set_error(ADVHMM_EINVAL, "null or negative argument");
     const bool want_path = (flags & ADVHMM_WANT_PATH) && !forward;
+    const bool want_sum = (flags & ADVHMM_WANT_SUMMARY) && !forward;
     if (want_path && (!path_len || !path_off || !path_total || (path_cap > 0 && !path)))
         return set_error(ADVHMM_EINVAL, "ADVHMM_WANT_PATH needs path_len, path_off, path and path_total");
+    if (want_sum && !summaries) return set_error(ADVHMM_EINVAL, "ADVHMM_WANT_SUMMARY needs a summaries buffer");
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU_TRY(cudaSetDevice(ctx->device));
     const int strands = (flags & ADVHMM_BOTH_STRANDS) ? 2 : 1;
@@ -1887,14 +1983,17 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
     // outputs: logp | path_len | path_off | cursor | bad
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t o_logp = 0, o_plen = al((size_t)n_out * 8), o_poff = o_plen + al((size_t)n_out * 4);
-    const size_t o_cursor = o_poff + al((size_t)n_out * 8), o_bad = o_cursor + 256, out_bytes = o_bad + 256;
+    const size_t o_cursor = o_poff + al((size_t)n_out * 8), o_bad = o_cursor + 256;
+    const size_t o_sum = o_bad + 256;
+    const size_t out_bytes = o_sum + (want_sum ? al((size_t)n_out * sizeof(advhmm_read_summary)) : 0);
     CU_TRY(ctx->d_out.ensure(out_bytes));
     unsigned char* d = ctx->d_out.as<unsigned char>();
     int64_t cap = want_path ? path_cap : 0;
     if (want_path) CU_TRY(ctx->d_paths.ensure((size_t)std::max<int64_t>(cap, 1) * sizeof(int32_t)));
     OutPtrs op{reinterpret_cast<double*>(d + o_logp), reinterpret_cast<int32_t*>(d + o_plen),
                reinterpret_cast<int64_t*>(d + o_poff), ctx->d_paths.as<int32_t>(), cap,
-               reinterpret_cast<unsigned long long*>(d + o_cursor)};
+               reinterpret_cast<unsigned long long*>(d + o_cursor),
+               want_sum ? reinterpret_cast<advhmm_read_summary*>(d + o_sum) : nullptr};
     int32_t* d_bad = reinterpret_cast<int32_t*>(d + o_bad);
     CU_TRY(cudaMemsetAsync(d_bad, 0x7f, sizeof(int32_t), ctx->stream));
     int rc = run_batch(ctx, models, n_models, group_off, ctx->d_seqs.as<uint8_t>(), seq_off, n_reads, flags, op,
@@ -1909,6 +2008,10 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
     memcpy(&bad, h + o_bad, sizeof bad);
     if (bad != 0x7f7f7f7f) return set_error(ADVHMM_ESYMBOL, "read %d contains a symbol code outside the model alphabet", bad);
     memcpy(logp, h + o_logp, (size_t)n_out * 8);
+    if (want_sum) {
+        memcpy(summaries, h + o_sum, (size_t)n_out * sizeof(advhmm_read_summary));
+        if (path_len && !want_path) memcpy(path_len, h + o_plen, (size_t)n_out * 4);
+    }
     if (want_path) {
         memcpy(path_len, h + o_plen, (size_t)n_out * 4);
         memcpy(path_off, h + o_poff, (size_t)n_out * 8);
@@ -2149,14 +2252,38 @@ int advhmm_viterbi_multi(advhmm_context* ctx, advhmm_model* const* models, int32
                          int32_t n_reads, uint32_t flags, double* logp, int32_t* path_len,
                          int64_t* path_off, int32_t* path, int64_t path_cap, int64_t* path_total)
 {
+    return advhmm_viterbi_multi_summary(ctx, models, n_models, group_off, seqs, seq_off, n_reads,
+                                        flags & ~ADVHMM_WANT_SUMMARY, logp, path_len, path_off, path, path_cap,
+                                        path_total, nullptr);
+}
+
+int advhmm_model_set_state_classes(advhmm_model* model, const uint8_t* classes)
+{
+    if (!model || !classes) return set_error(ADVHMM_EINVAL, "null argument");
+    if (!model->ctx || model->ctx->device < 0) return ADVHMM_OK;      // host-only context: nothing to upload
+    std::lock_guard<std::mutex> lock(model->ctx->mu);
+    CU_TRY(cudaSetDevice(model->ctx->device));
+    CU_TRY(cudaMemcpyAsync(model->d_classes, classes, (size_t)model->cm.g.m, cudaMemcpyHostToDevice, model->ctx->stream));
+    CU_TRY(cudaStreamSynchronize(model->ctx->stream));
+    return ADVHMM_OK;
+}
+
+int advhmm_viterbi_multi_summary(advhmm_context* ctx, advhmm_model* const* models, int32_t n_models,
+                                 const int64_t* group_off, const uint8_t* seqs, const int64_t* seq_off,
+                                 int32_t n_reads, uint32_t flags, double* logp, int32_t* path_len,
+                                 int64_t* path_off, int32_t* path, int64_t path_cap, int64_t* path_total,
+                                 advhmm_read_summary* summaries)
+{
     if (!ctx || !models || !group_off || n_models <= 0) return set_error(ADVHMM_EINVAL, "null argument");
     if (!(flags & ADVHMM_DEVICE_BUFFERS))
         return run_host(ctx, models, n_models, group_off, seqs, seq_off, n_reads, flags, false,
-                        logp, path_len, path_off, path, path_cap, path_total);
+                        logp, path_len, path_off, path, path_cap, path_total, summaries);
     // device-resident buffers: asynchronous on the context's stream, nothing is copied back
     if (ctx->device < 0) return set_error(ADVHMM_ECUDA, "this context has no CUDA device");
     const bool want_path = flags & ADVHMM_WANT_PATH;
-    if (!seq_off || !logp || (want_path && (!path_len || !path_off || !path_total)))
+    const bool want_sum = (flags & ADVHMM_WANT_SUMMARY) != 0;
+    if (!seq_off || !logp || (want_path && (!path_len || !path_off || !path_total)) ||
+        (want_sum && (!summaries || !path_len || !path_off)))
         return set_error(ADVHMM_EINVAL, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU_TRY(cudaSetDevice(ctx->device));
@@ -2164,7 +2291,7 @@ int advhmm_viterbi_multi(advhmm_context* ctx, advhmm_model* const* models, int32
     int32_t* d_bad = ctx->d_flags.as<int32_t>();
     CU_TRY(cudaMemsetAsync(d_bad, 0x7f, sizeof(int32_t), ctx->stream));
     OutPtrs op{logp, path_len, path_off, path, want_path ? path_cap : 0,
-               reinterpret_cast<unsigned long long*>(path_total)};
+               reinterpret_cast<unsigned long long*>(path_total), want_sum ? summaries : nullptr};
     return run_batch(ctx, models, n_models, group_off, seqs, seq_off, n_reads, flags & ~ADVHMM_DEVICE_BUFFERS, op,
                      false, d_bad);
 }

@@ -15,7 +15,9 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libadvhmm.so")
 
 OK, EINVAL, ECUDA, ENOMEM, ESYMBOL, ECAPACITY, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-WANT_PATH, BOTH_STRANDS, FP32, FORCE_GENERIC, DEVICE_BUFFERS = 0x1, 0x2, 0x4, 0x8, 0x100
+WANT_PATH, BOTH_STRANDS, FP32, FORCE_GENERIC, WANT_SUMMARY, DEVICE_BUFFERS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x100
+SUMMARY_DTYPE = np.dtype([(n, np.int32) for n in ("repeats", "n_match", "repeat_bp", "left_bp", "right_bp",
+                                                   "left_hits", "right_hits", "unit_starts_ends")])
 KIND_GENERIC, KIND_BANDED = 0, 1
 
 EXPORTS = (
@@ -24,6 +26,7 @@ EXPORTS = (
     "advhmm_context_profile_read", "advhmm_fp64_add_peak",
     "advhmm_model_create", "advhmm_model_destroy", "advhmm_model_info_get",
     "advhmm_viterbi_batch", "advhmm_log_probability_batch", "advhmm_viterbi_multi",
+    "advhmm_viterbi_multi_summary", "advhmm_model_set_state_classes",
     "advhmm_last_error", "advhmm_abi_version", "advhmm_encode_acgt",
 )
 
@@ -80,6 +83,8 @@ def load_library():
         lib.advhmm_viterbi_batch.argtypes = [vp, vp, vp, i32, u32, vp, vp, vp, vp, i64, vp]
         lib.advhmm_log_probability_batch.argtypes = [vp, vp, vp, i32, u32, vp]
         lib.advhmm_viterbi_multi.argtypes = [vp, vp, i32, vp, vp, vp, i32, u32, vp, vp, vp, vp, i64, vp]
+        lib.advhmm_viterbi_multi_summary.argtypes = [vp, vp, i32, vp, vp, vp, i32, u32, vp, vp, vp, vp, i64, vp, vp]
+        lib.advhmm_model_set_state_classes.argtypes = [vp, vp]
         lib.advhmm_last_error.restype = C.c_char_p
         lib.advhmm_abi_version.restype = C.c_int
         lib.advhmm_encode_acgt.argtypes = [C.c_char_p, i64, vp]
@@ -168,21 +173,24 @@ class Context(object):
 
     # -- many loci in one call -----------------------------------------------------------
     def viterbi_multi(self, models, groups, both_strands=False, want_path=True,
-                      force_generic=False, path_cap=None, precision="fp64"):
+                      force_generic=False, path_cap=None, precision="fp64", want_summary=False):
         """``groups[g]`` = list of uint8 code arrays decoded against ``models[g]``."""
         flat_codes = [c for grp in groups for c in grp]
         goff = np.zeros(len(groups) + 1, dtype=np.int64)
         np.cumsum([len(g) for g in groups], out=goff[1:])
         seqs, off = pack_reads(flat_codes)
         return self._run(models, goff, seqs, off, both_strands, want_path, force_generic, path_cap,
-                         fp32=(precision == "fp32"))
+                         fp32=(precision == "fp32"), want_summary=want_summary)
 
-    def _run(self, models, goff, seqs, off, both_strands, want_path, force_generic, path_cap, fp32=False):
+    def _run(self, models, goff, seqs, off, both_strands, want_path, force_generic, path_cap, fp32=False,
+             want_summary=False):
         R = len(off) - 1
         strands = 2 if both_strands else 1
         n_out = R * strands
         flags = (WANT_PATH if want_path else 0) | (BOTH_STRANDS if both_strands else 0) | \
-                (FORCE_GENERIC if force_generic else 0) | (FP32 if fp32 else 0)
+                (FORCE_GENERIC if force_generic else 0) | (FP32 if fp32 else 0) | \
+                (WANT_SUMMARY if want_summary else 0)
+        summ = np.zeros(n_out if want_summary else 0, dtype=SUMMARY_DTYPE)
         handles = (C.c_void_p * len(models))(*[m._h for m in models])
         logp = np.empty(n_out, dtype=np.float64)
         plen = np.full(n_out, -1, dtype=np.int32)
@@ -195,25 +203,34 @@ class Context(object):
         cap = int(path_cap or 0)
         while True:
             path = np.empty(max(cap, 1), dtype=np.int32)
-            rc = self._lib.advhmm_viterbi_multi(
+            rc = self._lib.advhmm_viterbi_multi_summary(
                 self._h, handles, len(models), goff.ctypes.data, seqs.ctypes.data, off.ctypes.data, R,
                 flags, logp.ctypes.data, plen.ctypes.data, poff.ctypes.data, path.ctypes.data, cap,
-                C.byref(total))
+                C.byref(total), summ.ctypes.data if want_summary else None)
             if rc == ECAPACITY and total.value > cap:
                 cap = int(total.value) + 16
                 continue
             _check(rc)
             break
-        return ViterbiResult(logp, plen, poff, path[:max(int(total.value), 0)])
+        return ViterbiResult(logp, plen, poff, path[:max(int(total.value), 0)], summ if want_summary else None)
 
 
 class ViterbiResult(object):
     """Arrays returned by one batched decode; ``path(i)`` is read i's state-index path."""
 
-    __slots__ = ("logp", "path_len", "path_off", "paths")
+    __slots__ = ("logp", "path_len", "path_off", "paths", "summaries")
 
-    def __init__(self, logp, path_len, path_off, paths):
+    def __init__(self, logp, path_len, path_off, paths, summaries=None):
         self.logp, self.path_len, self.path_off, self.paths = logp, path_len, path_off, paths
+        self.summaries = summaries      # SUMMARY_DTYPE records (on-device path reducers) or None
+
+    def flank_match_rate(self, i, accuracy_filter=False):
+        """get_flanking_regions_matching_rate (hmm_utils.py:209-268) from the device summary."""
+        s = self.summaries[i]
+        empty = 0.00001 if accuracy_filter else 1
+        right = float(s["right_hits"]) / s["right_bp"] if s["right_bp"] else empty
+        left = float(s["left_hits"]) / s["left_bp"] if s["left_bp"] else empty
+        return min(right, left)
 
     def __len__(self):
         return len(self.logp)
@@ -266,14 +283,21 @@ class DeviceModel(object):
             self._lib.advhmm_model_destroy(self._h)
         self._h = None
 
+    def set_state_classes(self, classes):
+        """Per-state class bytes for the on-device path reducers (see include/advhmm.h)."""
+        cls = np.ascontiguousarray(classes, dtype=np.uint8)
+        if len(cls) != self.n_states:
+            raise ValueError("need one class byte per state")
+        _check(self._lib.advhmm_model_set_state_classes(self._h, cls.ctypes.data))
+
     def viterbi(self, codes, both_strands=False, want_path=True, precision="fp64",
-                force_generic=False, path_cap=None):
+                force_generic=False, path_cap=None, want_summary=False):
         if precision not in ("fp64", "fp32"):
             raise EngineError(EUNSUPPORTED, "precision must be 'fp64' (default, bit-exact) or 'fp32'")
         seqs, off = pack_reads(codes)
         goff = np.array([0, len(codes)], dtype=np.int64)
         return self.ctx._run([self], goff, seqs, off, both_strands, want_path, force_generic, path_cap,
-                             fp32=(precision == "fp32"))
+                             fp32=(precision == "fp32"), want_summary=want_summary)
 
     def log_probability(self, codes):
         seqs, off = pack_reads(codes)

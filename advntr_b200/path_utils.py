@@ -210,3 +210,32 @@ def frameshift_mutations(selected, pattern_length):
             if abs(lengths[unit] - pattern_length) <= 2:
                 mutations[label] = mutations.get(label, 0) + 1
     return mutations, repeat_bp
+
+
+def state_classes(names, emis=None):
+    """Class byte of every state for the on-device reducers (``include/advhmm.h``): what the
+    functions above parse out of the state names, plus the base a flank match state expects
+    (the symbol its emission row favours)."""
+    import numpy as np
+    out = np.zeros(len(names), dtype=np.uint8)
+    for i, n in enumerate(names):
+        if n.startswith("M"):
+            kind = 1
+        elif n.startswith("I"):
+            kind = 2
+        elif n.startswith("D"):
+            kind = 3
+        elif n.startswith("unit_start"):
+            kind = 4
+        elif n.startswith("unit_end"):
+            kind = 5
+        else:
+            kind = 0
+        part = 0
+        if kind in (1, 2, 3):
+            part = 1 if n.endswith("suffix") else 2 if n.endswith("prefix") else 3
+        base = 0
+        if kind == 1 and part in (1, 2) and emis is not None:
+            base = int(np.argmax(emis[i]))
+        out[i] = kind | (part << 3) | (base << 5)
+    return out

@@ -455,8 +455,10 @@ class HiddenMarkovModel(object):
         if self._baked is None or self.d == 0:
             raise ValueError("must bake model before using Viterbi algorithm")
         if self._engine is None:
-            from . import engine
+            from . import engine, path_utils
             self._engine = engine.DeviceModel.from_baked(self._baked)
+            self._engine.set_state_classes(path_utils.state_classes([s.name for s in self.states],
+                                                                    self._baked["emis"]))
         return self._engine
 
     def _encode(self, sequence):
@@ -488,13 +490,15 @@ class HiddenMarkovModel(object):
         st = self.states
         return logp, [(int(i), st[i]) for i in res.path(0)]
 
-    def viterbi_batch(self, sequences, both_strands=False, want_path=True, precision="fp64"):
-        """Decode every read of a locus in ONE device call (the batched call site)."""
+    def viterbi_batch(self, sequences, both_strands=False, want_path=True, precision="fp64",
+                      want_summary=False):
+        """Decode every read of a locus in ONE device call (the batched call site).
+        ``want_summary``: also return the on-device path reducers (``result.summaries``)."""
         if self.d == 0:
             raise ValueError("must bake model before using Viterbi algorithm")
         codes = [self._encode(s) for s in sequences]
-        return self._device_model().viterbi(codes, both_strands=both_strands,
-                                            want_path=want_path, precision=precision)
+        return self._device_model().viterbi(codes, both_strands=both_strands, want_path=want_path,
+                                            precision=precision, want_summary=want_summary)
 
     def log_probability(self, sequence, check_input=True):
         """Forward log-likelihood (hmm.pyx:1258-1313)."""

@@ -43,6 +43,7 @@ extern "C" {
 #define ADVHMM_BOTH_STRANDS   0x2u  /* also decode the reverse complement of every read;   */
                                     /* results are interleaved: 2*i forward, 2*i+1 revcomp */
 #define ADVHMM_FP32           0x4u  /* fp32 DP arithmetic (tolerance documented in DESIGN) */
+#define ADVHMM_WANT_SUMMARY   0x10u /* fill advhmm_read_summary per read on the device         */
 #define ADVHMM_FORCE_GENERIC  0x8u  /* use the generic CSR kernel even if the model is     */
                                     /* banded (testing / cross-checking)                   */
 
@@ -154,6 +155,36 @@ int advhmm_viterbi_multi(advhmm_context* ctx,
                          uint32_t flags,
                          double* logp, int32_t* path_len, int64_t* path_off,
                          int32_t* path, int64_t path_cap, int64_t* path_total);
+
+/* ---- on-device path reducers ----------------------------------------------------------------
+ * What adVNTR derives from a Viterbi path (hmm_utils.py:155-286), computed by the backtrack
+ * kernel so that the host does not have to walk state names read by read.  The state classes
+ * are what those functions parse out of the state NAMES; the host sets them once per model:
+ *   bits 0-2 kind: 0 other, 1 match (name starts with 'M'), 2 insert ('I'), 3 delete ('D'),
+ *                  4 unit_start*, 5 unit_end*
+ *   bits 3-4 part: 1 name ends with 'suffix', 2 ends with 'prefix', 3 repeat unit, 0 n/a
+ *   bits 5-6      the flank base (0..3) a suffix/prefix match state expects
+ * repeats = get_number_of_repeats_in_vpath; n_match = get_number_of_matches_in_vpath;
+ * repeat_bp = get_number_of_repeat_bp_matches_in_vpath; left_bp / right_bp =
+ * get_left/right_flanking_region_size_in_vpath; left_hits / right_hits = the numerators of
+ * get_flanking_regions_matching_rate.  repeats = -1 for an impossible read. */
+typedef struct advhmm_read_summary {
+    int32_t repeats, n_match, repeat_bp, left_bp, right_bp, left_hits, right_hits, unit_starts_ends;
+} advhmm_read_summary;
+
+int advhmm_model_set_state_classes(advhmm_model* model, const uint8_t* classes /* [n_states] */);
+
+/* advhmm_viterbi_multi plus summaries[n_out] (host or device buffer like the others).  With
+ * ADVHMM_WANT_SUMMARY and without ADVHMM_WANT_PATH no path is written (path may be NULL), only
+ * path_len is filled. */
+int advhmm_viterbi_multi_summary(advhmm_context* ctx,
+                                 advhmm_model* const* models, int32_t n_models,
+                                 const int64_t* group_off,
+                                 const uint8_t* seqs, const int64_t* seq_off, int32_t n_reads,
+                                 uint32_t flags,
+                                 double* logp, int32_t* path_len, int64_t* path_off,
+                                 int32_t* path, int64_t path_cap, int64_t* path_total,
+                                 advhmm_read_summary* summaries);
 
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* advhmm_last_error(void);

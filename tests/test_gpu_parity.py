@@ -225,3 +225,27 @@ def test_fp32_mode(ctx, golden):
         same += int(path_utils.get_number_of_repeats_in_vpath(vp) == golden.ru_count[i])
         total += 1
     assert same >= 0.97 * total, "RU-count concordance %d/%d" % (same, total)
+
+
+@pytest.mark.parametrize("force_generic", [False, True], ids=["banded", "generic"])
+def test_on_device_path_reducers(ctx, golden, force_generic):
+    """Summaries computed by the backtrack kernel equal the reference's path consumers
+    (golden `consumers` = values of the reference's own hmm_utils functions)."""
+    from advntr_b200 import engine, path_utils
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", golden.name + ".npz"))
+    want = z["consumers"]
+    dm = engine.DeviceModel(ctx, golden.baked)
+    dm.set_state_classes(path_utils.state_classes(golden.names, golden.baked["emis"]))
+    res = dm.viterbi(golden.codes(), want_summary=True, force_generic=force_generic)
+    only = dm.viterbi(golden.codes(), want_summary=True, want_path=False, force_generic=force_generic)
+    dm.close()
+    assert np.array_equal(res.summaries, only.summaries) and np.array_equal(res.path_len, only.path_len)
+    for i, read in enumerate(golden.reads):
+        s = res.summaries[i]
+        if golden.ru_count[i] < 0:
+            assert s["repeats"] == -1
+            continue
+        assert s["repeats"] == golden.ru_count[i]
+        assert [s["n_match"], s["repeat_bp"], s["left_bp"], s["right_bp"]] == list(want[i, :4])
+        if read:
+            assert res.flank_match_rate(i) == want[i, 4]
