@@ -249,3 +249,38 @@ def test_on_device_path_reducers(ctx, golden, force_generic):
         assert [s["n_match"], s["repeat_bp"], s["left_bp"], s["right_bp"]] == list(want[i, :4])
         if read:
             assert res.flank_match_rate(i) == want[i, 4]
+
+
+@pytest.mark.parametrize("max_len", [1, 20, 33, 70, 100, 129, 150, 161, 200, 225, 257, 290, 320])
+def test_every_rows_per_lane_variant(ctx, golden_config1, max_len):
+    """The banded kernel is instantiated per rows-per-lane (ceil(longest read / 32) = 1..10);
+    each variant, with lengths that are and are not multiples of it, against the oracle."""
+    from advntr_b200 import synth
+    g = golden_config1
+    loc = synth.config1_locus()
+    rng = random.Random(max_len)
+    seq = loc.sequence
+    lens = sorted(set([max_len, max(1, max_len - 1), max(1, max_len - 7), max(1, max_len // 2), 1]))
+    reads = []
+    for L in lens:
+        for _ in range(3):
+            s = rng.randrange(0, len(seq) - L + 1)
+            reads.append(synth.sequencing_errors(rng, seq[s:s + L + 4], 0.02, 0.01, 0.01)[:L])
+    reads = [r for r in reads if r]
+    codes = [oracle.encode(r) for r in reads]
+    lp, paths = oracle.OracleModel(g.baked).viterbi(codes)
+    _, res = _decode(ctx, g.baked, codes)
+    assert same_bits(res.logp, lp)
+    assert_paths_equal([res.path(i) for i in range(len(res))], paths)
+
+
+def test_empty_batch_and_all_empty_reads(ctx, golden_config1):
+    from advntr_b200 import engine
+    g = golden_config1
+    dm = engine.DeviceModel(ctx, g.baked)
+    res = dm.viterbi([])
+    assert len(res) == 0
+    res = dm.viterbi([np.zeros(0, dtype=np.uint8)] * 3, both_strands=True)
+    assert len(res) == 6 and np.all(res.logp == g.logp[1])
+    assert all(np.array_equal(res.path(i), g.path(1)) for i in range(6))
+    dm.close()
