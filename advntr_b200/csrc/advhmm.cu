@@ -4,6 +4,10 @@
 // (/root/reference/pomegranate/hmm.pyx:1970-2136, 1371-1484) for batches of reads.
 // See DESIGN.md for the data layout and the roofline of each kernel.
 //
+// Files: engine_types.cuh (handles, device descriptors), kernels_common.cuh (TMA / mbarrier /
+// shuffle helpers, pack kernel), kernels_banded.cuh, kernels_generic.cuh, model_compile.hpp
+// (host-side graph analysis), this file (model upload, batch planning, launches, C-ABI).
+//
 // Kernels (all hand-written, no tensor cores -- this is max-plus DP, not a contraction):
 //   pack_reads_kernel        byte codes -> 2-bit packed reads (+ reverse complement, validation)
 //   banded_fill_kernel<RPL>  profile-shaped models: one warp per read, lanes own blocks of RPL
@@ -11,1388 +15,21 @@
 //                            column per lane, 3 shuffles per step); model tables staged into
 //                            shared memory with one TMA bulk copy per CTA; 6-bit traceback per
 //                            (position, column) packed into one word per lane and step.
-//   banded_backtrack_kernel  device backtrack to the state path (one thread per read)
-//   generic_fill_kernel      any baked model: row-synchronous CSR kernel, silent states by level
+//   banded_fill_f32_kernel   the same schedule in float (optional ADVHMM_FP32 mode)
+//   banded_long_kernel       long reads / models larger than shared memory: 256-position
+//                            stripes, carry through HBM, tables via the read-only path
+//   banded_backtrack_kernel  device backtrack to the state path + on-device path reducers
+//   generic_fill_kernel<FWD> any baked model: row-synchronous CSR kernel, silent states by level;
+//                            FWD = log_probability (sum-product with the reference's pair_lse)
 //   generic_backtrack_kernel
-//   generic_forward_kernel   log_probability (sum-product with the reference's pair_lse)
 //
 // Exactness: every DP value is produced by the same IEEE-754 double operations in the same
 // order as the reference ((v + t) + e per edge, strict '>' in candidate order), so paths and
 // log-probabilities are bit-identical; see model_compile.hpp for why the banded schedule may
 // skip / reorder the candidates it does.
-#include <cuda_runtime.h>
+#include "kernels_generic.cuh"
 
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <memory>
-#include <mutex>
-#include <new>
-#include <string>
-#include <type_traits>
-#include <utility>
-#include <vector>
-
-#include "model_compile.hpp"
-
-using namespace advhmm;
-
-// =============================================================================================
-// error plumbing
-// =============================================================================================
 namespace {
-
-thread_local std::string g_last_error;
-
-int set_error(int code, const char* fmt, ...)
-{
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    g_last_error = buf;
-    return code;
-}
-
-#define CU_TRY(expr)                                                                          \
-    do {                                                                                      \
-        cudaError_t e__ = (expr);                                                             \
-        if (e__ != cudaSuccess)                                                               \
-            return set_error(e__ == cudaErrorMemoryAllocation ? ADVHMM_ENOMEM : ADVHMM_ECUDA, \
-                             "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),         \
-                             __FILE__, __LINE__);                                             \
-    } while (0)
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, want = bytes); }
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct PinnedBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-// =============================================================================================
-// device-side model descriptors
-// =============================================================================================
-struct DevGeneric {
-    int m, S, K, start, end, finite, n_levels, max_in_degree;
-    const int32_t* in_off;
-    const int32_t* in_src;
-    const double* in_w;
-    const double* emis;
-    const double* v0;
-    const int32_t* tb0;
-    const int32_t* lvl_off;
-    const int32_t* lvl_state;
-    const uint8_t* classes;       // [m] state class bytes for the on-device path reducers
-};
-
-struct DevBanded {
-    int NC, P, S, m, NF, end_final, acc_col, n_acc;
-    int start, end, image_bytes, pad0;
-    double logp_empty;            // v0[end]: the answer for an empty read
-    const unsigned char* image;   // smem image, see kImg* (208 bytes per column)
-    const int32_t* st;            // [3*NC] slot -> state
-    const int32_t* tb1;           // [4*S]
-    const int32_t* acc_src_col;   // [n_acc]
-    const int32_t* fin_state;     // [NF]
-    const int32_t* fin_off;       // [NF+1]
-    const int32_t* fin_src;
-    const double* fin_w;
-    const int32_t* tb0;           // [m]
-    // fp32 twin (ADVHMM_FP32): float image (112 bytes per column) and the host-evaluated tables
-    // re-evaluated in float arithmetic
-    const unsigned char* image_f;
-    int image_f_bytes, pad1;
-    float logp_empty_f, pad2;
-    const int32_t* tb1_f;
-    const int32_t* tb0_f;
-    const float* fin_w_f;
-    const uint8_t* classes;       // [m]
-};
-
-struct Tile {
-    const void* model;   // DevBanded* or DevGeneric*
-    int32_t first;       // first index into order[]
-    int32_t cnt;         // reads in this tile (<= warps per block)
-};
-
-constexpr int kMaxRPL = 10;             // read positions per lane: reads up to 320 bases on the banded path
-constexpr int kBandedWarpsMax = 16;     // reads per CTA (banded): run-time choice, see ctx->banded_warps
-constexpr int kGenericWarpsMax = 8;
-
-}  // namespace
-
-struct advhmm_context {
-    int device = -1;             // < 0: host-only context (model analysis without a GPU)
-    cudaStream_t stream = nullptr;
-    bool owns_stream = false;
-    int sm_count = 0;
-    size_t smem_optin = 0;
-    int64_t launches = 0;
-    size_t workspace_budget = 0;
-    DevBuf d_seqs, d_seq_off, d_pk, d_meta, d_work, d_out, d_paths, d_flags;
-    PinnedBuf h_meta, h_out;
-    cudaEvent_t meta_done = nullptr;
-    // optional per-kernel timing (bench.py roofline): event pairs around every fill launch
-    bool profile = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];   // [0] banded fill, [1] backtrack
-    size_t prof_used[2] = {0, 0};
-    int banded_smem_set[kMaxRPL + 4] = {0};   // dynamic-smem opt-in already applied per kernel variant
-    int banded_warps = 8;        // reads per CTA of the banded kernel
-    bool int_compare = false;    // integer-pipe compares (ADVHMM_ICMP=1); needs all tables <= 0
-    bool launch_int_compare = false;   // ... and every model of the current batch qualifies
-    int generic_smem_set = 0;
-    int banded_f32_smem_set[kMaxRPL + 1] = {0};
-    std::mutex mu;
-};
-
-struct advhmm_model {
-    advhmm_context* ctx = nullptr;
-    CompiledModel cm;
-    DevBuf blob;                 // all device tables of this model
-    DevGeneric* d_generic = nullptr;
-    DevGeneric* d_generic_fwd = nullptr;   // same tables, row 0 closed with pair_lse (forward)
-    DevBanded* d_banded = nullptr;
-    uint8_t* d_classes = nullptr;  // [n_states] state class bytes (zero until set_state_classes)
-    int banded_smem = 0;         // image bytes (0: not banded / does not fit)
-    advhmm_model_info info{};
-};
-
-// =============================================================================================
-// small device helpers
-// =============================================================================================
-namespace {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-{
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-
-__device__ __forceinline__ double shfl_up_f64(double v, int delta)
-{
-    int lo = __double2loint(v), hi = __double2hiint(v);
-    lo = __shfl_up_sync(0xffffffffu, lo, delta);
-    hi = __shfl_up_sync(0xffffffffu, hi, delta);
-    return __hiloint2double(hi, lo);
-}
-__device__ __forceinline__ double shfl_xor_f64(double v, int mask)
-{
-    int lo = __double2loint(v), hi = __double2hiint(v);
-    lo = __shfl_xor_sync(0xffffffffu, lo, mask);
-    hi = __shfl_xor_sync(0xffffffffu, hi, mask);
-    return __hiloint2double(hi, lo);
-}
-
-// symbol i of a 2-bit packed read
-__device__ __forceinline__ int packed_sym(const uint32_t* __restrict__ pk, int i)
-{
-    return (pk[i >> 4] >> ((i & 15) * 2)) & 3;
-}
-
-// lexicographic (max value, min index) warp all-reduce; result in every lane
-__device__ __forceinline__ void warp_argmax_first(double& v, int& idx)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        double ov = shfl_xor_f64(v, off);
-        int oi = __shfl_xor_sync(0xffffffffu, idx, off);
-        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-    }
-}
-
-// =============================================================================================
-// pack kernel: one CTA (32 threads) per result read
-// =============================================================================================
-struct PackArgs {
-    const uint8_t* seqs;
-    const int64_t* seq_off;     // [n_reads+1]
-    const int64_t* pk_off;      // [n_out] word offsets
-    uint32_t* pk;
-    int32_t* rlen;              // [n_out]
-    int32_t* bad;               // [1]: first read index with a code >= n_symbols (atomicMin)
-    int n_out, strands, n_symbols;
-};
-
-__global__ void __launch_bounds__(32) pack_reads_kernel(PackArgs a)
-{
-    const int q = blockIdx.x;
-    if (q >= a.n_out) return;
-    const int r = q / a.strands;
-    const bool rc = (a.strands == 2) && (q & 1);
-    const int64_t s0 = a.seq_off[r];
-    const int n = (int)(a.seq_off[r + 1] - s0);
-    const uint8_t* __restrict__ s = a.seqs + s0;
-    uint32_t* __restrict__ out = a.pk + a.pk_off[q];
-    const int words = (n + 15) / 16 + 1;
-    if (threadIdx.x == 0) a.rlen[q] = n;
-    bool bad = false;
-    for (int w = threadIdx.x; w < words; w += 32) {
-        uint32_t word = 0;
-        const int base = w * 16;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int p = base + k;
-            if (p < n) {
-                int code = rc ? s[n - 1 - p] : s[p];
-                if (code >= a.n_symbols) { bad = true; code = 0; }
-                if (rc) code = 3 - code;          // A<->T, C<->G under codes A,C,G,T = 0..3
-                word |= (uint32_t)(code & 3) << (2 * k);
-            }
-        }
-        out[w] = word;
-    }
-    if (bad) atomicMin(a.bad, r);
-}
-
-// =============================================================================================
-// banded fill kernel
-// =============================================================================================
-struct BandedArgs {
-    const Tile* tiles;
-    const int32_t* order;       // result-read id of every work item
-    int32_t chunk_base;         // first work item of this chunk (workspace slot = item - chunk_base)
-    const uint32_t* pk;
-    const int64_t* pk_off;
-    const int32_t* rlen;
-    double* logp;               // [n_out]
-    uint32_t* tbw;              // traceback words, per slot 32 * Pmax * (RPL > 5 ? 2 : 1) words
-    size_t tbw_stride;          // 32-bit words per slot
-    uint16_t* acc_tb;           // collector choice (source column) per (slot, position)
-    int acc_stride;             // entries per slot (32 * RPL)
-    double* vfin;               // last-row values, per slot 3 * Pmax
-    size_t vfin_stride;
-    int32_t* ftb;               // final-state choices, per slot 32
-};
-
-// shared-memory image of a banded model (byte offsets from the start of dynamic smem), P = NCpad:
-//   [0, 80P)          w10[c][10] : wII wIM wID | wMI wMM wMD | wDI wDM wDD | accw      (doubles)
-//   [80P, 144P)       e2[sym][c][2] : emission log-prob of the I and M slot           (doubles)
-//   [144P, 208P)      v1[sym][c][2] : first-row values of the I and M slot            (doubles)
-// One 16-byte row per (sym, c) means a lane fetches both emissions with one LDS.128, and all ten
-// weights of a column with five LDS.128 off a single address register (80-byte stride: the
-// quarter-warp's eight 16-byte accesses fall into disjoint bank groups).
-constexpr int kImgW = 0, kImgE = 80, kImgV1 = 144, kImgBytesPerCol = 208;
-
-__device__ __forceinline__ double2 lds128(uint32_t addr)
-{
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
-}
-
-// First strict maximum of three candidates in candidate order (hmm.pyx:2039 `if cand > best`).
-// Two traceback bits: bit0 = (a1 > a0), bit1 = (a2 > max(a0, a1));  source = bit1 ? 2 : bit0.
-template <int J, int N, typename F>
-__device__ __forceinline__ void static_for(F&& f)
-{
-    if constexpr (J < N) {
-        f(std::integral_constant<int, J>{});
-        static_for<J + 1, N>(f);
-    }
-}
-
-template <int SH, bool ICMP>
-__device__ __forceinline__ double max3_first(double a0, double a1, double a2, uint32_t& bits)
-{
-    double m;
-    if (ICMP) {
-        // All DP values are <= 0 (sums of log-probabilities; checked when the model is compiled),
-        // so a > b  <=>  bits(a) < bits(b) as unsigned 64-bit integers (+0.0 is the largest value
-        // and the smallest pattern, -inf the smallest value and the largest non-NaN pattern).
-        // The compares then run on the integer pipe and leave the fp64 pipe to the adds.
-        asm("{\n\t"
-            ".reg .pred p1, p2;\n\t"
-            ".reg .b64 t, x0, x1, x2;\n\t"
-            "mov.b64 x0, %2;\n\t"
-            "mov.b64 x1, %3;\n\t"
-            "mov.b64 x2, %4;\n\t"
-            "setp.lt.u64 p1, x1, x0;\n\t"
-            "selp.b64 t, x1, x0, p1;\n\t"
-            "@p1 or.b32 %1, %1, %5;\n\t"
-            "setp.lt.u64 p2, x2, t;\n\t"
-            "selp.b64 t, x2, t, p2;\n\t"
-            "@p2 or.b32 %1, %1, %6;\n\t"
-            "mov.b64 %0, t;\n\t"
-            "}"
-            : "=d"(m), "+r"(bits)
-            : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
-    } else {
-        // written in PTX so that each compare costs one DSETP, one 64-bit select and one predicated OR
-        asm("{\n\t"
-            ".reg .pred p1, p2;\n\t"
-            ".reg .f64 t;\n\t"
-            "setp.gt.f64 p1, %3, %2;\n\t"
-            "selp.f64 t, %3, %2, p1;\n\t"
-            "@p1 or.b32 %1, %1, %5;\n\t"
-            "setp.gt.f64 p2, %4, t;\n\t"
-            "selp.f64 %0, %4, t, p2;\n\t"
-            "@p2 or.b32 %1, %1, %6;\n\t"
-            "}"
-            : "=d"(m), "+r"(bits)
-            : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
-    }
-    return m;
-}
-
-// ALIGNED: the read length is a multiple of RPL, so the last read position is the last row of a
-// lane and its values can be stored from fixed registers.
-template <int RPL, bool ALIGNED, bool ICMP>
-__device__ __forceinline__ void banded_sweep(const int NC, const int P, const int nl, const int ln, const int jn,
-                                             const int lane, const uint32_t s_base, const uint32_t symbits,
-                                             const int acc_col, uint32_t* __restrict__ tbw,
-                                             uint16_t* __restrict__ acc_tb, double* __restrict__ vfin)
-{
-    constexpr int NW = RPL > 5 ? 2 : 1;
-    uint32_t eaddr[RPL];                           // smem address of e2[sym_j][0]
-#pragma unroll
-    for (int j = 0; j < RPL; ++j)
-        eaddr[j] = s_base + (uint32_t)kImgE * P + ((symbits >> (2 * j)) & 3u) * (uint32_t)(16 * P);
-    const uint32_t v1_delta = (uint32_t)(kImgV1 - kImgE) * P;
-
-    double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
-    int accarg[RPL];
-#pragma unroll
-    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; accarg[j] = 0; }
-    double bI = kNegInf, bM = kNegInf, bD = kNegInf;   // row above my block, previous column
-    const bool store_last = ALIGNED && lane == ln;
-    // lane-skewed views: index them with the step t (column c = t - lane).  The empty asm keeps
-    // ptxas from re-deriving these addresses inside the loop.
-    uint32_t* tbw_t = tbw - (ptrdiff_t)lane * NW;
-    double* vfin_t = vfin - lane;
-    uint32_t w_t = s_base - (uint32_t)lane * 80u;       // + 80 t  -> w10[c]
-    uint32_t e_t[RPL];                                  // + 16 t  -> e2[sym_j][c]
-#pragma unroll
-    for (int j = 0; j < RPL; ++j) { e_t[j] = eaddr[j] - (uint32_t)lane * 16u; asm volatile("" : "+r"(e_t[j])); }
-    asm volatile("" : "+l"(tbw_t), "+l"(vfin_t), "+r"(w_t));
-
-    const int steps = NC + nl - 1;
-#pragma unroll 1
-    for (int t = 0; t < steps; ++t) {
-        // the row above my block at column c was finished by lane-1 in the previous step
-        const double uI0 = shfl_up_f64(cI[RPL - 1], 1);
-        const double uM0 = shfl_up_f64(cM[RPL - 1], 1);
-        const double uD0 = shfl_up_f64(cD[RPL - 1], 1);
-        const int c = t - lane;
-        if (c < 0 || c >= NC || lane >= nl) continue;
-
-        const uint32_t wa = w_t + (uint32_t)t * 80u;
-        const double2 w01 = lds128(wa), w23 = lds128(wa + 16), w45 = lds128(wa + 32);
-        const double2 w67 = lds128(wa + 48), w89 = lds128(wa + 64);
-        const double wII = w01.x, wIM = w01.y, wID = w23.x, wMI = w23.y, wMM = w45.x, wMD = w45.y;
-        const double wDI = w67.x, wDM = w67.y, wDD = w89.x, aw = w89.y;
-        const uint32_t cb = (uint32_t)t * 16u;
-
-        // M and D slots depend only on values of the previous column / previous step
-        double nM[RPL], nD[RPL], eIr[RPL];
-        uint32_t word[NW];
-#pragma unroll
-        for (int k = 0; k < NW; ++k) word[k] = 0;
-        static_for<0, RPL>([&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            const double2 e = lds128(e_t[j] + cb);             // {eI, eM}
-            eIr[j] = e.x;
-            const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-            nM[j] = max3_first<6 * (j % 5) + 2, ICMP>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
-            nD[j] = max3_first<6 * (j % 5) + 4, ICMP>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
-        });
-        if (lane == 0) {                                       // first read position: from row 0
-            const double2 f = lds128(e_t[0] + v1_delta + cb);
-            nM[0] = f.y;
-            eIr[0] = f.x;                                      // (carries vI of row 1, see below)
-        }
-        // collector (end_repeating_pattern_match): D of its column is the best unit_end so far.
-        // Both cases are rare per lane (1 and `copies` columns of NC), hence real branches.
-        if (c == acc_col) {
-#pragma unroll
-            for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
-        }
-        if (aw > kNegInf) {                                    // a unit_end column
-#pragma unroll
-            for (int j = 0; j < RPL; ++j) {
-                const double cand = nD[j] + aw;
-                if (cand > acc[j]) { acc[j] = cand; accarg[j] = c; }
-            }
-        }
-        // I slots chain down the rows of this column
-        double uI = uI0, uM = uM0, uD = uD0;
-        static_for<0, RPL>([&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            double vI = max3_first<6 * (j % 5), ICMP>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
-            if (j == 0 && lane == 0) vI = eIr[0];
-            uI = vI; uM = nM[j]; uD = nD[j];
-            cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
-        });
-        bI = uI0; bM = uM0; bD = uD0;
-        if (NW == 1) tbw_t[t] = word[0];
-        else reinterpret_cast<uint2*>(tbw_t)[t] = make_uint2(word[0], word[NW - 1]);
-        if (ALIGNED) {
-            if (store_last) { vfin_t[t] = cI[RPL - 1]; vfin_t[P + t] = cM[RPL - 1]; vfin_t[2 * P + t] = cD[RPL - 1]; }
-        } else if (lane == ln) {
-            double fI = cI[0], fM = cM[0], fD = cD[0];
-#pragma unroll
-            for (int j = 1; j < RPL; ++j)
-                if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
-            vfin_t[t] = fI; vfin_t[P + t] = fM; vfin_t[2 * P + t] = fD;
-        }
-    }
-    // which unit_end fed the collector, per read position (read by the backtrack only)
-    if (lane < nl) {
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) acc_tb[j] = (uint16_t)accarg[j];
-    }
-}
-
-template <int RPL, int WPB, bool ICMP>
-__global__ void __launch_bounds__(WPB * 32, 2)
-banded_fill_kernel(const BandedArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ double s_fval[WPB][32];
-
-    const Tile tile = a.tiles[blockIdx.x];
-    const DevBanded* __restrict__ M = reinterpret_cast<const DevBanded*>(tile.model);
-    const int P = M->P, NC = M->NC;
-
-    // ---- stage the model tables: one elected thread issues TMA bulk copies -----------------
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)M->image_bytes;
-        mbar_expect_tx(&s_bar, bytes);
-#pragma unroll 1
-        for (uint32_t o = 0; o < bytes; o += 65536u)
-            tma_bulk_g2s(smem_raw + o, M->image + o, min(65536u, bytes - o), &s_bar);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    mbar_wait(&s_bar, 0);
-    if (warp >= tile.cnt) return;
-
-    const int item = tile.first + warp;
-    const int q = a.order[item];
-    const size_t slot = (size_t)(item - a.chunk_base);
-    const int n = a.rlen[q];
-    if (n == 0) {
-        if (lane == 0) a.logp[q] = M->logp_empty;
-        return;
-    }
-    const int nl = (n + RPL - 1) / RPL;                 // lanes in use
-    const int ln = (n - 1) / RPL, jn = (n - 1) % RPL;   // owner of the last read position
-
-    // ---- my RPL symbols (2 bits each) ------------------------------------------------------
-    const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
-    uint32_t symbits;
-    {
-        const int bit = 2 * lane * RPL;
-        const int w = bit >> 5, sh = bit & 31;
-        const int last_word = (n + 15) / 16;            // allocation has (n+15)/16 + 1 words
-        const uint32_t lo = (w <= last_word) ? pk[w] : 0u;
-        const uint32_t hi = (w + 1 <= last_word) ? pk[w + 1] : 0u;
-        symbits = __funnelshift_r(lo, hi, sh);
-    }
-    constexpr int NW = RPL > 5 ? 2 : 1;
-    uint32_t* __restrict__ tbw = a.tbw + slot * a.tbw_stride + (size_t)lane * P * NW;
-    uint16_t* __restrict__ acc_tb = a.acc_tb + slot * (size_t)a.acc_stride + lane * RPL;
-    double* __restrict__ vfin = a.vfin + slot * a.vfin_stride;
-    const uint32_t s_base = smem_u32(smem_raw);
-    if (jn == RPL - 1)
-        banded_sweep<RPL, true, ICMP>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
-    else
-        banded_sweep<RPL, false, ICMP>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
-    __syncwarp();
-
-    // ---- final-only silent states on the last row (hub reductions across the warp) ---------
-    const int NF = M->NF;
-    int32_t* __restrict__ ftb = a.ftb + slot * 32;
-    for (int f = 0; f < NF; ++f) {
-        const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
-        double best = kNegInf;
-        int arg = 0x7fffffff;
-        for (int k = k0 + lane; k < k1; k += 32) {
-            const int code = M->fin_src[k];
-            const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
-            const double cand = sv + M->fin_w[k];
-            if (cand > best) { best = cand; arg = k; }
-        }
-        warp_argmax_first(best, arg);
-        if (lane == 0) {
-            s_fval[warp][f] = best;
-            ftb[f] = (best > kNegInf) ? M->fin_src[arg] : 0;
-        }
-        __syncwarp();
-    }
-    if (lane == 0) a.logp[q] = s_fval[warp][M->end_final];
-}
-
-// =============================================================================================
-// fp32 variant of the banded fill kernel (optional mode, ADVHMM_FP32): same schedule and
-// operation order with float tables / float arithmetic.  Image: 112 bytes per column
-//   [0, 48P)    w12[c][12] floats: the ten weights of the fp64 image + 2 pad
-//   [48P, 80P)  e2[sym][c][2] floats        [80P, 112P)  v1[sym][c][2] floats
-// =============================================================================================
-constexpr int kImgFE = 48, kImgFV1 = 80, kImgFBytesPerCol = 112;
-
-__device__ __forceinline__ float4 lds128f(uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float2 lds64f(uint32_t addr)
-{
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
-
-template <int SH>
-__device__ __forceinline__ float max3_first_f32(float a0, float a1, float a2, uint32_t& bits)
-{
-    float m;
-    asm("{\n\t"
-        ".reg .pred p1, p2;\n\t"
-        ".reg .f32 t;\n\t"
-        "setp.gt.f32 p1, %3, %2;\n\t"
-        "selp.f32 t, %3, %2, p1;\n\t"
-        "@p1 or.b32 %1, %1, %5;\n\t"
-        "setp.gt.f32 p2, %4, t;\n\t"
-        "selp.f32 %0, %4, t, p2;\n\t"
-        "@p2 or.b32 %1, %1, %6;\n\t"
-        "}"
-        : "=f"(m), "+r"(bits)
-        : "f"(a0), "f"(a1), "f"(a2), "n"(1u << SH), "n"(2u << SH));
-    return m;
-}
-
-template <int RPL>
-__global__ void __launch_bounds__(8 * 32, 2)
-banded_fill_f32_kernel(const BandedArgs a)
-{
-    constexpr int WPB = 8, NW = RPL > 5 ? 2 : 1;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_fval[WPB][32];
-    const float kNI = -__int_as_float(0x7f800000);
-
-    const Tile tile = a.tiles[blockIdx.x];
-    const DevBanded* __restrict__ M = reinterpret_cast<const DevBanded*>(tile.model);
-    const int P = M->P, NC = M->NC, acc_col = M->acc_col;
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)M->image_f_bytes;
-        mbar_expect_tx(&s_bar, bytes);
-#pragma unroll 1
-        for (uint32_t o = 0; o < bytes; o += 65536u)
-            tma_bulk_g2s(smem_raw + o, M->image_f + o, min(65536u, bytes - o), &s_bar);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    mbar_wait(&s_bar, 0);
-    if (warp >= tile.cnt) return;
-    const int item = tile.first + warp;
-    const int q = a.order[item];
-    const size_t slot = (size_t)(item - a.chunk_base);
-    const int n = a.rlen[q];
-    if (n == 0) {
-        if (lane == 0) a.logp[q] = (double)M->logp_empty_f;
-        return;
-    }
-    const int nl = (n + RPL - 1) / RPL;
-    const int ln = (n - 1) / RPL, jn = (n - 1) % RPL;
-    const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
-    uint32_t symbits;
-    {
-        const int bit = 2 * lane * RPL;
-        const int w = bit >> 5, sh = bit & 31;
-        const int last_word = (n + 15) / 16;
-        const uint32_t lo = (w <= last_word) ? pk[w] : 0u;
-        const uint32_t hi = (w + 1 <= last_word) ? pk[w + 1] : 0u;
-        symbits = __funnelshift_r(lo, hi, sh);
-    }
-    uint32_t* tbw_t = a.tbw + slot * a.tbw_stride + (size_t)lane * P * NW - (ptrdiff_t)lane * NW;
-    uint16_t* __restrict__ acc_tb = a.acc_tb + slot * (size_t)a.acc_stride + lane * RPL;
-    float* __restrict__ vfin = reinterpret_cast<float*>(a.vfin + slot * a.vfin_stride);
-    float* vfin_t = vfin - lane;
-    const uint32_t s_base = smem_u32(smem_raw);
-    uint32_t w_t = s_base - (uint32_t)lane * 48u;
-    uint32_t e_t[RPL];
-#pragma unroll
-    for (int j = 0; j < RPL; ++j) {
-        e_t[j] = s_base + (uint32_t)kImgFE * P + ((symbits >> (2 * j)) & 3u) * (uint32_t)(8 * P) - (uint32_t)lane * 8u;
-        asm volatile("" : "+r"(e_t[j]));
-    }
-    asm volatile("" : "+l"(tbw_t), "+l"(vfin_t), "+r"(w_t));
-    const uint32_t v1_delta = (uint32_t)(kImgFV1 - kImgFE) * P;
-
-    float cI[RPL], cM[RPL], cD[RPL], acc[RPL];
-    int accarg[RPL];
-#pragma unroll
-    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNI; accarg[j] = 0; }
-    float bI = kNI, bM = kNI, bD = kNI;
-
-    const int steps = NC + nl - 1;
-#pragma unroll 1
-    for (int t = 0; t < steps; ++t) {
-        const float uI0 = __shfl_up_sync(0xffffffffu, cI[RPL - 1], 1);
-        const float uM0 = __shfl_up_sync(0xffffffffu, cM[RPL - 1], 1);
-        const float uD0 = __shfl_up_sync(0xffffffffu, cD[RPL - 1], 1);
-        const int c = t - lane;
-        if (c < 0 || c >= NC || lane >= nl) continue;
-        const uint32_t wa = w_t + (uint32_t)t * 48u;
-        const float4 w0 = lds128f(wa), w1 = lds128f(wa + 16), w2 = lds128f(wa + 32);
-        const float wII = w0.x, wIM = w0.y, wID = w0.z, wMI = w0.w, wMM = w1.x, wMD = w1.y;
-        const float wDI = w1.z, wDM = w1.w, wDD = w2.x, aw = w2.y;
-        const uint32_t cb = (uint32_t)t * 8u;
-        float nM[RPL], nD[RPL], eIr[RPL];
-        uint32_t word[NW];
-#pragma unroll
-        for (int k = 0; k < NW; ++k) word[k] = 0;
-        static_for<0, RPL>([&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            const float2 e = lds64f(e_t[j] + cb);
-            eIr[j] = e.x;
-            const float oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-            nM[j] = max3_first_f32<6 * (j % 5) + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
-            nD[j] = max3_first_f32<6 * (j % 5) + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
-        });
-        if (lane == 0) {
-            const float2 f = lds64f(e_t[0] + v1_delta + cb);
-            nM[0] = f.y;
-            eIr[0] = f.x;
-        }
-        if (c == acc_col) {
-#pragma unroll
-            for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
-        }
-        if (aw > kNI) {
-#pragma unroll
-            for (int j = 0; j < RPL; ++j) {
-                const float cand = nD[j] + aw;
-                if (cand > acc[j]) { acc[j] = cand; accarg[j] = c; }
-            }
-        }
-        float uI = uI0, uM = uM0, uD = uD0;
-        static_for<0, RPL>([&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            float vI = max3_first_f32<6 * (j % 5)>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
-            if (j == 0 && lane == 0) vI = eIr[0];
-            uI = vI; uM = nM[j]; uD = nD[j];
-            cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
-        });
-        bI = uI0; bM = uM0; bD = uD0;
-        if (NW == 1) tbw_t[t] = word[0];
-        else reinterpret_cast<uint2*>(tbw_t)[t] = make_uint2(word[0], word[NW - 1]);
-        if (lane == ln) {
-            float fI = cI[0], fM = cM[0], fD = cD[0];
-#pragma unroll
-            for (int j = 1; j < RPL; ++j)
-                if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
-            vfin_t[t] = fI; vfin_t[P + t] = fM; vfin_t[2 * P + t] = fD;
-        }
-    }
-    if (lane < nl) {
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) acc_tb[j] = (uint16_t)accarg[j];
-    }
-    __syncwarp();
-    const int NF = M->NF;
-    int32_t* __restrict__ ftb = a.ftb + slot * 32;
-    for (int f = 0; f < NF; ++f) {
-        const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
-        float best = kNI;
-        int arg = 0x7fffffff;
-        for (int k = k0 + lane; k < k1; k += 32) {
-            const int code = M->fin_src[k];
-            const float sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
-            const float cand = sv + M->fin_w_f[k];
-            if (cand > best) { best = cand; arg = k; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, arg, off);
-            if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
-        }
-        if (lane == 0) {
-            s_fval[warp][f] = best;
-            ftb[f] = (best > kNI) ? M->fin_src[arg] : 0;
-        }
-        __syncwarp();
-    }
-    if (lane == 0) a.logp[q] = (double)s_fval[warp][M->end_final];
-}
-
-// =============================================================================================
-// banded fill kernel for long reads / large models (PacBio-like, BASELINE config 3)
-//
-// Same recurrence, tables and traceback encoding as banded_fill_kernel, but
-//   * a read is cut into stripes of 32*RPL positions that one warp sweeps one after the other;
-//     the last position of a stripe is carried to the next stripe through a per-read buffer in
-//     global memory (3 doubles per column, updated in place: writes trail reads by >= 32 columns)
-//     that lane 0 consumes through a double-buffered 32-column ring in shared memory;
-//   * the model tables are read from global memory through the read-only path (the image of a
-//     100-copy model is > 1 MB); the warps of an SM walk the columns together, so L1 serves them.
-// =============================================================================================
-struct LongArgs {
-    const Tile* tiles;
-    const int32_t* order;
-    int32_t chunk_base;
-    const uint32_t* pk;
-    const int64_t* pk_off;
-    const int32_t* rlen;
-    double* logp;
-    uint32_t* tbw;              // per slot: stripes_max * 32 * Pmax * 2 words
-    size_t tbw_stride;
-    uint16_t* acc_tb;           // per slot: stripes_max * 32 * RPL entries
-    size_t acc_stride;
-    double* vfin;               // per slot 3 * Pmax
-    size_t vfin_stride;
-    double* carry;              // per slot 3 * Pmax
-    size_t carry_stride;
-    int32_t* ftb;               // per slot 32
-};
-
-constexpr int kLongRPL = 8;
-constexpr int kLongWarps = 4;
-
-__device__ __forceinline__ double2 ldg128(const unsigned char* p)
-{
-    double2 v;
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-
-__global__ void __launch_bounds__(kLongWarps * 32, 2)
-banded_long_kernel(const LongArgs a)
-{
-    constexpr int RPL = kLongRPL, NW = 2, H = 32 * RPL;
-    __shared__ double s_ring[kLongWarps][2][3][32];
-    __shared__ double s_fval[kLongWarps][32];
-
-    const Tile tile = a.tiles[blockIdx.x];
-    const DevBanded* __restrict__ M = reinterpret_cast<const DevBanded*>(tile.model);
-    const int P = M->P, NC = M->NC, acc_col = M->acc_col;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp >= tile.cnt) return;
-    const int item = tile.first + warp;
-    const int q = a.order[item];
-    const size_t slot = (size_t)(item - a.chunk_base);
-    const int n = a.rlen[q];
-    if (n == 0) {
-        if (lane == 0) a.logp[q] = M->logp_empty;
-        return;
-    }
-    const unsigned char* __restrict__ img = M->image;
-    const unsigned char* __restrict__ img_e = img + (size_t)kImgE * P;
-    const unsigned char* __restrict__ img_v1 = img + (size_t)kImgV1 * P;
-    const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
-    double* __restrict__ vfin = a.vfin + slot * a.vfin_stride;
-    double* __restrict__ carry = a.carry + slot * a.carry_stride;
-    const int n_stripes = (n + H - 1) / H;
-    const int last_word = (n + 15) / 16;
-
-    for (int s = 0; s < n_stripes; ++s) {
-        const int rows = min(H, n - s * H);
-        const int nl = (rows + RPL - 1) / RPL;
-        const bool last_stripe = (s == n_stripes - 1);
-        const int ln = (rows - 1) / RPL, jn = (rows - 1) % RPL;
-        uint32_t symbits;
-        {
-            const int bit = 2 * (s * H + lane * RPL);
-            const int w = bit >> 5;
-            symbits = (w <= last_word) ? (pk[w] >> (bit & 31)) & 0xffffu : 0u;
-        }
-        size_t eoff[RPL];
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) eoff[j] = (size_t)((symbits >> (2 * j)) & 3u) * 16u * P;
-
-        uint32_t* __restrict__ tbw = a.tbw + slot * a.tbw_stride + ((size_t)(s * 32 + lane) * P) * NW;
-        uint16_t* __restrict__ acc_tb = a.acc_tb + slot * a.acc_stride + (size_t)s * H + lane * RPL;
-
-        double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
-        int accarg[RPL];
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; accarg[j] = 0; }
-        double bI = kNegInf, bM = kNegInf, bD = kNegInf;
-
-        if (s > 0) {                           // ring block 0 = carried values of columns 0..31
-#pragma unroll
-            for (int k = 0; k < 3; ++k) s_ring[warp][0][k][lane] = carry[(size_t)k * P + lane];
-        }
-        __syncwarp();
-
-        const int steps = NC + nl - 1;
-#pragma unroll 1
-        for (int t = 0; t < steps; ++t) {
-            if (s > 0 && (t & 31) == 0) {      // prefetch the next 32 carried columns
-                const int col = t + 32 + lane;
-                const int buf = ((t >> 5) + 1) & 1;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) s_ring[warp][buf][k][lane] = (col < P) ? carry[(size_t)k * P + col] : kNegInf;
-                __syncwarp();
-            }
-            double uI0 = shfl_up_f64(cI[RPL - 1], 1);
-            double uM0 = shfl_up_f64(cM[RPL - 1], 1);
-            double uD0 = shfl_up_f64(cD[RPL - 1], 1);
-            const int c = t - lane;
-            if (c < 0 || c >= NC || lane >= nl) continue;
-            if (lane == 0 && s > 0) {
-                const int buf = (t >> 5) & 1;
-                uI0 = s_ring[warp][buf][0][t & 31];
-                uM0 = s_ring[warp][buf][1][t & 31];
-                uD0 = s_ring[warp][buf][2][t & 31];
-            }
-            const unsigned char* wp = img + (size_t)c * 80u;
-            const double2 w01 = ldg128(wp), w23 = ldg128(wp + 16), w45 = ldg128(wp + 32);
-            const double2 w67 = ldg128(wp + 48), w89 = ldg128(wp + 64);
-            const double wII = w01.x, wIM = w01.y, wID = w23.x, wMI = w23.y, wMM = w45.x, wMD = w45.y;
-            const double wDI = w67.x, wDM = w67.y, wDD = w89.x, aw = w89.y;
-            const size_t cb = (size_t)c * 16u;
-
-            double nM[RPL], nD[RPL], eIr[RPL];
-            uint32_t word[NW] = {0u, 0u};
-            static_for<0, RPL>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                const double2 e = ldg128(img_e + eoff[j] + cb);
-                eIr[j] = e.x;
-                const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-                nM[j] = max3_first<6 * (j % 5) + 2, false>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
-                nD[j] = max3_first<6 * (j % 5) + 4, false>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
-            });
-            const bool first_row = (lane == 0 && s == 0);
-            if (first_row) {
-                const double2 f = ldg128(img_v1 + eoff[0] + cb);
-                nM[0] = f.y;
-                eIr[0] = f.x;
-            }
-            if (c == acc_col) {
-#pragma unroll
-                for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
-            }
-            if (aw > kNegInf) {
-#pragma unroll
-                for (int j = 0; j < RPL; ++j) {
-                    const double cand = nD[j] + aw;
-                    if (cand > acc[j]) { acc[j] = cand; accarg[j] = c; }
-                }
-            }
-            double uI = uI0, uM = uM0, uD = uD0;
-            static_for<0, RPL>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                double vI = max3_first<6 * (j % 5), false>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
-                if (j == 0 && first_row) vI = eIr[0];
-                uI = vI; uM = nM[j]; uD = nD[j];
-                cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
-            });
-            bI = uI0; bM = uM0; bD = uD0;
-            reinterpret_cast<uint2*>(tbw)[c] = make_uint2(word[0], word[1]);
-            if (!last_stripe) {
-                if (lane == 31) {              // full stripe: lane 31 owns its last position
-                    carry[c] = cI[RPL - 1]; carry[(size_t)P + c] = cM[RPL - 1]; carry[(size_t)2 * P + c] = cD[RPL - 1];
-                }
-            } else if (lane == ln) {
-                double fI = cI[0], fM = cM[0], fD = cD[0];
-#pragma unroll
-                for (int j = 1; j < RPL; ++j)
-                    if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
-                vfin[c] = fI; vfin[(size_t)P + c] = fM; vfin[(size_t)2 * P + c] = fD;
-            }
-        }
-        if (lane < nl) {
-#pragma unroll
-            for (int j = 0; j < RPL; ++j) acc_tb[j] = (uint16_t)accarg[j];
-        }
-        __syncwarp();
-    }
-
-    // final-only silent states on the last row
-    const int NF = M->NF;
-    int32_t* __restrict__ ftb = a.ftb + slot * 32;
-    for (int f = 0; f < NF; ++f) {
-        const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
-        double best = kNegInf;
-        int arg = 0x7fffffff;
-        for (int k = k0 + lane; k < k1; k += 32) {
-            const int code = M->fin_src[k];
-            const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
-            const double cand = sv + M->fin_w[k];
-            if (cand > best) { best = cand; arg = k; }
-        }
-        warp_argmax_first(best, arg);
-        if (lane == 0) {
-            s_fval[warp][f] = best;
-            ftb[f] = (best > kNegInf) ? M->fin_src[arg] : 0;
-        }
-        __syncwarp();
-    }
-    if (lane == 0) a.logp[q] = s_fval[warp][M->end_final];
-}
-
-// =============================================================================================
-// on-device path reducers (hmm_utils.py:155-286): what adVNTR derives from a state path, computed
-// while the backtrack walks it (from the end of the read to its start)
-// =============================================================================================
-struct PathReducer {
-    const uint8_t* __restrict__ cls;
-    const uint32_t* __restrict__ pk;
-    int n, rem = 0;                      // read length; emitting states seen so far (from the end)
-    int n_match = 0, repeat_bp = 0, left_bp = 0, right_bp = 0, left_hits = 0, right_hits = 0;
-    int starts = 0, ends = 0, first_start = -1, last_start = -1, first_end = -1, last_end = -1;
-
-    __device__ __forceinline__ PathReducer(const uint8_t* c, const uint32_t* p, int len) : cls(c), pk(p), n(len) {}
-
-    __device__ __forceinline__ void visit(int state)
-    {
-        const int c = cls[state];
-        const int kind = c & 7, part = (c >> 3) & 3;
-        if (kind == 1 || kind == 2) {                       // M or I: emits read base n - rem - 1
-            if (kind == 1) {
-                ++n_match;
-                if (part == 1 || part == 2) {
-                    const int hit = packed_sym(pk, n - rem - 1) == ((c >> 5) & 3);
-                    if (part == 1) left_hits += hit; else right_hits += hit;
-                }
-            }
-            if (part == 1) ++left_bp; else if (part == 2) ++right_bp; else ++repeat_bp;
-            ++rem;
-        } else if (kind == 4) {                             // unit_start: >= 3 bases still to come
-            if (rem >= 3) { ++starts; const int bp = n - rem; if (last_start < 0) last_start = bp; first_start = bp; }
-        } else if (kind == 5) {                             // unit_end: >= 3 bases consumed
-            const int bp = n - rem;
-            if (bp >= 3) { ++ends; if (last_end < 0) last_end = bp; first_end = bp; }
-        }
-    }
-    __device__ __forceinline__ void store(advhmm_read_summary* out) const
-    {
-        int delta = 0;
-        if (first_start >= 0 && first_end >= 0 && first_end < first_start && last_start > last_end) delta = 1;
-        advhmm_read_summary s;
-        s.repeats = max(starts, ends) + delta;
-        s.n_match = n_match; s.repeat_bp = repeat_bp; s.left_bp = left_bp; s.right_bp = right_bp;
-        s.left_hits = left_hits; s.right_hits = right_hits;
-        s.unit_starts_ends = starts | (ends << 16);
-        *out = s;
-    }
-};
-
-// =============================================================================================
-// banded backtrack kernel: one thread per read
-// =============================================================================================
-struct BandedBtArgs {
-    const Tile* tiles;
-    const int32_t* order;
-    int32_t chunk_base;
-    int32_t n_items;            // work items in this chunk
-    int32_t rpl;                // RPL the fill kernel ran with
-    int32_t fp32;               // fill ran in fp32: use the float-evaluated predecessor tables
-    const uint32_t* pk;
-    const int64_t* pk_off;
-    const int32_t* rlen;
-    const double* logp;
-    const uint32_t* tbw;
-    size_t tbw_stride;
-    const uint16_t* acc_tb;
-    size_t acc_stride;
-    const int32_t* ftb;
-    const int32_t* item_tile;   // tile index of every work item
-    int32_t* path_len;          // [n_out]
-    int64_t* path_off;          // [n_out]
-    int32_t* path;              // NULL: no paths wanted (summaries only)
-    int64_t path_cap;
-    unsigned long long* cursor; // total path entries
-    advhmm_read_summary* summaries;   // NULL or [n_out]
-};
-
-template <typename Emit>
-__device__ __forceinline__ void banded_walk(const DevBanded* __restrict__ M, const BandedBtArgs& a,
-                                            size_t slot, int n, int sym0, Emit emit)
-{
-    const int P = M->P, rpl = a.rpl;
-    const int32_t* __restrict__ ftb = a.ftb + slot * 32;
-    int state;
-    if (n == 0) {
-        state = M->end;
-    } else {
-        int f = M->end_final, code;
-        for (;;) {
-            emit(M->fin_state[f]);
-            code = ftb[f];
-            if (code >= 0) break;
-            f = -(code + 1);
-        }
-        int sl = code / P, c = code - sl * P, r = n;
-        state = -1;
-        const int nw = rpl > 5 ? 2 : 1;
-        const uint32_t* tbw = a.tbw + slot * a.tbw_stride;
-        const uint16_t* acc_tb = a.acc_tb + slot * a.acc_stride;
-        while (r >= 1) {
-            const int s = M->st[sl * M->NC + c];
-            emit(s);
-            const int ln = (r - 1) / rpl, j = (r - 1) - ln * rpl;   // ln = stripe * 32 + lane
-            const uint32_t t = tbw[((size_t)ln * P + c) * nw + j / 5] >> (6 * (j % 5));
-            // two bits per slot: bit0 = second candidate beat the first, bit1 = third beat both
-            const int kI = (t & 2u) ? 2 : (int)(t & 1u);
-            const int kM = (t & 8u) ? 2 : (int)((t >> 2) & 1u);
-            const int kD = (t & 32u) ? 2 : (int)((t >> 4) & 1u);
-            if (sl == SLOT_D) {
-                if (c == M->acc_col) c = acc_tb[r - 1];
-                else { sl = kD; c -= 1; }
-            } else if (r == 1) {
-                state = (a.fp32 ? M->tb1_f : M->tb1)[sym0 * M->S + s];
-                r = 0;
-            } else if (sl == SLOT_M) { sl = kM; c -= 1; r -= 1; }
-            else { sl = kI; r -= 1; }
-        }
-    }
-    // row 0: silent closure back to the start state
-    int guard = M->m + 1;
-    const int32_t* __restrict__ tb0 = a.fp32 ? M->tb0_f : M->tb0;
-    while (state != M->start && state >= 0 && guard-- > 0) { emit(state); state = tb0[state]; }
-    emit(state);
-}
-
-__global__ void __launch_bounds__(128) banded_backtrack_kernel(const BandedBtArgs a)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < a.n_items;
-    int len = 0, q = 0, n = 0, sym0 = 0;
-    size_t slot = 0;
-    const DevBanded* M = nullptr;
-    bool possible = false;
-    if (active) {
-        const int item = a.chunk_base + i;
-        q = a.order[item];
-        slot = (size_t)i;
-        M = reinterpret_cast<const DevBanded*>(a.tiles[a.item_tile[item]].model);
-        n = a.rlen[q];
-        possible = a.logp[q] > kNegInf;
-        if (possible) {
-            if (n > 0) sym0 = packed_sym(a.pk + a.pk_off[q], 0);
-            if (a.summaries) {
-                // the walk starts at the model's end state and finishes at its start state; like
-                // the reference's vpath[1:-1] both are silent "other" states and reduce to nothing
-                PathReducer red(M->classes, a.pk + a.pk_off[q], n);
-                banded_walk(M, a, slot, n, sym0, [&](int s) { ++len; red.visit(s); });
-                red.store(a.summaries + q);
-            } else {
-                banded_walk(M, a, slot, n, sym0, [&](int) { ++len; });
-            }
-        } else if (a.summaries) {
-            advhmm_read_summary z = {};
-            z.repeats = -1;
-            a.summaries[q] = z;
-        }
-    }
-    if (!a.path) {                       // summaries only
-        if (active) { a.path_len[q] = possible ? len : -1; a.path_off[q] = 0; }
-        return;
-    }
-    // warp-aggregated allocation of output space
-    const unsigned lane = threadIdx.x & 31;
-    int incl = len;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(a.cursor, (unsigned long long)total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    if (!active) return;
-    if (!possible) { a.path_len[q] = -1; a.path_off[q] = 0; return; }
-    const int64_t off = (int64_t)base + (incl - len);
-    a.path_off[q] = off;
-    if (off + len > a.path_cap) { a.path_len[q] = -2; return; }   // caller buffer too small
-    a.path_len[q] = len;
-    int32_t* out = a.path + off;
-    int w = len;
-    banded_walk(M, a, slot, n, sym0, [&](int s) { out[--w] = s; });
-}
-
-// =============================================================================================
-// generic kernels (any baked model): one warp per read, rows in shared or global memory
-// =============================================================================================
-struct GenericArgs {
-    const Tile* tiles;
-    const int32_t* order;
-    int32_t chunk_base;
-    const uint32_t* pk;
-    const int64_t* pk_off;
-    const int32_t* rlen;
-    double* logp;
-    int32_t* end_state;         // [n_out] state the path ends in
-    uint16_t* tb;               // per slot: max_n * m slots (rows 1..n)
-    size_t tb_stride;
-    double* rows;               // global DP rows (2 * m per slot) when they do not fit in smem
-    size_t rows_stride;
-    int warps;                  // warps per CTA
-    int rows_in_smem;
-};
-
-template <bool FWD>
-__device__ __forceinline__ double pair_lse_dev(double x, double y)
-{
-    // utils.pyx:72-90
-    if (x == kNegInf) return y;
-    if (y == kNegInf) return x;
-    if (x > y) return x + log(exp(y - x) + 1.0);
-    return y + log(exp(x - y) + 1.0);
-}
-
-// FWD = false: Viterbi (max, traceback); FWD = true: forward (pair_lse, no traceback)
-template <bool FWD>
-__global__ void __launch_bounds__(kGenericWarpsMax * 32) generic_fill_kernel(const GenericArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const Tile tile = a.tiles[blockIdx.x];
-    const DevGeneric* __restrict__ G = reinterpret_cast<const DevGeneric*>(tile.model);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp >= tile.cnt) return;
-    const int item = tile.first + warp;
-    const int q = a.order[item];
-    const size_t slot = (size_t)(item - a.chunk_base);
-    const int n = a.rlen[q];
-    const int m = G->m, S = G->S, K = G->K;
-    double* prev;
-    double* cur;
-    if (a.rows_in_smem) {
-        prev = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * m;
-    } else {
-        prev = a.rows + slot * a.rows_stride;
-    }
-    cur = prev + m;
-    const int32_t* __restrict__ in_off = G->in_off;
-    const int32_t* __restrict__ in_src = G->in_src;
-    const double* __restrict__ in_w = G->in_w;
-    const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
-    uint16_t* __restrict__ tb = FWD ? nullptr : a.tb + slot * a.tb_stride;
-
-    for (int l = lane; l < m; l += 32) prev[l] = G->v0[l];
-    __syncwarp();
-    // NOTE: the forward recurrence's row 0 uses pair_lse instead of max; for FWD the caller passes
-    // a model whose v0 was computed with pair_lse (DevGeneric::v0 of the forward table set).
-    for (int i = 0; i < n; ++i) {
-        const int x = packed_sym(pk, i);
-        // emitting states (hmm.pyx:2026-2042 / 1427-1444)
-        for (int l = lane; l < S; l += 32) {
-            const double e = G->emis[(size_t)l * K + x];
-            const int k0 = in_off[l], k1 = in_off[l + 1];
-            double best = kNegInf;
-            int code = 0;
-            for (int k = k0; k < k1; ++k) {
-                if (FWD) {
-                    best = pair_lse_dev<true>(best, prev[in_src[k]] + in_w[k]);
-                } else {
-                    const double cand = (prev[in_src[k]] + in_w[k]) + e;
-                    if (cand > best) { best = cand; code = k - k0; }
-                }
-            }
-            if (FWD) best = best + e;
-            cur[l] = best;
-            if (!FWD) tb[(size_t)i * m + l] = (uint16_t)code;
-        }
-        __syncwarp();
-        // silent states, level by level (states of one level do not feed each other)
-        const int nlv = G->n_levels;
-        for (int L = 0; L < nlv; ++L) {
-            const int lo = G->lvl_off[L], hi = G->lvl_off[L + 1];
-            for (int p = lo + lane; p < hi; p += 32) {
-                const int l = G->lvl_state[p];
-                const int k0 = in_off[l], k1 = in_off[l + 1];
-                double best = kNegInf;
-                int code = 0;
-                if (FWD) {
-                    // pass 1 (emitting sources) and pass 2 (silent sources) are summed separately
-                    // and then combined (hmm.pyx:1446-1480)
-                    double acc2 = kNegInf;
-                    for (int k = k0; k < k1; ++k) {
-                        const int src = in_src[k];
-                        const double t = cur[src] + in_w[k];
-                        if (src < S) best = pair_lse_dev<true>(best, t);
-                        else acc2 = pair_lse_dev<true>(acc2, t);
-                    }
-                    best = pair_lse_dev<true>(best, acc2);
-                } else {
-                    for (int k = k0; k < k1; ++k) {
-                        const double cand = cur[in_src[k]] + in_w[k];
-                        if (cand > best) { best = cand; code = k - k0; }
-                    }
-                    tb[(size_t)i * m + l] = (uint16_t)code;
-                }
-                cur[l] = best;
-            }
-            __syncwarp();
-        }
-        double* t = prev; prev = cur; cur = t;
-    }
-    // termination (hmm.pyx:2089-2098 / 1300-1313)
-    if (G->finite) {
-        if (lane == 0) {
-            a.logp[q] = prev[G->end];
-            if (!FWD) a.end_state[q] = G->end;
-        }
-    } else if (FWD) {
-        if (lane == 0) {
-            double s = kNegInf;
-            for (int l = 0; l < S; ++l) s = pair_lse_dev<true>(s, prev[l]);
-            a.logp[q] = s;
-        }
-    } else {
-        double best = kNegInf;
-        int arg = 0x7fffffff;
-        for (int l = lane; l < m; l += 32)
-            if (prev[l] > best) { best = prev[l]; arg = l; }
-        warp_argmax_first(best, arg);
-        if (lane == 0) { a.logp[q] = best; a.end_state[q] = (best > kNegInf) ? arg : -1; }
-    }
-}
-
-struct GenericBtArgs {
-    const Tile* tiles;
-    const int32_t* order;
-    int32_t chunk_base;
-    int32_t n_items;
-    const int32_t* rlen;
-    const double* logp;
-    const int32_t* end_state;
-    const uint16_t* tb;
-    size_t tb_stride;
-    const int32_t* item_tile;
-    int32_t* path_len;
-    int64_t* path_off;
-    int32_t* path;
-    int64_t path_cap;
-    unsigned long long* cursor;
-    const uint32_t* pk;
-    const int64_t* pk_off;
-    advhmm_read_summary* summaries;
-};
-
-template <typename Emit>
-__device__ __forceinline__ void generic_walk(const DevGeneric* __restrict__ G, const uint16_t* __restrict__ tb,
-                                             int n, int end, Emit emit)
-{
-    const int m = G->m, S = G->S;
-    int px = n, py = end;
-    while (px > 0) {
-        emit(py);
-        const int src = G->in_src[G->in_off[py] + tb[(size_t)(px - 1) * m + py]];
-        if (py < S) --px;
-        py = src;
-    }
-    int guard = m + 1;
-    while (py != G->start && py >= 0 && guard-- > 0) { emit(py); py = G->tb0[py]; }
-    emit(py);
-}
-
-__global__ void __launch_bounds__(128) generic_backtrack_kernel(const GenericBtArgs a)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < a.n_items;
-    int len = 0, q = 0, n = 0, end = 0;
-    const DevGeneric* G = nullptr;
-    const uint16_t* tb = nullptr;
-    bool possible = false;
-    if (active) {
-        const int item = a.chunk_base + i;
-        q = a.order[item];
-        G = reinterpret_cast<const DevGeneric*>(a.tiles[a.item_tile[item]].model);
-        n = a.rlen[q];
-        tb = a.tb + (size_t)i * a.tb_stride;
-        end = a.end_state[q];
-        possible = a.logp[q] > kNegInf && end >= 0;
-        if (possible) {
-            if (a.summaries) {
-                PathReducer red(G->classes, a.pk + a.pk_off[q], n);
-                generic_walk(G, tb, n, end, [&](int s) { ++len; red.visit(s); });
-                red.store(a.summaries + q);
-            } else {
-                generic_walk(G, tb, n, end, [&](int) { ++len; });
-            }
-        } else if (a.summaries) {
-            advhmm_read_summary z = {};
-            z.repeats = -1;
-            a.summaries[q] = z;
-        }
-    }
-    if (!a.path) {
-        if (active) { a.path_len[q] = possible ? len : -1; a.path_off[q] = 0; }
-        return;
-    }
-    const unsigned lane = threadIdx.x & 31;
-    int incl = len;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(a.cursor, (unsigned long long)total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    if (!active) return;
-    if (!possible) { a.path_len[q] = -1; a.path_off[q] = 0; return; }
-    const int64_t off = (int64_t)base + (incl - len);
-    a.path_off[q] = off;
-    if (off + len > a.path_cap) { a.path_len[q] = -2; return; }
-    a.path_len[q] = len;
-    int32_t* out = a.path + off;
-    int w = len;
-    generic_walk(G, tb, n, end, [&](int s) { out[--w] = s; });
-}
 
 // =============================================================================================
 // host side: model upload

@@ -1,0 +1,170 @@
+// engine_types.cuh: error plumbing, device descriptors, context / model handles -- part of libadvhmm.so (see advhmm.cu for the overview)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "model_compile.hpp"
+
+using namespace advhmm;
+
+// error plumbing
+// =============================================================================================
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                          \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return set_error(e__ == cudaErrorMemoryAllocation ? ADVHMM_ENOMEM : ADVHMM_ECUDA, \
+                             "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),         \
+                             __FILE__, __LINE__);                                             \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, want = bytes); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// =============================================================================================
+// device-side model descriptors
+// =============================================================================================
+struct DevGeneric {
+    int m, S, K, start, end, finite, n_levels, max_in_degree;
+    const int32_t* in_off;
+    const int32_t* in_src;
+    const double* in_w;
+    const double* emis;
+    const double* v0;
+    const int32_t* tb0;
+    const int32_t* lvl_off;
+    const int32_t* lvl_state;
+    const uint8_t* classes;       // [m] state class bytes for the on-device path reducers
+};
+
+struct DevBanded {
+    int NC, P, S, m, NF, end_final, acc_col, n_acc;
+    int start, end, image_bytes, pad0;
+    double logp_empty;            // v0[end]: the answer for an empty read
+    const unsigned char* image;   // smem image, see kImg* (208 bytes per column)
+    const int32_t* st;            // [3*NC] slot -> state
+    const int32_t* tb1;           // [4*S]
+    const int32_t* acc_src_col;   // [n_acc]
+    const int32_t* fin_state;     // [NF]
+    const int32_t* fin_off;       // [NF+1]
+    const int32_t* fin_src;
+    const double* fin_w;
+    const int32_t* tb0;           // [m]
+    // fp32 twin (ADVHMM_FP32): float image (112 bytes per column) and the host-evaluated tables
+    // re-evaluated in float arithmetic
+    const unsigned char* image_f;
+    int image_f_bytes, pad1;
+    float logp_empty_f, pad2;
+    const int32_t* tb1_f;
+    const int32_t* tb0_f;
+    const float* fin_w_f;
+    const uint8_t* classes;       // [m]
+};
+
+struct Tile {
+    const void* model;   // DevBanded* or DevGeneric*
+    int32_t first;       // first index into order[]
+    int32_t cnt;         // reads in this tile (<= warps per block)
+};
+
+constexpr int kMaxRPL = 10;             // read positions per lane: reads up to 320 bases on the banded path
+constexpr int kBandedWarpsMax = 16;     // reads per CTA (banded): run-time choice, see ctx->banded_warps
+constexpr int kGenericWarpsMax = 8;
+
+}  // namespace
+
+struct advhmm_context {
+    int device = -1;             // < 0: host-only context (model analysis without a GPU)
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    size_t workspace_budget = 0;
+    DevBuf d_seqs, d_seq_off, d_pk, d_meta, d_work, d_out, d_paths, d_flags;
+    PinnedBuf h_meta, h_out;
+    cudaEvent_t meta_done = nullptr;
+    // optional per-kernel timing (bench.py roofline): event pairs around every fill launch
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];   // [0] banded fill, [1] backtrack
+    size_t prof_used[2] = {0, 0};
+    int banded_smem_set[kMaxRPL + 4] = {0};   // dynamic-smem opt-in already applied per kernel variant
+    int banded_warps = 8;        // reads per CTA of the banded kernel
+    bool int_compare = false;    // integer-pipe compares (ADVHMM_ICMP=1); needs all tables <= 0
+    bool launch_int_compare = false;   // ... and every model of the current batch qualifies
+    int generic_smem_set = 0;
+    int banded_f32_smem_set[kMaxRPL + 1] = {0};
+    std::mutex mu;
+};
+
+struct advhmm_model {
+    advhmm_context* ctx = nullptr;
+    CompiledModel cm;
+    DevBuf blob;                 // all device tables of this model
+    DevGeneric* d_generic = nullptr;
+    DevGeneric* d_generic_fwd = nullptr;   // same tables, row 0 closed with pair_lse (forward)
+    DevBanded* d_banded = nullptr;
+    uint8_t* d_classes = nullptr;  // [n_states] state class bytes (zero until set_state_classes)
+    int banded_smem = 0;         // image bytes (0: not banded / does not fit)
+    advhmm_model_info info{};
+};
+
+// =============================================================================================
+// small device helpers
+// =============================================================================================

@@ -340,6 +340,41 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - te0) * 1e3
         assert h_total.value == n_paths
+    # ---- extra (reported, not the headline): on-device reducers instead of paths; fp32 mode ----
+    extra = {}
+    if not args.no_e2e:
+        summ = np.zeros(R, dtype=engine.SUMMARY_DTYPE)
+        h_summ = torch.from_numpy(summ.view(np.int32).reshape(R, 8)).pin_memory()
+
+        def step_summary():
+            rc = lib.advhmm_viterbi_multi_summary(ctx._h, handles, len(models), goff.ctypes.data, h_seqs.data_ptr(),
+                                                  off.ctypes.data, R, engine.WANT_SUMMARY, h_logp.data_ptr(),
+                                                  h_plen.data_ptr(), h_poff.data_ptr(), None, 0, None,
+                                                  h_summ.data_ptr())
+            engine._check(rc)
+        step_summary()
+        torch.cuda.synchronize()
+        ts = time.perf_counter()
+        for _ in range(args.steps):
+            step_summary()
+        torch.cuda.synchronize()
+        extra["e2e_summary_ms"] = (time.perf_counter() - ts) * 1e3 / args.steps
+
+        def step_fp32():
+            rc = lib.advhmm_viterbi_multi(ctx._h, handles, len(models), goff.ctypes.data, d_seqs.data_ptr(),
+                                          off.ctypes.data, R, flags_dev | engine.FP32, d_logp.data_ptr(),
+                                          d_plen.data_ptr(), d_poff.data_ptr(), d_path.data_ptr(), path_cap,
+                                          d_total.data_ptr())
+            engine._check(rc)
+        step_fp32()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            step_fp32()
+        f1.record(stream)
+        torch.cuda.synchronize()
+        extra["fp32_ms"] = f0.elapsed_time(f1) / args.steps
     sampler.stop()
 
     # ---- max over ranks -------------------------------------------------------------------------
@@ -368,6 +403,15 @@ def run_ours(args):
             line["e2e"] = {"value": reads_all * K / (e2e_all * 1e-3), "unit": "reads/s",
                            "gcups": cells_all * K / (e2e_all * 1e-3) / 1e9,
                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_all / K}
+        if extra:
+            line["extras"] = {
+                "e2e_summary_only": {"value": R * world / (extra["e2e_summary_ms"] * 1e-3), "unit": "reads/s",
+                                     "note": "host buffers, on-device path reducers (32 B/read) instead of "
+                                             "full state paths; rank-0 time x n_gpus",
+                                     "d2h_bytes_per_step": R * (8 + 4 + 32)},
+                "fp32_mode": {"value": R * world / (extra["fp32_ms"] * 1e-3), "unit": "reads/s",
+                              "note": "optional ADVHMM_FP32 mode, device-resident, full paths; tolerance "
+                                      "and RU-count concordance in tests/test_gpu_parity.py::test_fp32_mode"}}
         line["roofline"] = roofline(ctx, wl, fill_ms, fill_n, bt_ms, bt_n, ms, K)
         if world == 1 and not args.no_cpu_baseline:
             procs = host_cores()
