@@ -2,7 +2,12 @@
 #pragma once
 #include "kernels_common.cuh"
 
+#ifndef ADV_STEP_UNROLL
+#define ADV_STEP_UNROLL 1      // unroll factor of the column-step loop of banded_fill_kernel
+#endif
+
 namespace {
+constexpr int kStepUnroll = ADV_STEP_UNROLL;
 // =============================================================================================
 // banded fill kernel
 // =============================================================================================
@@ -125,7 +130,7 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
     asm volatile("" : "+l"(tbw_t), "+l"(vfin_t), "+r"(w_t));
 
     const int steps = NC + nl - 1;
-#pragma unroll 1
+#pragma unroll kStepUnroll
     for (int t = 0; t < steps; ++t) {
         // the row above my block at column c was finished by lane-1 in the previous step
         const double uI0 = shfl_up_f64(cI[RPL - 1], 1);
@@ -182,8 +187,13 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
             cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
         });
         bI = uI0; bM = uM0; bD = uD0;
+#ifdef ADV_TB_STCS
+        if (NW == 1) __stcs(&tbw_t[t], word[0]);
+        else __stcs(&reinterpret_cast<uint2*>(tbw_t)[t], make_uint2(word[0], word[NW - 1]));
+#else
         if (NW == 1) tbw_t[t] = word[0];
         else reinterpret_cast<uint2*>(tbw_t)[t] = make_uint2(word[0], word[NW - 1]);
+#endif
         if (ALIGNED) {
             if (store_last) { vfin_t[t] = cI[RPL - 1]; vfin_t[P + t] = cM[RPL - 1]; vfin_t[2 * P + t] = cD[RPL - 1]; }
         } else if (lane == ln) {

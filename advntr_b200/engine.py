@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libadvhmm.so")
+LIB_PATH = os.environ.get("ADVHMM_LIB") or os.path.join(_PKG, "libadvhmm.so")
 
 OK, EINVAL, ECUDA, ENOMEM, ESYMBOL, ECAPACITY, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 WANT_PATH, BOTH_STRANDS, FP32, FORCE_GENERIC, WANT_SUMMARY, DEVICE_BUFFERS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x100
@@ -104,6 +104,21 @@ def encode_acgt(seq):
     out = np.empty(len(raw), dtype=np.uint8)
     bad = load_library().advhmm_encode_acgt(raw, len(raw), out.ctypes.data)
     return out, int(bad)
+
+
+def encode_batch(sequences):
+    """list of ASCII DNA strings -> (flat uint8 codes, int64 offsets[R+1]) with ONE encode call.
+    Raises the reference's ValueError for the first symbol that is not ACGT (hmm.pyx:72-79)."""
+    R = len(sequences)
+    off = np.zeros(R + 1, dtype=np.int64)
+    if R:
+        np.cumsum(np.fromiter(map(len, sequences), dtype=np.int64, count=R), out=off[1:])
+    raw = "".join(sequences).encode("ascii", "replace")
+    flat = np.empty(max(len(raw), 1), dtype=np.uint8)
+    bad = load_library().advhmm_encode_acgt(raw, len(raw), flat.ctypes.data)
+    if bad >= 0:
+        raise ValueError("Symbol '{}' is not defined in a distribution".format(chr(raw[bad])))
+    return flat, off
 
 
 def pack_reads(codes):
@@ -296,6 +311,13 @@ class DeviceModel(object):
             raise EngineError(EUNSUPPORTED, "precision must be 'fp64' (default, bit-exact) or 'fp32'")
         seqs, off = pack_reads(codes)
         goff = np.array([0, len(codes)], dtype=np.int64)
+        return self.ctx._run([self], goff, seqs, off, both_strands, want_path, force_generic, path_cap,
+                             fp32=(precision == "fp32"), want_summary=want_summary)
+
+    def viterbi_packed(self, seqs, off, both_strands=False, want_path=True, precision="fp64",
+                       force_generic=False, path_cap=None, want_summary=False):
+        """``viterbi`` for reads already flattened to (uint8 codes, int64 offsets)."""
+        goff = np.array([0, len(off) - 1], dtype=np.int64)
         return self.ctx._run([self], goff, seqs, off, both_strands, want_path, force_generic, path_cap,
                              fp32=(precision == "fp32"), want_summary=want_summary)
 

@@ -496,9 +496,16 @@ class HiddenMarkovModel(object):
         ``want_summary``: also return the on-device path reducers (``result.summaries``)."""
         if self.d == 0:
             raise ValueError("must bake model before using Viterbi algorithm")
+        dm = self._device_model()
+        if self._baked["alphabet"] == "ACGT" and all(isinstance(s, str) for s in sequences):
+            # one encode call for the whole batch instead of one per read
+            from . import engine
+            seqs, off = engine.encode_batch(sequences)
+            return dm.viterbi_packed(seqs, off, both_strands=both_strands, want_path=want_path,
+                                     precision=precision, want_summary=want_summary)
         codes = [self._encode(s) for s in sequences]
-        return self._device_model().viterbi(codes, both_strands=both_strands, want_path=want_path,
-                                            precision=precision, want_summary=want_summary)
+        return dm.viterbi(codes, both_strands=both_strands, want_path=want_path,
+                          precision=precision, want_summary=want_summary)
 
     def log_probability(self, sequence, check_input=True):
         """Forward log-likelihood (hmm.pyx:1258-1313)."""
