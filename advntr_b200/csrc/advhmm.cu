@@ -28,6 +28,10 @@
 // log-probabilities are bit-identical; see model_compile.hpp for why the banded schedule may
 // skip / reorder the candidates it does.
 #include "kernels_generic.cuh"
+#include "kernels_kfilter.cuh"
+
+#include <algorithm>
+#include <unordered_map>
 
 namespace {
 
@@ -691,6 +695,193 @@ __global__ void __launch_bounds__(256) fp64_add_peak_kernel(double* out, int ite
 }  // namespace
 
 // =============================================================================================
+// keyword pre-filter: host side
+// =============================================================================================
+struct advhmm_kfilter {
+    advhmm_context* ctx = nullptr;
+    DevKFilter dev{};
+    DevBuf tables, seqs, meta, counters, hits;
+    int64_t n_keywords = 0, n_unique = 0;
+};
+
+namespace {
+
+unsigned long long next_pow2(unsigned long long x)
+{
+    unsigned long long p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+struct KfWord {                         // one distinct (length class, keyword)
+    int cls;
+    std::string codes;                  // symbol codes 0..4
+    std::vector<int32_t> loci;
+};
+
+int kfilter_build(advhmm_kfilter* kf, int64_t n, const char* words, const int64_t* word_off, const int32_t* locus)
+{
+    advhmm_context* ctx = kf->ctx;
+    // length classes
+    std::vector<int> lengths;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t k = word_off[i + 1] - word_off[i];
+        if (k < 1 || k > kKfMaxK)
+            return set_error(k < 1 ? ADVHMM_EINVAL : ADVHMM_EUNSUPPORTED,
+                             "keyword %lld has length %lld: the device filter handles 1..%d", (long long)i, (long long)k, kKfMaxK);
+        if (std::find(lengths.begin(), lengths.end(), (int)k) == lengths.end()) lengths.push_back((int)k);
+    }
+    std::sort(lengths.begin(), lengths.end());
+    if ((int)lengths.size() > kKfMaxClasses)
+        return set_error(ADVHMM_EUNSUPPORTED, "%d distinct keyword lengths: the device filter handles %d per filter",
+                         (int)lengths.size(), kKfMaxClasses);
+    DevKFilter& d = kf->dev;
+    d = DevKFilter{};
+    d.n_classes = (int)lengths.size();
+    int kmax = 1;
+    for (int c = 0; c < d.n_classes; ++c) {
+        KfClass& cl = d.cls[c];
+        cl.k = lengths[c];
+        cl.exact = cl.k <= 21;
+        cl.key_mask = (3 * cl.k >= 64) ? ~0ull : ((1ull << (3 * cl.k)) - 1);
+        cl.salt = 0xD6E8FEB86659FD93ull * (unsigned long long)(c + 1);
+        cl.bk = 1;
+        for (int j = 0; j < cl.k; ++j) cl.bk *= kKfBase;
+        kmax = std::max(kmax, cl.k);
+    }
+    d.halo = (kmax - 1 + 15) / 16 * 16;
+    // distinct keywords per class, each with the loci that own it (in the caller's order)
+    std::unordered_map<std::string, size_t> index;
+    std::vector<KfWord> uniq;
+    index.reserve((size_t)n * 2);
+    for (int64_t i = 0; i < n; ++i) {
+        const int k = (int)(word_off[i + 1] - word_off[i]);
+        const int c = (int)(std::lower_bound(lengths.begin(), lengths.end(), k) - lengths.begin());
+        std::string codes((size_t)k, '\0');
+        for (int j = 0; j < k; ++j) codes[j] = (char)kf_code((unsigned char)words[word_off[i] + j]);
+        auto it = index.find(codes);       // the length is part of the string, hence of the class
+        if (it == index.end()) {
+            it = index.emplace(codes, uniq.size()).first;
+            uniq.push_back(KfWord{c, codes, {}});
+        }
+        uniq[it->second].loci.push_back(locus[i]);
+    }
+    const unsigned long long nu = uniq.size();
+    const unsigned long long tsize = next_pow2(std::max<unsigned long long>(64, nu * 2));
+    const unsigned long long bwords = std::min<unsigned long long>(1ull << 28, next_pow2(std::max<unsigned long long>(1 << 10, nu * 2)));
+    int bbits = 0;
+    while ((1ull << bbits) < bwords) ++bbits;
+    std::vector<KfEntry> table(tsize, KfEntry{0, 0, 0, 0, 0, 0});
+    std::vector<uint32_t> bloom(bwords, 0);
+    std::vector<int32_t> loci;
+    std::vector<uint8_t> text;
+    loci.reserve((size_t)n);
+    for (const KfWord& w : uniq) {
+        const KfClass& cl = d.cls[w.cls];
+        unsigned long long key = 0;
+        if (cl.exact) for (char ch : w.codes) key = (key << 3) | (unsigned long long)ch;
+        else          for (char ch : w.codes) key = key * kKfBase + ((unsigned long long)ch + 1u);
+        uint32_t a, m;
+        const unsigned long long h = kf_hash(key, cl.salt, a, m);
+        bloom[a >> (32 - bbits)] |= m;
+        unsigned long long slot = kf_slot(h, tsize - 1);
+        while (table[slot].loci_cnt) slot = (slot + 1) & (tsize - 1);
+        KfEntry& e = table[slot];
+        e.key = key;
+        e.cls = (uint32_t)w.cls;
+        e.loci_off = (uint32_t)loci.size();
+        e.loci_cnt = (uint32_t)w.loci.size();
+        e.text_off = (uint32_t)text.size();
+        loci.insert(loci.end(), w.loci.begin(), w.loci.end());
+        if (!cl.exact) text.insert(text.end(), w.codes.begin(), w.codes.end());
+    }
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_table = 0, o_bloom = al(table.size() * sizeof(KfEntry));
+    const size_t o_loci = o_bloom + al(bloom.size() * 4), o_text = o_loci + al(loci.size() * 4 + 4);
+    const size_t total = o_text + al(text.size() + 16);
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(kf->tables.ensure(total));
+    unsigned char* dp = kf->tables.as<unsigned char>();
+    CU_TRY(cudaMemcpyAsync(dp + o_table, table.data(), table.size() * sizeof(KfEntry), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(dp + o_bloom, bloom.data(), bloom.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!loci.empty())
+        CU_TRY(cudaMemcpyAsync(dp + o_loci, loci.data(), loci.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!text.empty())
+        CU_TRY(cudaMemcpyAsync(dp + o_text, text.data(), text.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    d.table = reinterpret_cast<const KfEntry*>(dp + o_table);
+    d.table_mask = tsize - 1;
+    d.bloom = reinterpret_cast<const uint32_t*>(dp + o_bloom);
+    d.bloom_shift = (uint32_t)(32 - bbits);
+    d.loci = reinterpret_cast<const int32_t*>(dp + o_loci);
+    d.text = dp + o_text;
+    kf->n_keywords = n;
+    kf->n_unique = (int64_t)nu;
+    return ADVHMM_OK;
+}
+
+// d_seqs and the hit arrays are device pointers; seq_off is the host copy of the offsets (also
+// uploaded); d_n_hits a device counter.  Queues scan + compaction on the context's stream; the only
+// host synchronisation is the read-back of the "counter table full" flag.
+int kfilter_scan_device(advhmm_kfilter* kf, const unsigned char* d_seqs, const int64_t* seq_off, int n_reads,
+                        int min_matches, int32_t* d_hit_read, int32_t* d_hit_locus, int32_t* d_hit_count,
+                        int64_t hit_cap, unsigned long long* d_n_hits)
+{
+    advhmm_context* ctx = kf->ctx;
+    const int64_t n_bases = n_reads > 0 ? seq_off[n_reads] : 0;
+    CU_TRY(cudaMemsetAsync(d_n_hits, 0, sizeof(unsigned long long), ctx->stream));
+    if (n_bases <= 0 || kf->dev.n_classes == 0) return ADVHMM_OK;
+    if (reinterpret_cast<uintptr_t>(d_seqs) % 16)
+        return set_error(ADVHMM_EINVAL, "keyword filter: the device read buffer must be 16-byte aligned");
+    // which read owns the first byte of every tile (the last read with seq_off[r] <= tile start)
+    const int64_t n_tiles = (n_bases + kKfTile - 1) / kKfTile;
+    std::vector<int32_t> tile_first((size_t)n_tiles + 1);
+    {
+        int32_t r = 0;
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const int64_t p = t * kKfTile;
+            while (r + 1 < n_reads && seq_off[r + 1] <= p) ++r;
+            tile_first[(size_t)t] = r;
+        }
+        tile_first[(size_t)n_tiles] = n_reads - 1;
+    }
+    const size_t off_bytes = ((size_t)(n_reads + 1) * 8 + 255) / 256 * 256;
+    CU_TRY(kf->meta.ensure(off_bytes + (size_t)(n_tiles + 1) * 4));
+    int64_t* d_off = kf->meta.as<int64_t>();
+    int32_t* d_tile = reinterpret_cast<int32_t*>(kf->meta.as<unsigned char>() + off_bytes);
+    CU_TRY(cudaMemcpyAsync(d_off, seq_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(d_tile, tile_first.data(), (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));      // tile_first is a stack-owned vector
+    const size_t smem = (size_t)kf->dev.halo + kKfTile;
+    unsigned long long cap = next_pow2(std::max<unsigned long long>(1 << 16, (unsigned long long)n_reads / 2));
+    for (int attempt = 0; attempt < 10; ++attempt, cap <<= 2) {
+        const size_t bytes = (size_t)cap * 12 + 256;
+        CU_TRY(kf->counters.ensure(bytes));
+        unsigned long long* ck = kf->counters.as<unsigned long long>();
+        uint32_t* cv = reinterpret_cast<uint32_t*>(ck + cap);
+        int32_t* ovf = reinterpret_cast<int32_t*>(cv + cap);
+        CU_TRY(cudaMemsetAsync(ck, 0xff, (size_t)cap * 8, ctx->stream));
+        CU_TRY(cudaMemsetAsync(cv, 0, (size_t)cap * 4 + 64, ctx->stream));
+        KfScanArgs sa{kf->dev, d_seqs, d_off, d_tile, n_bases, n_reads, 0, ck, cv, cap - 1, ovf};
+        kfilter_scan_kernel<<<(unsigned)n_tiles, kKfThreads, smem, ctx->stream>>>(sa);
+        CU_TRY(cudaGetLastError());
+        ctx->launches++;
+        int32_t overflow = 0;
+        CU_TRY(cudaMemcpyAsync(&overflow, ovf, sizeof overflow, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        if (overflow) continue;
+        KfCompactArgs ca{ck, cv, cap, min_matches, d_hit_read, d_hit_locus, d_hit_count, (long long)hit_cap, d_n_hits};
+        kfilter_compact_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(ca);
+        CU_TRY(cudaGetLastError());
+        ctx->launches++;
+        return ADVHMM_OK;
+    }
+    return set_error(ADVHMM_ENOMEM, "keyword filter: occurrence counter table kept overflowing");
+}
+
+}  // namespace
+
+// =============================================================================================
 // C-ABI
 // =============================================================================================
 extern "C" {
@@ -931,6 +1122,87 @@ int advhmm_viterbi_multi_summary(advhmm_context* ctx, advhmm_model* const* model
                reinterpret_cast<unsigned long long*>(path_total), want_sum ? summaries : nullptr};
     return run_batch(ctx, models, n_models, group_off, seqs, seq_off, n_reads, flags & ~ADVHMM_DEVICE_BUFFERS, op,
                      false, d_bad);
+}
+
+int advhmm_kfilter_create(advhmm_context* ctx, int64_t n_keywords, const char* keywords, const int64_t* keyword_off,
+                          const int32_t* keyword_locus, advhmm_kfilter** out)
+{
+    if (!ctx || !out || n_keywords < 0 || (n_keywords > 0 && (!keywords || !keyword_off || !keyword_locus)))
+        return set_error(ADVHMM_EINVAL, "null or negative argument");
+    *out = nullptr;
+    if (ctx->device < 0) return set_error(ADVHMM_ECUDA, "this context has no CUDA device");
+    std::unique_ptr<advhmm_kfilter> kf(new (std::nothrow) advhmm_kfilter);
+    if (!kf) return set_error(ADVHMM_ENOMEM, "out of host memory");
+    kf->ctx = ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    int rc = kfilter_build(kf.get(), n_keywords, keywords, keyword_off, keyword_locus);
+    if (rc) {
+        kf->tables.release();
+        return rc;
+    }
+    *out = kf.release();
+    return ADVHMM_OK;
+}
+
+void advhmm_kfilter_destroy(advhmm_kfilter* kf)
+{
+    if (!kf) return;
+    if (kf->ctx && kf->ctx->device >= 0) {
+        cudaSetDevice(kf->ctx->device);
+        cudaStreamSynchronize(kf->ctx->stream);
+        for (DevBuf* b : {&kf->tables, &kf->seqs, &kf->meta, &kf->counters, &kf->hits}) b->release();
+    }
+    delete kf;
+}
+
+int advhmm_kfilter_scan(advhmm_kfilter* kf, const char* seqs, const int64_t* seq_off, int32_t n_reads,
+                        int32_t min_matches, uint32_t flags, int32_t* hit_read, int32_t* hit_locus,
+                        int32_t* hit_count, int64_t hit_cap, int64_t* n_hits)
+{
+    if (!kf || (n_reads > 0 && !seq_off) || n_reads < 0 || !n_hits || hit_cap < 0 ||
+        (hit_cap > 0 && (!hit_read || !hit_locus || !hit_count)))
+        return set_error(ADVHMM_EINVAL, "null or negative argument");
+    if (n_reads > 0) {
+        if (seq_off[0] != 0) return set_error(ADVHMM_EINVAL, "seq_off[0] must be 0");
+        for (int32_t r = 0; r < n_reads; ++r)
+            if (seq_off[r + 1] < seq_off[r]) return set_error(ADVHMM_EINVAL, "seq_off must be non-decreasing");
+        if (seq_off[n_reads] > 0 && !seqs) return set_error(ADVHMM_EINVAL, "null read buffer");
+    }
+    advhmm_context* ctx = kf->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU_TRY(cudaSetDevice(ctx->device));
+    if (flags & ADVHMM_DEVICE_BUFFERS)
+        // seqs, hit_* and n_hits are device pointers; seq_off stays a host array
+        return kfilter_scan_device(kf, reinterpret_cast<const unsigned char*>(seqs), seq_off, n_reads, min_matches,
+                                   hit_read, hit_locus, hit_count, hit_cap, reinterpret_cast<unsigned long long*>(n_hits));
+    *n_hits = 0;
+    if (n_reads == 0) return ADVHMM_OK;
+    const int64_t n_bases = seq_off[n_reads];
+    CU_TRY(kf->seqs.ensure((size_t)n_bases + 16));
+    if (n_bases) CU_TRY(cudaMemcpyAsync(kf->seqs.p, seqs, (size_t)n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t hb = ((size_t)std::max<int64_t>(hit_cap, 1) * 4 + 255) / 256 * 256;
+    CU_TRY(kf->hits.ensure(3 * hb + 256));
+    unsigned char* dh = kf->hits.as<unsigned char>();
+    int32_t* d_r = reinterpret_cast<int32_t*>(dh);
+    int32_t* d_l = reinterpret_cast<int32_t*>(dh + hb);
+    int32_t* d_c = reinterpret_cast<int32_t*>(dh + 2 * hb);
+    unsigned long long* d_n = reinterpret_cast<unsigned long long*>(dh + 3 * hb);
+    int rc = kfilter_scan_device(kf, kf->seqs.as<unsigned char>(), seq_off, n_reads, min_matches,
+                                 d_r, d_l, d_c, hit_cap, d_n);
+    if (rc) return rc;
+    unsigned long long total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, d_n, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    *n_hits = (int64_t)total;
+    if ((int64_t)total > hit_cap)
+        return set_error(ADVHMM_ECAPACITY, "hit buffers too small: need %lld entries, have %lld", (long long)total, (long long)hit_cap);
+    if (total) {
+        CU_TRY(cudaMemcpyAsync(hit_read, d_r, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(hit_locus, d_l, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(hit_count, d_c, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return ADVHMM_OK;
 }
 
 }  // extern "C"

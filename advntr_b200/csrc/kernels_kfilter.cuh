@@ -1,0 +1,281 @@
+// kernels_kfilter.cuh -- GPU keyword pre-filter, the step right before the Viterbi hot path
+// (SURVEY.md section 8f rank 3).  Replaces the Aho-Corasick scan of the reference's
+// `adVNTR-Filtering` binary (/root/reference/filtering/main.cc:229-300): for every unmapped read
+// and every locus, count the occurrences of the locus's keywords in the read.
+//
+// An Aho-Corasick automaton reports, at every text position, every keyword that ends there.  With
+// the keywords grouped by length ("classes") that is an exact k-mer lookup per class and position,
+// which parallelises over POSITIONS instead of over reads:
+//
+//   * the reads are one flat byte stream (as the caller passes them, no separators).  A CTA owns a
+//     tile of kKfTile bytes; one elected thread stages tile + halo (the k_max-1 bytes before it)
+//     into shared memory with ONE TMA bulk copy (cp.async.bulk, completion on an mbarrier); the
+//     CTA converts it in place to 3-bit symbol codes (A,C,G,T = 0..3, anything else = 4: the
+//     reference's char_to_num, main.cc:43-54; lower case is "anything else" there too).
+//   * a thread scans 80 consecutive end positions (80 B = 20 words per thread: the quarter-warp's
+//     LDS.128 hit disjoint bank groups).  k <= 21: the k-mer is a 3k-bit integer rolled by
+//     shift/or (exact key).  k > 21: a 64-bit polynomial rolling hash, verified against the
+//     keyword text on a hit (exact result either way).
+//   * every position probes a blocked Bloom filter (3 bits in one 32-bit word, 64 bits per
+//     keyword, false-positive rate ~1e-3, L2 resident): 8 positions are hashed and their words
+//     loaded before any is tested, so the loads overlap.
+//   * a Bloom hit takes the slow path: open-addressing table (key, class) -> list of loci that
+//     own the keyword; which read the position belongs to is found by a binary search in seq_off
+//     restricted to the reads that intersect the tile (host-computed tile_first[]); k-mers that
+//     would span a read boundary are rejected there -- the main loop carries no boundary logic.
+//   * (read, locus) occurrence counters live in a second open-addressing table (atomicCAS insert,
+//     atomicAdd count): exact for any number of loci per read; a full table is reported to the
+//     host, which retries with a larger one.  A compaction kernel emits the triples with
+//     count >= min_matches.
+// Integer / byte work: no tensor cores.  Per text byte the scan issues ~30 integer instructions,
+// so the bound is the integer issue rate, not HBM (bench: tools/kbench_filter.py).
+#pragma once
+#include "kernels_common.cuh"
+
+namespace {
+
+constexpr int kKfThreads = 256;
+constexpr int kKfPerThread = 80;
+constexpr int kKfTile = kKfThreads * kKfPerThread;      // 20,480 bytes of text per CTA
+constexpr int kKfMaxClasses = 16;                        // distinct keyword lengths per filter
+constexpr int kKfMaxK = 4096;                            // longest keyword (halo in shared memory)
+constexpr int kKfGroup = 8;                              // positions hashed before the first test
+constexpr unsigned long long kKfMul = 0x9E3779B97F4A7C15ull;
+constexpr unsigned long long kKfBase = 0x100000001B3ull; // rolling-hash base (odd)
+
+struct KfClass {
+    int k;
+    int exact;                       // 1: 3-bit packed key (k <= 21); 0: rolling hash + verification
+    unsigned long long key_mask;     // 3k low bits (exact)
+    unsigned long long salt;         // separates the classes in the shared tables
+    unsigned long long bk;           // kKfBase^k (rolling hash: weight of the symbol that leaves)
+};
+
+struct KfEntry {                     // 32 bytes = one sector per probe
+    unsigned long long key;
+    uint32_t loci_off, loci_cnt;     // loci_cnt == 0: empty slot
+    uint32_t text_off, cls;
+    unsigned long long pad;
+};
+
+struct DevKFilter {
+    int n_classes, halo;             // halo: bytes staged before a tile (multiple of 16, >= k_max - 1)
+    KfClass cls[kKfMaxClasses];
+    const uint32_t* bloom;
+    uint32_t bloom_shift, pad;       // word index = hash >> bloom_shift
+    const KfEntry* table;
+    unsigned long long table_mask;
+    const int32_t* loci;
+    const uint8_t* text;             // symbol codes of the hashed keywords (verification)
+};
+
+__host__ __device__ __forceinline__ int kf_code(unsigned char ch)
+{
+    return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
+}
+
+// -> a: 32 well-mixed bits (Bloom word, top bits first); m: the three Bloom bits; returns the full product
+__host__ __device__ __forceinline__ unsigned long long kf_hash(unsigned long long key, unsigned long long salt,
+                                                               uint32_t& a, uint32_t& m)
+{
+    const unsigned long long h = (key ^ salt) * kKfMul;
+    a = (uint32_t)(h >> 32);
+    const uint32_t b = (a ^ (uint32_t)h) * 0x85EBCA6Bu;
+    m = (1u << (b >> 27)) | (1u << ((b >> 22) & 31)) | (1u << ((b >> 17) & 31));
+    return h;
+}
+__host__ __device__ __forceinline__ unsigned long long kf_slot(unsigned long long h, unsigned long long mask)
+{
+    return (h >> 20) & mask;
+}
+
+// four ASCII bytes -> four symbol codes
+__device__ __forceinline__ uint32_t kf_codes4(uint32_t w)
+{
+    const uint32_t mA = __vcmpeq4(w, 0x41414141u), mC = __vcmpeq4(w, 0x43434343u);
+    const uint32_t mG = __vcmpeq4(w, 0x47474747u), mT = __vcmpeq4(w, 0x54545454u);
+    return (mC & 0x01010101u) | (mG & 0x02020202u) | (mT & 0x03030303u) | (~(mA | mC | mG | mT) & 0x04040404u);
+}
+
+struct KfScanArgs {
+    DevKFilter f;
+    const unsigned char* seqs;          // ASCII reads, back to back; 16-byte aligned, readable to the next multiple of 16
+    const int64_t* seq_off;             // [n_reads + 1]
+    const int32_t* tile_first;          // [n_tiles + 1]: read that owns the first byte of the tile; last = n_reads - 1
+    int64_t n_bases;
+    int32_t n_reads, pad;
+    unsigned long long* cnt_keys;       // (read << 32 | locus), ~0ull = empty
+    uint32_t* cnt_vals;
+    unsigned long long cnt_mask;
+    int32_t* overflow;                  // set to 1 when the counter table is full
+};
+
+__device__ __forceinline__ void kf_count(const KfScanArgs& a, int r, int32_t locus)
+{
+    const unsigned long long ck = ((unsigned long long)(uint32_t)r << 32) | (uint32_t)locus;
+    unsigned long long cs = (ck * kKfMul >> 17) & a.cnt_mask;
+    for (unsigned long long probes = 0; probes <= a.cnt_mask; ++probes) {
+        const unsigned long long old = atomicCAS(&a.cnt_keys[cs], ~0ull, ck);
+        if (old == ~0ull || old == ck) { atomicAdd(&a.cnt_vals[cs], 1u); return; }
+        cs = (cs + 1) & a.cnt_mask;
+    }
+    *a.overflow = 1;
+}
+
+// Bloom hits (bit j of `hits`: end position p_first + j) of class c: exact lookup, read lookup,
+// boundary check, counting.  The k-mer is re-read from shared memory, so the main loop keeps no
+// per-position state alive.
+__device__ __noinline__ void kf_slow_path(const KfScanArgs& a, int c, uint32_t hits, int64_t p_first,
+                                          const unsigned char* __restrict__ sm, int64_t base)
+{
+    const KfClass cl = a.f.cls[c];
+    const int k = cl.k;
+    for (; hits; hits &= hits - 1) {
+        const int64_t p = p_first + (__ffs(hits) - 1);
+        if (p >= a.n_bases || p - k + 1 < 0) continue;
+        const unsigned char* __restrict__ s = sm + (p - k + 1 - base);     // the k-mer's symbol codes
+        unsigned long long key = 0;
+        if (cl.exact) for (int j = 0; j < k; ++j) key = (key << 3) | s[j];
+        else          for (int j = 0; j < k; ++j) key = key * kKfBase + (s[j] + 1u);
+        uint32_t aa, mm;
+        const unsigned long long h = kf_hash(key, cl.salt, aa, mm);
+        unsigned long long slot = kf_slot(h, a.f.table_mask);
+        for (;;) {
+            const KfEntry* e = a.f.table + slot;
+            const uint32_t cnt = e->loci_cnt;
+            if (cnt == 0) break;                                           // empty slot: not a keyword
+            if (e->key == key && e->cls == (uint32_t)c) {
+                bool same = true;
+                if (!cl.exact) {
+                    const uint8_t* __restrict__ t = a.f.text + e->text_off;
+                    for (int j = 0; j < k && same; ++j) same = (s[j] == t[j]);
+                }
+                if (same) {
+                    // the read that owns position p: the last one with seq_off[r] <= p
+                    int lo = a.tile_first[blockIdx.x], hi = a.tile_first[blockIdx.x + 1];
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (a.seq_off[mid] <= p) lo = mid; else hi = mid - 1;
+                    }
+                    if (p - k + 1 >= a.seq_off[lo]) {                      // else it starts in the previous read
+                        const uint32_t off = e->loci_off;
+                        for (uint32_t j = 0; j < cnt; ++j) kf_count(a, lo, a.f.loci[off + j]);
+                    }
+                    break;                                                 // (keyword, class) is unique in the table
+                }
+            }
+            slot = (slot + 1) & a.f.table_mask;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kKfThreads) kfilter_scan_kernel(const __grid_constant__ KfScanArgs a)
+{
+    extern __shared__ __align__(16) unsigned char kf_smem[];
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const int halo = a.f.halo;
+    const int64_t tile0 = (int64_t)blockIdx.x * kKfTile;
+    const int64_t base = tile0 - halo;                          // text position of kf_smem[0]
+    const int64_t lo = base < 0 ? 0 : base;
+    const int64_t n16 = (a.n_bases + 15) & ~(int64_t)15;
+    const int64_t hi = tile0 + kKfTile < n16 ? tile0 + kKfTile : n16;
+    const uint32_t bytes = (uint32_t)(hi - lo);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, bytes);
+        tma_bulk_g2s(kf_smem + (lo - base), a.seqs + lo, bytes, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    {   // ASCII -> symbol codes, in place; consecutive threads take consecutive 16-byte chunks
+        uint4* v = reinterpret_cast<uint4*>(kf_smem + (lo - base));
+        for (uint32_t i = tid; i < bytes / 16; i += kKfThreads) {
+            uint4 w = v[i];
+            w.x = kf_codes4(w.x); w.y = kf_codes4(w.y); w.z = kf_codes4(w.z); w.w = kf_codes4(w.w);
+            v[i] = w;
+        }
+    }
+    __syncthreads();
+    const int64_t p0 = tile0 + (int64_t)tid * kKfPerThread;     // first end position of this thread
+    if (p0 >= a.n_bases) return;
+    const uint32_t* __restrict__ bloom = a.f.bloom;
+    const uint32_t bshift = a.f.bloom_shift;
+    const unsigned char* __restrict__ mine = kf_smem + halo + tid * kKfPerThread;
+    for (int c = 0; c < a.f.n_classes; ++c) {
+        const int k = a.f.cls[c].k;
+        const unsigned long long salt = a.f.cls[c].salt;
+        int back = k - 1;                                       // symbols before p0 that enter the first k-mer
+        if (back > p0) back = (int)p0;
+        if (a.f.cls[c].exact) {
+            const unsigned long long mask = a.f.cls[c].key_mask;
+            unsigned long long key = 0;
+            for (int j = -back; j < 0; ++j) key = (key << 3) | mine[j];
+#pragma unroll 1
+            for (int ch = 0; ch < kKfPerThread / 16; ++ch) {
+                const uint4 w4 = *reinterpret_cast<const uint4*>(mine + ch * 16);
+                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int g = 0; g < 16 / kKfGroup; ++g) {
+                    uint32_t words[kKfGroup], masks[kKfGroup];
+#pragma unroll
+                    for (int j = 0; j < kKfGroup; ++j) {
+                        const int b = g * kKfGroup + j;
+                        const uint32_t code = (w[b >> 2] >> ((b & 3) * 8)) & 0xffu;
+                        key = ((key << 3) | code) & mask;
+                        uint32_t aa;
+                        kf_hash(key, salt, aa, masks[j]);
+                        words[j] = __ldg(bloom + (aa >> bshift));
+                    }
+                    uint32_t hits = 0;
+#pragma unroll
+                    for (int j = 0; j < kKfGroup; ++j) hits |= ((words[j] & masks[j]) == masks[j] ? 1u : 0u) << j;
+                    if (hits) kf_slow_path(a, c, hits, p0 + ch * 16 + g * kKfGroup, kf_smem, base);
+                }
+            }
+        } else {
+            const unsigned long long bk = a.f.cls[c].bk;
+            unsigned long long key = 0;
+            int fed = 0;
+            for (int j = -back; j < 0; ++j, ++fed) key = key * kKfBase + (mine[j] + 1u);
+#pragma unroll 1
+            for (int j = 0; j < kKfPerThread; ++j) {
+                key = key * kKfBase + (mine[j] + 1u);
+                if (fed == k) key -= (mine[j - k] + 1u) * bk; else ++fed;
+                uint32_t aa, m;
+                kf_hash(key, salt, aa, m);
+                if ((__ldg(bloom + (aa >> bshift)) & m) == m) kf_slow_path(a, c, 1u, p0 + j, kf_smem, base);
+            }
+        }
+    }
+}
+
+struct KfCompactArgs {
+    const unsigned long long* cnt_keys;
+    const uint32_t* cnt_vals;
+    unsigned long long cnt_size;
+    int32_t min_matches;
+    int32_t* hit_read;
+    int32_t* hit_locus;
+    int32_t* hit_count;
+    long long hit_cap;
+    unsigned long long* n_hits;
+};
+
+__global__ void __launch_bounds__(256) kfilter_compact_kernel(const KfCompactArgs a)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.cnt_size) return;
+    const unsigned long long key = a.cnt_keys[i];
+    if (key == ~0ull) return;
+    const uint32_t c = a.cnt_vals[i];
+    if ((int32_t)c < a.min_matches) return;
+    const unsigned long long o = atomicAdd(a.n_hits, 1ull);
+    if ((long long)o < a.hit_cap) {
+        a.hit_read[o] = (int32_t)(key >> 32);
+        a.hit_locus[o] = (int32_t)(key & 0xffffffffu);
+        a.hit_count[o] = (int32_t)c;
+    }
+}
+
+}  // namespace

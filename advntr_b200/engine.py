@@ -27,6 +27,7 @@ EXPORTS = (
     "advhmm_model_create", "advhmm_model_destroy", "advhmm_model_info_get",
     "advhmm_viterbi_batch", "advhmm_log_probability_batch", "advhmm_viterbi_multi",
     "advhmm_viterbi_multi_summary", "advhmm_model_set_state_classes",
+    "advhmm_kfilter_create", "advhmm_kfilter_destroy", "advhmm_kfilter_scan",
     "advhmm_last_error", "advhmm_abi_version", "advhmm_encode_acgt",
 )
 
@@ -85,6 +86,10 @@ def load_library():
         lib.advhmm_viterbi_multi.argtypes = [vp, vp, i32, vp, vp, vp, i32, u32, vp, vp, vp, vp, i64, vp]
         lib.advhmm_viterbi_multi_summary.argtypes = [vp, vp, i32, vp, vp, vp, i32, u32, vp, vp, vp, vp, i64, vp, vp]
         lib.advhmm_model_set_state_classes.argtypes = [vp, vp]
+        lib.advhmm_kfilter_create.argtypes = [vp, i64, C.c_char_p, vp, vp, C.POINTER(vp)]
+        lib.advhmm_kfilter_destroy.argtypes = [vp]
+        lib.advhmm_kfilter_destroy.restype = None
+        lib.advhmm_kfilter_scan.argtypes = [vp, vp, vp, i32, i32, u32, vp, vp, vp, i64, vp]
         lib.advhmm_last_error.restype = C.c_char_p
         lib.advhmm_abi_version.restype = C.c_int
         lib.advhmm_encode_acgt.argtypes = [C.c_char_p, i64, vp]
@@ -328,6 +333,57 @@ class DeviceModel(object):
         _check(self._lib.advhmm_log_probability_batch(self._h, seqs.ctypes.data, off.ctypes.data, R, 0,
                                                       logp.ctypes.data))
         return logp
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceKeywordFilter(object):
+    """Keywords (any mix of lengths) on one context (``advhmm_kfilter``)."""
+
+    def __init__(self, ctx, keywords, locus_ids):
+        self._lib = load_library()
+        self.ctx = ctx
+        raw = "".join(keywords).encode("ascii", "replace")
+        off = np.zeros(len(keywords) + 1, dtype=np.int64)
+        if len(keywords):
+            np.cumsum(np.fromiter(map(len, keywords), dtype=np.int64, count=len(keywords)), out=off[1:])
+        ids = np.ascontiguousarray(locus_ids, dtype=np.int32)
+        if len(ids) != len(keywords):
+            raise ValueError("one locus id per keyword")
+        h = C.c_void_p()
+        _check(self._lib.advhmm_kfilter_create(ctx._h, len(keywords), raw, off.ctypes.data, ids.ctypes.data, C.byref(h)))
+        self._h = h
+
+    def scan(self, flat, off, min_matches):
+        """flat: ASCII bytes of all reads back to back (uint8 array); off: int64 offsets.  Returns
+        the arrays (read index, locus id, occurrences) of the pairs with occurrences >= min_matches."""
+        R = len(off) - 1
+        cap = max(1024, 2 * R)
+        total = C.c_int64(0)
+        while True:
+            hr, hl, hc = (np.empty(cap, dtype=np.int32) for _ in range(3))
+            rc = self._lib.advhmm_kfilter_scan(self._h, flat.ctypes.data, off.ctypes.data, R, int(min_matches), 0,
+                                               hr.ctypes.data, hl.ctypes.data, hc.ctypes.data, cap, C.byref(total))
+            if rc == ECAPACITY and total.value > cap:
+                cap = int(total.value) + 16
+                continue
+            _check(rc)
+            n = int(total.value)
+            return hr[:n], hl[:n], hc[:n]
+
+    def scan_device(self, d_seqs_ptr, off, min_matches, d_hit_read, d_hit_locus, d_hit_count, cap, d_n_hits):
+        """Device-resident form (``ADVHMM_DEVICE_BUFFERS``): raw device pointers, results stay on the device."""
+        _check(self._lib.advhmm_kfilter_scan(self._h, d_seqs_ptr, off.ctypes.data, len(off) - 1, int(min_matches),
+                                             DEVICE_BUFFERS, d_hit_read, d_hit_locus, d_hit_count, int(cap), d_n_hits))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self._lib.advhmm_kfilter_destroy(self._h)
+        self._h = None
 
     def __del__(self):
         try:

@@ -179,3 +179,31 @@ def config2_read_codes(locus, coverage=30, decoys=50, seed=None):
         reads.append(revcomp_codes(d))
     lengths = np.fromiter((len(r) for r in reads), dtype=np.int64, count=len(reads))
     return np.concatenate(reads), lengths
+
+
+def kfilter_case(n_loci=30, reads_per_locus=8, decoys=400, seed=77, keyword_size=15):
+    """Input of the keyword pre-filter parity case: keywords of config-2 loci as
+    ``genome_analyzer.py:181`` writes them (keyword_size=15) + unmapped reads: locus reads on either
+    strand and random decoys, a few with N and with lower-case stretches.
+    -> (keywords_by_locus, names, seqs)."""
+    from . import keyword_filter
+    rng = random.Random(seed)
+    loci = [config2_locus(i) for i in range(1, n_loci + 1)]
+    kw = [(l.id, sorted(keyword_filter.get_keywords_for_filtering(l.left, l.right, l.segments, l.pattern,
+                                                                   keyword_size=keyword_size))) for l in loci]
+    names, seqs = [], []
+    for l in loci:
+        for _ in range(reads_per_locus):
+            s = rng.randrange(300, 560)
+            r = sequencing_errors(rng, l.sequence[s:s + 158], 0.01, 0.001, 0.001)[:150]
+            if rng.random() < 0.5:
+                r = revcomp(r)
+            if rng.random() < 0.1:
+                p = rng.randrange(len(r))
+                r = r[:p] + "N" + r[p + 1:]
+            if rng.random() < 0.05:
+                r = r[:40] + r[40:60].lower() + r[60:]
+            names.append("r%d" % len(names)); seqs.append(r)
+    for _ in range(decoys):
+        names.append("r%d" % len(names)); seqs.append(rand_dna(rng, 150))
+    return kw, names, seqs

@@ -186,6 +186,31 @@ int advhmm_viterbi_multi_summary(advhmm_context* ctx,
                                  int32_t* path, int64_t path_cap, int64_t* path_total,
                                  advhmm_read_summary* summaries);
 
+/* ---- keyword pre-filter (the step before the hot path) ----------------------------------------
+ * Replaces the Aho-Corasick scan of the `adVNTR-Filtering` binary (filtering/main.cc:229-300,
+ * fed by genome_analyzer.py:173-197): count, for every read and locus, the occurrences of the
+ * locus's keywords in the read.  Keyword i = keywords[keyword_off[i] .. keyword_off[i+1]), any
+ * length from 1 to 4096, at most 16 distinct lengths per filter (adVNTR writes 15-mers for short
+ * reads and two 80-mers per locus for long reads, vntr_finder.py:140-154); keywords and reads are
+ * ASCII, anything but upper-case ACGT is the reference's fifth symbol (main.cc:43-54).
+ * keyword_locus[i] is any caller-chosen int32 id of the locus that owns keyword i (the same keyword
+ * may be listed for several loci; listing it twice for one locus counts twice, as two words of the
+ * reference's machine would).
+ * scan(): reads back to back, read r = seqs[seq_off[r] .. seq_off[r+1]).  Returns the triples
+ * (read index, locus id, occurrences) with occurrences >= min_matches, in unspecified order;
+ * *n_hits = number of triples (or needed, with ADVHMM_ECAPACITY).  The per-locus cap / ordering /
+ * output format of main.cc:283-332 is host logic (advntr_b200/keyword_filter.py).
+ * With ADVHMM_DEVICE_BUFFERS seqs, hit_* and n_hits are device pointers (seq_off stays a host
+ * array); seqs must be 16-byte aligned and readable up to the next multiple of 16 bytes. */
+typedef struct advhmm_kfilter advhmm_kfilter;
+int  advhmm_kfilter_create(advhmm_context* ctx, int64_t n_keywords, const char* keywords,
+                           const int64_t* keyword_off, const int32_t* keyword_locus, advhmm_kfilter** out);
+void advhmm_kfilter_destroy(advhmm_kfilter* kf);
+int  advhmm_kfilter_scan(advhmm_kfilter* kf, const char* seqs, const int64_t* seq_off, int32_t n_reads,
+                         int32_t min_matches, uint32_t flags,
+                         int32_t* hit_read, int32_t* hit_locus, int32_t* hit_count,
+                         int64_t hit_cap, int64_t* n_hits);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* advhmm_last_error(void);
 int         advhmm_abi_version(void);

@@ -154,7 +154,33 @@ def make_callsite_case(pom):
         seen["cnt"]))
 
 
+def make_kfilter_case():
+    """stdout of the reference's adVNTR-Filtering binary (filtering/main.cc, compiled unmodified)."""
+    import subprocess, tempfile, gzip
+    import build_ref
+    assert build_ref.build_filter()
+    kw, names, seqs = synth.kfilter_case()
+    with tempfile.TemporaryDirectory() as d:
+        fa, kf = os.path.join(d, "reads.fa"), os.path.join(d, "kw.txt")
+        with open(fa, "w") as fh:
+            for n, s in zip(names, seqs):
+                fh.write(">%s\n%s\n" % (n, s))
+        with open(kf, "w") as fh:
+            for vid, words in kw:
+                fh.write("%d %s\n" % (vid, " ".join(words)))
+        out = {}
+        for mm in (5, 2):
+            res = subprocess.run([build_ref.FILTER_BIN, fa, "--min_matches", str(mm)], stdin=open(kf),
+                                 capture_output=True, text=True, check=True)
+            out[str(mm)] = res.stdout
+    with gzip.open(os.path.join(HERE, "kfilter_reference_stdout.json.gz"), "wt") as fh:
+        json.dump(out, fh)
+    print("kfilter: %d loci, %d reads, %d output lines (min 5), %d (min 2)" % (
+        len(kw), len(names), out["5"].count("\n"), out["2"].count("\n")))
+
+
 def main():
+    make_kfilter_case()
     pom = refenv.reference_pomegranate()
     hu = refenv.reference_hmm_utils(pom, "ref")
     settings = refenv.reference_settings()
