@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(256) fp64_add_peak_kernel(double* out, int ite
 struct advhmm_kfilter {
     advhmm_context* ctx = nullptr;
     DevKFilter dev{};
-    DevBuf tables, seqs, meta, counters, hits;
+    DevBuf tables, seqs, meta, tiles, counters, hits;
     int64_t n_keywords = 0, n_unique = 0;
 };
 
@@ -820,38 +820,25 @@ int kfilter_build(advhmm_kfilter* kf, int64_t n, const char* words, const int64_
     return ADVHMM_OK;
 }
 
-// d_seqs and the hit arrays are device pointers; seq_off is the host copy of the offsets (also
-// uploaded); d_n_hits a device counter.  Queues scan + compaction on the context's stream; the only
-// host synchronisation is the read-back of the "counter table full" flag.
-int kfilter_scan_device(advhmm_kfilter* kf, const unsigned char* d_seqs, const int64_t* seq_off, int n_reads,
-                        int min_matches, int32_t* d_hit_read, int32_t* d_hit_locus, int32_t* d_hit_count,
-                        int64_t hit_cap, unsigned long long* d_n_hits)
+// d_seqs, d_off and the hit arrays are device pointers; d_n_hits a device counter.  Queues tile
+// index + scan + compaction on the context's stream; the only host synchronisation is the
+// read-back of the "counter table full" flag.
+int kfilter_scan_device(advhmm_kfilter* kf, const unsigned char* d_seqs, const int64_t* d_off, int n_reads,
+                        int64_t n_bases, int min_matches, int32_t* d_hit_read, int32_t* d_hit_locus,
+                        int32_t* d_hit_count, int64_t hit_cap, unsigned long long* d_n_hits)
 {
     advhmm_context* ctx = kf->ctx;
-    const int64_t n_bases = n_reads > 0 ? seq_off[n_reads] : 0;
     CU_TRY(cudaMemsetAsync(d_n_hits, 0, sizeof(unsigned long long), ctx->stream));
     if (n_bases <= 0 || kf->dev.n_classes == 0) return ADVHMM_OK;
     if (reinterpret_cast<uintptr_t>(d_seqs) % 16)
         return set_error(ADVHMM_EINVAL, "keyword filter: the device read buffer must be 16-byte aligned");
-    // which read owns the first byte of every tile (the last read with seq_off[r] <= tile start)
+    // which read owns the first byte of every tile
     const int64_t n_tiles = (n_bases + kKfTile - 1) / kKfTile;
-    std::vector<int32_t> tile_first((size_t)n_tiles + 1);
-    {
-        int32_t r = 0;
-        for (int64_t t = 0; t < n_tiles; ++t) {
-            const int64_t p = t * kKfTile;
-            while (r + 1 < n_reads && seq_off[r + 1] <= p) ++r;
-            tile_first[(size_t)t] = r;
-        }
-        tile_first[(size_t)n_tiles] = n_reads - 1;
-    }
-    const size_t off_bytes = ((size_t)(n_reads + 1) * 8 + 255) / 256 * 256;
-    CU_TRY(kf->meta.ensure(off_bytes + (size_t)(n_tiles + 1) * 4));
-    int64_t* d_off = kf->meta.as<int64_t>();
-    int32_t* d_tile = reinterpret_cast<int32_t*>(kf->meta.as<unsigned char>() + off_bytes);
-    CU_TRY(cudaMemcpyAsync(d_off, seq_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(d_tile, tile_first.data(), (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));      // tile_first is a stack-owned vector
+    CU_TRY(kf->tiles.ensure((size_t)(n_tiles + 1) * 4));
+    int32_t* d_tile = kf->tiles.as<int32_t>();
+    kfilter_tile_index_kernel<<<(unsigned)((n_tiles + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_off, n_reads, n_tiles, d_tile);
+    CU_TRY(cudaGetLastError());
+    ctx->launches++;
     const size_t smem = (size_t)kf->dev.halo + kKfTile;
     unsigned long long cap = next_pow2(std::max<unsigned long long>(1 << 16, (unsigned long long)n_reads / 2));
     for (int attempt = 0; attempt < 10; ++attempt, cap <<= 2) {
@@ -863,7 +850,10 @@ int kfilter_scan_device(advhmm_kfilter* kf, const unsigned char* d_seqs, const i
         CU_TRY(cudaMemsetAsync(ck, 0xff, (size_t)cap * 8, ctx->stream));
         CU_TRY(cudaMemsetAsync(cv, 0, (size_t)cap * 4 + 64, ctx->stream));
         KfScanArgs sa{kf->dev, d_seqs, d_off, d_tile, n_bases, n_reads, 0, ck, cv, cap - 1, ovf};
-        kfilter_scan_kernel<<<(unsigned)n_tiles, kKfThreads, smem, ctx->stream>>>(sa);
+        {
+            ProfScope prof(ctx, 0);
+            kfilter_scan_kernel<<<(unsigned)n_tiles, kKfThreads, smem, ctx->stream>>>(sa);
+        }
         CU_TRY(cudaGetLastError());
         ctx->launches++;
         int32_t overflow = 0;
@@ -1150,7 +1140,7 @@ void advhmm_kfilter_destroy(advhmm_kfilter* kf)
     if (kf->ctx && kf->ctx->device >= 0) {
         cudaSetDevice(kf->ctx->device);
         cudaStreamSynchronize(kf->ctx->stream);
-        for (DevBuf* b : {&kf->tables, &kf->seqs, &kf->meta, &kf->counters, &kf->hits}) b->release();
+        for (DevBuf* b : {&kf->tables, &kf->seqs, &kf->meta, &kf->tiles, &kf->counters, &kf->hits}) b->release();
     }
     delete kf;
 }
@@ -1162,22 +1152,35 @@ int advhmm_kfilter_scan(advhmm_kfilter* kf, const char* seqs, const int64_t* seq
     if (!kf || (n_reads > 0 && !seq_off) || n_reads < 0 || !n_hits || hit_cap < 0 ||
         (hit_cap > 0 && (!hit_read || !hit_locus || !hit_count)))
         return set_error(ADVHMM_EINVAL, "null or negative argument");
-    if (n_reads > 0) {
-        if (seq_off[0] != 0) return set_error(ADVHMM_EINVAL, "seq_off[0] must be 0");
-        for (int32_t r = 0; r < n_reads; ++r)
-            if (seq_off[r + 1] < seq_off[r]) return set_error(ADVHMM_EINVAL, "seq_off must be non-decreasing");
-        if (seq_off[n_reads] > 0 && !seqs) return set_error(ADVHMM_EINVAL, "null read buffer");
-    }
+    if ((flags & ADVHMM_DEVICE_OFFSETS) && !(flags & ADVHMM_DEVICE_BUFFERS))
+        return set_error(ADVHMM_EINVAL, "ADVHMM_DEVICE_OFFSETS needs ADVHMM_DEVICE_BUFFERS");
     advhmm_context* ctx = kf->ctx;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU_TRY(cudaSetDevice(ctx->device));
+    const int64_t* d_off = nullptr;
+    int64_t n_bases = 0;
+    if (flags & ADVHMM_DEVICE_OFFSETS) {
+        d_off = seq_off;
+        if (n_reads > 0) {
+            CU_TRY(cudaMemcpyAsync(&n_bases, seq_off + n_reads, sizeof n_bases, cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+    } else if (n_reads > 0) {
+        if (seq_off[0] != 0) return set_error(ADVHMM_EINVAL, "seq_off[0] must be 0");
+        for (int32_t r = 0; r < n_reads; ++r)
+            if (seq_off[r + 1] < seq_off[r]) return set_error(ADVHMM_EINVAL, "seq_off must be non-decreasing");
+        n_bases = seq_off[n_reads];
+        if (n_bases > 0 && !seqs) return set_error(ADVHMM_EINVAL, "null read buffer");
+        CU_TRY(kf->meta.ensure((size_t)(n_reads + 1) * 8));
+        CU_TRY(cudaMemcpyAsync(kf->meta.p, seq_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_off = kf->meta.as<int64_t>();
+    }
     if (flags & ADVHMM_DEVICE_BUFFERS)
-        // seqs, hit_* and n_hits are device pointers; seq_off stays a host array
-        return kfilter_scan_device(kf, reinterpret_cast<const unsigned char*>(seqs), seq_off, n_reads, min_matches,
+        // seqs, hit_* and n_hits are device pointers
+        return kfilter_scan_device(kf, reinterpret_cast<const unsigned char*>(seqs), d_off, n_reads, n_bases, min_matches,
                                    hit_read, hit_locus, hit_count, hit_cap, reinterpret_cast<unsigned long long*>(n_hits));
     *n_hits = 0;
     if (n_reads == 0) return ADVHMM_OK;
-    const int64_t n_bases = seq_off[n_reads];
     CU_TRY(kf->seqs.ensure((size_t)n_bases + 16));
     if (n_bases) CU_TRY(cudaMemcpyAsync(kf->seqs.p, seqs, (size_t)n_bases, cudaMemcpyHostToDevice, ctx->stream));
     const size_t hb = ((size_t)std::max<int64_t>(hit_cap, 1) * 4 + 255) / 256 * 256;
@@ -1187,7 +1190,7 @@ int advhmm_kfilter_scan(advhmm_kfilter* kf, const char* seqs, const int64_t* seq
     int32_t* d_l = reinterpret_cast<int32_t*>(dh + hb);
     int32_t* d_c = reinterpret_cast<int32_t*>(dh + 2 * hb);
     unsigned long long* d_n = reinterpret_cast<unsigned long long*>(dh + 3 * hb);
-    int rc = kfilter_scan_device(kf, kf->seqs.as<unsigned char>(), seq_off, n_reads, min_matches,
+    int rc = kfilter_scan_device(kf, kf->seqs.as<unsigned char>(), d_off, n_reads, n_bases, min_matches,
                                  d_r, d_l, d_c, hit_cap, d_n);
     if (rc) return rc;
     unsigned long long total = 0;

@@ -250,6 +250,26 @@ __global__ void __launch_bounds__(kKfThreads) kfilter_scan_kernel(const __grid_c
     }
 }
 
+// tile_first[t] = the read that owns text position t * kKfTile (the last r with seq_off[r] <= p);
+// tile_first[n_tiles] = n_reads - 1
+__global__ void __launch_bounds__(256) kfilter_tile_index_kernel(const int64_t* __restrict__ seq_off, int n_reads,
+                                                                 int64_t n_tiles, int32_t* __restrict__ tile_first)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    int lo = 0, hi = n_reads - 1;
+    if (t < n_tiles) {
+        const int64_t p = t * kKfTile;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seq_off[mid] <= p) lo = mid; else hi = mid - 1;
+        }
+    } else {
+        lo = hi;
+    }
+    tile_first[t] = lo;
+}
+
 struct KfCompactArgs {
     const unsigned long long* cnt_keys;
     const uint32_t* cnt_vals;

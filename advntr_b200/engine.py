@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ADVHMM_LIB") or os.path.join(_PKG, "libadvhmm.so")
 
 OK, EINVAL, ECUDA, ENOMEM, ESYMBOL, ECAPACITY, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-WANT_PATH, BOTH_STRANDS, FP32, FORCE_GENERIC, WANT_SUMMARY, DEVICE_BUFFERS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x100
+WANT_PATH, BOTH_STRANDS, FP32, FORCE_GENERIC, WANT_SUMMARY, DEVICE_BUFFERS, DEVICE_OFFSETS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x100, 0x200
 SUMMARY_DTYPE = np.dtype([(n, np.int32) for n in ("repeats", "n_match", "repeat_bp", "left_bp", "right_bp",
                                                    "left_hits", "right_hits", "unit_starts_ends")])
 KIND_GENERIC, KIND_BANDED = 0, 1
@@ -375,10 +375,17 @@ class DeviceKeywordFilter(object):
             n = int(total.value)
             return hr[:n], hl[:n], hc[:n]
 
-    def scan_device(self, d_seqs_ptr, off, min_matches, d_hit_read, d_hit_locus, d_hit_count, cap, d_n_hits):
-        """Device-resident form (``ADVHMM_DEVICE_BUFFERS``): raw device pointers, results stay on the device."""
-        _check(self._lib.advhmm_kfilter_scan(self._h, d_seqs_ptr, off.ctypes.data, len(off) - 1, int(min_matches),
-                                             DEVICE_BUFFERS, d_hit_read, d_hit_locus, d_hit_count, int(cap), d_n_hits))
+    def scan_device(self, d_seqs_ptr, off, n_reads, min_matches, d_hit_read, d_hit_locus, d_hit_count, cap, d_n_hits):
+        """Device-resident form (``ADVHMM_DEVICE_BUFFERS``): raw device pointers, results stay on the
+        device.  ``off``: host int64 array, or an int (device pointer, ``ADVHMM_DEVICE_OFFSETS``)."""
+        flags = DEVICE_BUFFERS
+        if isinstance(off, int):
+            flags |= DEVICE_OFFSETS
+            off_ptr = off
+        else:
+            off_ptr = off.ctypes.data
+        _check(self._lib.advhmm_kfilter_scan(self._h, d_seqs_ptr, off_ptr, int(n_reads), int(min_matches),
+                                             flags, d_hit_read, d_hit_locus, d_hit_count, int(cap), d_n_hits))
 
     def close(self):
         if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):

@@ -201,7 +201,10 @@ int advhmm_viterbi_multi_summary(advhmm_context* ctx,
  * *n_hits = number of triples (or needed, with ADVHMM_ECAPACITY).  The per-locus cap / ordering /
  * output format of main.cc:283-332 is host logic (advntr_b200/keyword_filter.py).
  * With ADVHMM_DEVICE_BUFFERS seqs, hit_* and n_hits are device pointers (seq_off stays a host
- * array); seqs must be 16-byte aligned and readable up to the next multiple of 16 bytes. */
+ * array unless ADVHMM_DEVICE_OFFSETS is set as well: then it is a device array too and nothing but
+ * eight bytes crosses the bus); seqs must be 16-byte aligned and readable up to the next multiple
+ * of 16 bytes. */
+#define ADVHMM_DEVICE_OFFSETS 0x200u
 typedef struct advhmm_kfilter advhmm_kfilter;
 int  advhmm_kfilter_create(advhmm_context* ctx, int64_t n_keywords, const char* keywords,
                            const int64_t* keyword_off, const int32_t* keyword_locus, advhmm_kfilter** out);

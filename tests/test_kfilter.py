@@ -193,3 +193,33 @@ def test_device_filter_per_locus_cap(ctx):
         kfilter_oracle.filter_output(kw, names, seqs, min_matches=1, max_reads=7)
     assert [len(shown) for _, _, shown in per_locus] == [8, 8] and [c for _, c, _ in per_locus] == [7, 7]
     kf.close()
+
+
+@pytest.mark.gpu
+def test_device_resident_scan_equals_host_scan(ctx):
+    """ADVHMM_DEVICE_BUFFERS (+ ADVHMM_DEVICE_OFFSETS): reads, offsets and the triples stay on the device."""
+    import torch
+    from advntr_b200 import keyword_filter
+    kw, names, seqs = synth.kfilter_case(n_loci=40, reads_per_locus=20, decoys=3000, seed=5)
+    kf = keyword_filter.KeywordFilter(kw, ctx=ctx)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    flat = np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8)
+    hr, hl, hc = kf.filter.scan(flat, off, 3)
+    want = sorted(zip(hr.tolist(), hl.tolist(), hc.tolist()))
+    assert len(want) > 100
+    d_seqs = torch.zeros(len(flat) + 16, dtype=torch.uint8, device="cuda")
+    d_seqs[:len(flat)] = torch.from_numpy(flat.copy())
+    d_off = torch.from_numpy(off).cuda()
+    cap = 4 * len(want)
+    d_r, d_l, d_c = (torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(3))
+    d_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for offsets in (off, d_off.data_ptr()):
+        d_n.zero_()
+        kf.filter.scan_device(d_seqs.data_ptr(), offsets, len(seqs), 3, d_r.data_ptr(), d_l.data_ptr(),
+                              d_c.data_ptr(), cap, d_n.data_ptr())
+        ctx.synchronize()
+        n = int(d_n.item())
+        got = sorted(zip(d_r[:n].tolist(), d_l[:n].tolist(), d_c[:n].tolist()))
+        assert got == want
+    kf.close()
