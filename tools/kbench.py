@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from advntr_b200 import engine
+if os.environ.get('ADVHMM_LIB'):
+    engine.LIB_PATH = os.path.abspath(os.environ['ADVHMM_LIB'])
 n_loci = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 wl = bench.build_workload(0, n_loci, 30, 50)
@@ -33,6 +35,6 @@ for _ in range(steps): step(F)
 e1.record(stream); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 fm, fn, bm, bn = ctx.profile_read()
-print("prec=%s WPB=%s ICMP=%s loci=%d reads=%d: step %.2f ms (%.2f Mreads/s, %.0f GCUPS) fill %.2f ms/step (%d launches) backtrack %.2f ms/step | logp checksum %r" % (
-    os.environ.get("ADVHMM_PRECISION", "fp64"), os.environ.get("ADVHMM_WPB", "8"), os.environ.get("ADVHMM_ICMP", "0"), n_loci, R, ms, R / ms / 1e3, wl["cells"] / ms / 1e6,
+print("lib=%s prec=%s WPB=%s ICMP=%s loci=%d reads=%d: step %.2f ms (%.2f Mreads/s, %.0f GCUPS) fill %.2f ms/step (%d launches) backtrack %.2f ms/step | logp checksum %r" % (
+    os.path.basename(engine.LIB_PATH), os.environ.get("ADVHMM_PRECISION", "fp64"), os.environ.get("ADVHMM_WPB", "8"), os.environ.get("ADVHMM_ICMP", "0"), n_loci, R, ms, R / ms / 1e3, wl["cells"] / ms / 1e6,
     fm / steps, fn // steps, bm / steps, float(d_logp.sum().item())))
