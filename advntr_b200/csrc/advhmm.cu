@@ -51,14 +51,17 @@ struct BlobBuilder {
 };
 
 // forward-algorithm row 0 (hmm.pyx:1402-1424): same closure as Viterbi's with pair_lse
+double host_pair_lse(double x, double y)       // utils.pyx:72-90
+{
+    if (x == kNegInf) return y;
+    if (y == kNegInf) return x;
+    if (x > y) return x + std::log(std::exp(y - x) + 1.0);
+    return y + std::log(std::exp(x - y) + 1.0);
+}
+
 std::vector<double> forward_row0(const GenericTables& g)
 {
-    auto lse = [](double x, double y) {
-        if (x == kNegInf) return y;
-        if (y == kNegInf) return x;
-        if (x > y) return x + std::log(std::exp(y - x) + 1.0);
-        return y + std::log(std::exp(x - y) + 1.0);
-    };
+    auto lse = host_pair_lse;
     std::vector<double> f(g.m, kNegInf);
     f[g.start] = 0.0;
     for (int l = g.S; l < g.m; ++l) {
@@ -89,7 +92,7 @@ int upload_model(advhmm_model* mod)
     const size_t o_f0 = bb.add(f0);
     // banded tables
     size_t o_image = 0, o_st = 0, o_tb1 = 0, o_acc = 0, o_fs = 0, o_fo = 0, o_fsrc = 0, o_fw = 0;
-    size_t o_image_f = 0, o_tb1f = 0, o_tb0f = 0, o_fwf = 0;
+    size_t o_image_f = 0, o_tb1f = 0, o_tb0f = 0, o_fwf = 0, o_f1 = 0;
     int image_bytes = 0, image_f_bytes = 0;
     if (b.valid) {
         const size_t P = b.NCpad;
@@ -108,6 +111,15 @@ int upload_model(advhmm_model* mod)
         }
         image_bytes = (int)image.size();
         o_image = bb.add(image);
+        // forward first-row table: emitting states of row 1 from the forward row 0 (hmm.pyx:1427-1444)
+        std::vector<double> f1(8 * P, kNegInf);
+        for (int l = 0; l < g.S; ++l) {
+            double acc = kNegInf;
+            for (int k = g.in_off[l]; k < g.in_off[l + 1]; ++k) acc = host_pair_lse(acc, f0[g.in_src[k]] + g.in_w[k]);
+            const int sl = b.slot_of[l] == SLOT_I ? 0 : 1;
+            for (int x = 0; x < 4; ++x) f1[((size_t)x * P + b.col_of[l]) * 2 + sl] = acc + g.emis[(size_t)l * 4 + x];
+        }
+        o_f1 = bb.add(f1);
         std::vector<int32_t> st(3 * (size_t)b.NC);
         for (int t = 0; t < 3; ++t) memcpy(st.data() + (size_t)t * b.NC, b.st[t].data(), sizeof(int32_t) * b.NC);
         o_st = bb.add(st); o_tb1 = bb.add(b.tb1); o_acc = bb.add(b.acc_src_col);
@@ -187,6 +199,8 @@ int upload_model(advhmm_model* mod)
         db.tb1_f = (const int32_t*)P8(o_tb1f); db.tb0_f = (const int32_t*)P8(o_tb0f);
         db.fin_w_f = (const float*)P8(o_fwf);
         db.classes = (const uint8_t*)P8(o_cls);
+        db.f1 = (const double*)P8(o_f1);
+        db.logp_empty_fwd = f0[g.end];
         memcpy(bb.bytes.data() + o_db, &db, sizeof db);
     }
     CU_TRY(cudaMemcpyAsync(base, bb.bytes.data(), bb.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -272,6 +286,29 @@ int launch_banded_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const 
     return ADVHMM_OK;
 }
 
+int launch_banded_fwd_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const BandedArgs& args)
+{
+    ProfScope prof(ctx, 0);
+#define ADV_CASE(R)                                                                                   \
+    case R:                                                                                           \
+        if (smem > ctx->banded_fwd_smem_set[R]) {                                                     \
+            CU_TRY(cudaFuncSetAttribute(banded_forward_kernel<R, 8>,                                  \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
+            ctx->banded_fwd_smem_set[R] = smem;                                                       \
+        }                                                                                             \
+        banded_forward_kernel<R, 8><<<grid, 8 * 32, smem, ctx->stream>>>(args);                       \
+        break;
+    switch (rpl) {
+        ADV_CASE(1) ADV_CASE(2) ADV_CASE(3) ADV_CASE(4) ADV_CASE(5)
+        ADV_CASE(6) ADV_CASE(7) ADV_CASE(8) ADV_CASE(9) ADV_CASE(10)
+        default: return set_error(ADVHMM_EINVAL, "unsupported rows-per-lane %d", rpl);
+    }
+#undef ADV_CASE
+    CU_TRY(cudaGetLastError());
+    ctx->launches++;
+    return ADVHMM_OK;
+}
+
 int launch_banded_f32_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const BandedArgs& args)
 {
     ProfScope prof(ctx, 0);
@@ -338,7 +375,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         if (!mod || mod->ctx != ctx) return set_error(ADVHMM_EINVAL, "model %d does not belong to this context", gi);
         const int64_t r0 = group_off[gi], r1 = group_off[gi + 1];
         if (r0 < 0 || r1 < r0 || r1 > n_reads) return set_error(ADVHMM_EINVAL, "bad group_off at model %d", gi);
-        const bool banded = !forward && mod->d_banded && !(flags & ADVHMM_FORCE_GENERIC);
+        const bool banded = mod->d_banded && !(flags & ADVHMM_FORCE_GENERIC);
         for (int64_t r = r0; r < r1; ++r) {
             const int len = (int)(seq_off[r + 1] - seq_off[r]);
             Family* f = &fam_generic;
@@ -348,13 +385,12 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
                     pl.max_P_short = std::max(pl.max_P_short, mod->cm.b.NCpad);
                     pl.max_smem_short = std::max(pl.max_smem_short, mod->banded_smem);
                     all_nonpositive = all_nonpositive && mod->cm.b.nonpositive;
-                } else {
+                } else if (!forward) {
                     f = &fam_long;
                     pl.max_P_long = std::max(pl.max_P_long, mod->cm.b.NCpad);
-                }
-            } else {
-                pl.max_m_generic = std::max(pl.max_m_generic, mod->cm.g.m);
+                }                                   // forward of long reads: generic kernel
             }
+            if (f == &fam_generic) pl.max_m_generic = std::max(pl.max_m_generic, mod->cm.g.m);
             f->max_len = std::max(f->max_len, len);
             for (int s = 0; s < strands; ++s) {
                 f->items.push_back((int32_t)(r * strands + s));
@@ -519,8 +555,9 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         fa.acc_tb = reinterpret_cast<uint16_t*>(w + so_acc); fa.acc_stride = 32 * rpl;
         fa.vfin = reinterpret_cast<double*>(w + so_vfin); fa.vfin_stride = 3 * Ps;
         fa.ftb = reinterpret_cast<int32_t*>(w + so_ftb);
-        int rc = fp32 ? launch_banded_f32_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa)
-                      : launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa);
+        int rc = forward ? launch_banded_fwd_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa)
+                 : fp32  ? launch_banded_f32_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa)
+                         : launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa);
         if (rc) return rc;
         if (want_walk) {
             rc = launch_backtrack(lo, hi - lo, rpl, fa.tbw, fa.tbw_stride, fa.acc_tb, (size_t)fa.acc_stride, fa.ftb);

@@ -115,6 +115,9 @@ struct DevBanded {
     const int32_t* tb0_f;
     const float* fin_w_f;
     const uint8_t* classes;       // [m]
+    // forward (log_probability): first-row table [sym][P]{I, M} evaluated with pair_lse, value of the empty read
+    const double* f1;
+    double logp_empty_fwd;
 };
 
 struct Tile {
@@ -150,6 +153,7 @@ struct advhmm_context {
     bool launch_int_compare = false;   // ... and every model of the current batch qualifies
     int generic_smem_set = 0;
     int banded_f32_smem_set[kMaxRPL + 1] = {0};
+    int banded_fwd_smem_set[kMaxRPL + 1] = {0};
     std::mutex mu;
 };
 

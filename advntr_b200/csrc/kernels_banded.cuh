@@ -294,6 +294,170 @@ banded_fill_kernel(const BandedArgs a)
 }
 
 // =============================================================================================
+// banded forward kernel (HiddenMarkovModel.log_probability / _forward, hmm.pyx:1258-1313,
+// 1371-1484): the same register wavefront with log-sum-exp in place of max and no traceback.
+// The reference folds a state's candidates with pair_lse in in-edge order (utils.pyx:72-90) and,
+// for silent states, combines the emitting-source and silent-source partial sums at the end;
+// here the three candidates of a slot are summed in one shifted log-sum-exp.  The contract for
+// forward is 1e-9 relative (the device exp/log differ from glibc's in the last bits anyway), not
+// bit identity.  Row 1 comes from the host-evaluated forward first-row table (global memory,
+// read by lane 0 only); reads longer than 32 * kMaxRPL or models whose image does not fit in
+// shared memory take the generic forward kernel.
+// =============================================================================================
+__device__ __forceinline__ double lse3(double a, double b, double c)
+{
+    const double m = fmax(a, fmax(b, c));
+    if (m == kNegInf) return kNegInf;
+    return m + log(exp(a - m) + exp(b - m) + exp(c - m));
+}
+__device__ __forceinline__ double lse2(double a, double b)
+{
+    const double m = fmax(a, b);
+    if (m == kNegInf) return kNegInf;
+    return m + log(exp(a - m) + exp(b - m));
+}
+
+template <int RPL, int WPB>
+__global__ void __launch_bounds__(WPB * 32, 2)
+banded_forward_kernel(const BandedArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ double s_fval[WPB][32];
+
+    const Tile tile = a.tiles[blockIdx.x];
+    const DevBanded* __restrict__ M = reinterpret_cast<const DevBanded*>(tile.model);
+    const int P = M->P, NC = M->NC;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // weights + emissions only: the Viterbi first-row table at the end of the image is not used
+        const uint32_t bytes = (uint32_t)kImgV1 * (uint32_t)P;
+        mbar_expect_tx(&s_bar, bytes);
+#pragma unroll 1
+        for (uint32_t o = 0; o < bytes; o += 65536u)
+            tma_bulk_g2s(smem_raw + o, M->image + o, min(65536u, bytes - o), &s_bar);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    mbar_wait(&s_bar, 0);
+    if (warp >= tile.cnt) return;
+
+    const int item = tile.first + warp;
+    const int q = a.order[item];
+    const size_t slot = (size_t)(item - a.chunk_base);
+    const int n = a.rlen[q];
+    if (n == 0) {
+        if (lane == 0) a.logp[q] = M->logp_empty_fwd;
+        return;
+    }
+    const int nl = (n + RPL - 1) / RPL;
+    const int ln = (n - 1) / RPL, jn = (n - 1) % RPL;
+    const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
+    uint32_t symbits;
+    {
+        const int bit = 2 * lane * RPL;
+        const int w = bit >> 5, sh = bit & 31;
+        const int last_word = (n + 15) / 16;
+        const uint32_t lo = (w <= last_word) ? pk[w] : 0u;
+        const uint32_t hi = (w + 1 <= last_word) ? pk[w + 1] : 0u;
+        symbits = __funnelshift_r(lo, hi, sh);
+    }
+    double* __restrict__ vfin = a.vfin + slot * a.vfin_stride;
+    const uint32_t s_base = smem_u32(smem_raw);
+    uint32_t eaddr[RPL];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+        eaddr[j] = s_base + (uint32_t)kImgE * P + ((symbits >> (2 * j)) & 3u) * (uint32_t)(16 * P);
+    const double2* __restrict__ f1 = reinterpret_cast<const double2*>(M->f1) + (size_t)(symbits & 3u) * P;   // lane 0: [c] -> {I, M}
+
+    double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) cI[j] = cM[j] = cD[j] = acc[j] = kNegInf;
+    double bI = kNegInf, bM = kNegInf, bD = kNegInf;
+    const int acc_col = M->acc_col;
+    const int steps = NC + nl - 1;
+#pragma unroll 1
+    for (int t = 0; t < steps; ++t) {
+        const double uI0 = shfl_up_f64(cI[RPL - 1], 1);
+        const double uM0 = shfl_up_f64(cM[RPL - 1], 1);
+        const double uD0 = shfl_up_f64(cD[RPL - 1], 1);
+        const int c = t - lane;
+        if (c < 0 || c >= NC || lane >= nl) continue;
+        const uint32_t wa = s_base + (uint32_t)c * 80u;
+        const double2 w01 = lds128(wa), w23 = lds128(wa + 16), w45 = lds128(wa + 32);
+        const double2 w67 = lds128(wa + 48), w89 = lds128(wa + 64);
+        const double wII = w01.x, wIM = w01.y, wID = w23.x, wMI = w23.y, wMM = w45.x, wMD = w45.y;
+        const double wDI = w67.x, wDM = w67.y, wDD = w89.x, aw = w89.y;
+        double nM[RPL], nD[RPL], eIr[RPL];
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+            const double2 e = lds128(eaddr[j] + (uint32_t)c * 16u);   // {eI, eM}
+            eIr[j] = e.x;
+            const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
+            nM[j] = lse3(oI + wMI, oM + wMM, oD + wMD) + e.y;           // emission after the sum (hmm.pyx:1444)
+            nD[j] = lse3(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD);
+        }
+        double first_I = kNegInf;
+        if (lane == 0) {
+            const double2 f = __ldg(f1 + c);
+            nM[0] = f.y;
+            first_I = f.x;
+        }
+        if (c == acc_col) {
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
+        }
+        if (aw > kNegInf) {
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) acc[j] = lse2(acc[j], nD[j] + aw);
+        }
+        double uI = uI0, uM = uM0, uD = uD0;
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+            double vI = lse3(uI + wII, uM + wIM, uD + wID) + eIr[j];
+            if (j == 0 && lane == 0) vI = first_I;
+            uI = vI; uM = nM[j]; uD = nD[j];
+            cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
+        }
+        bI = uI0; bM = uM0; bD = uD0;
+        if (lane == ln) {
+            double fI = cI[0], fM = cM[0], fD = cD[0];
+#pragma unroll
+            for (int j = 1; j < RPL; ++j)
+                if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
+            vfin[c] = fI; vfin[P + c] = fM; vfin[2 * P + c] = fD;
+        }
+    }
+    __syncwarp();
+
+    // final-only silent states on the last row: log-sum-exp over the candidate list, across the warp
+    const int NF = M->NF;
+    for (int f = 0; f < NF; ++f) {
+        const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
+        double mx = kNegInf;
+        for (int k = k0 + lane; k < k1; k += 32) {
+            const int code = M->fin_src[k];
+            const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
+            mx = fmax(mx, sv + M->fin_w[k]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, shfl_xor_f64(mx, off));
+        double sum = 0.0;
+        if (mx > kNegInf)
+            for (int k = k0 + lane; k < k1; k += 32) {
+                const int code = M->fin_src[k];
+                const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
+                sum += exp(sv + M->fin_w[k] - mx);
+            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += shfl_xor_f64(sum, off);
+        if (lane == 0) s_fval[warp][f] = (mx > kNegInf) ? mx + log(sum) : kNegInf;
+        __syncwarp();
+    }
+    if (lane == 0) a.logp[q] = s_fval[warp][M->end_final];
+}
+
+// =============================================================================================
 // fp32 variant of the banded fill kernel (optional mode, ADVHMM_FP32): same schedule and
 // operation order with float tables / float arithmetic.  Image: 112 bytes per column
 //   [0, 48P)    w12[c][12] floats: the ten weights of the fp64 image + 2 pad

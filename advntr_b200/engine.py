@@ -326,12 +326,14 @@ class DeviceModel(object):
         return self.ctx._run([self], goff, seqs, off, both_strands, want_path, force_generic, path_cap,
                              fp32=(precision == "fp32"), want_summary=want_summary)
 
-    def log_probability(self, codes):
+    def log_probability(self, codes, force_generic=False):
+        """Forward log-probabilities (``hmm.pyx:1258-1313``): banded wavefront kernel for reads up to
+        320 bases on profile-shaped models, generic kernel otherwise (or with ``force_generic``)."""
         seqs, off = pack_reads(codes)
         R = len(codes)
         logp = np.empty(R, dtype=np.float64)
-        _check(self._lib.advhmm_log_probability_batch(self._h, seqs.ctypes.data, off.ctypes.data, R, 0,
-                                                      logp.ctypes.data))
+        _check(self._lib.advhmm_log_probability_batch(self._h, seqs.ctypes.data, off.ctypes.data, R,
+                                                      FORCE_GENERIC if force_generic else 0, logp.ctypes.data))
         return logp
 
     def __del__(self):

@@ -64,10 +64,33 @@ def test_score_only(ctx, golden_config1):
 def test_forward_log_probability(ctx, golden):
     from advntr_b200 import engine
     dm = engine.DeviceModel(ctx, golden.baked)
-    fwd = dm.log_probability(golden.codes())
+    fwd = dm.log_probability(golden.codes())                         # banded forward kernel
+    gen = dm.log_probability(golden.codes(), force_generic=True)      # generic CSR forward kernel
     dm.close()
     # north-star tolerance for log-probabilities: 1e-9 relative (device exp/log vs glibc)
     assert np.allclose(fwd, golden.forward, rtol=1e-9, atol=0)
+    assert np.allclose(gen, golden.forward, rtol=1e-9, atol=0)
+
+
+def test_forward_long_reads_and_fresh_reads_vs_oracle(ctx, golden_config1):
+    """Forward on 400 fresh config-1 reads (banded kernel) and on reads longer than the banded
+    kernel's 320 bases (generic kernel), against the C restatement of hmm.pyx:1371-1484."""
+    import random
+    import oracle
+    from advntr_b200 import engine, synth
+    loc = synth.config1_locus()
+    rng = random.Random(99)
+    reads = loc.reads(rng, 400) + [synth.revcomp(r) for r in loc.reads(rng, 50)]
+    reads += [loc.reads(rng, 1, length=L)[0] for L in (1, 2, 5, 33, 97, 160, 222, 319, 320)]
+    long_reads = [loc.left + loc.pattern * 8 + loc.right, synth.rand_dna(rng, 321), synth.rand_dna(rng, 700)]
+    om = oracle.OracleModel(golden_config1.baked)
+    dm = engine.DeviceModel(ctx, golden_config1.baked)
+    for batch in (reads, long_reads, reads[:20] + long_reads):
+        codes = [oracle.encode(r) for r in batch]
+        got = dm.log_probability(codes)
+        want = om.log_probability(codes)
+        assert np.allclose(got, want, rtol=1e-9, atol=0)
+    dm.close()
 
 
 def test_fresh_reads_vs_oracle_and_chunking(ctx, golden_config1, monkeypatch):
