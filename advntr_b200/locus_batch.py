@@ -4,12 +4,13 @@
 reads on both strands).  ``LocusDecoder`` keeps the same decisions -- which strand of an
 unmapped read wins, which reads are recruited, which are spanning -- but feeds all reads of
 the locus (or of many loci, ``decode_many``) to the engine at once and applies the path
-consumers to the returned paths.  BAM / FASTA input, the genotype likelihood and the DNN
-pre-filter stay outside (out of scope).
+consumers to the returned paths.  The statistics applied to the repeat counts afterwards (genotype likelihood,
+frameshift test) are in ``genotype.py``; BAM / FASTA input, PacBio flank alignment (pairwise2) and
+the DNN pre-filter stay outside (out of scope).
 """
 from __future__ import annotations
 
-from . import engine, fast_compile, path_utils, read_matcher
+from . import engine, fast_compile, genotype, path_utils, read_matcher
 
 
 class SelectedRead(object):
@@ -37,6 +38,7 @@ class LocusDecoder(object):
         self.read_length = read_length
         self.scaled_score = scaled_score
         self.min_repeat_bp_to_add_read = 2            # vntr_finder.py:66-69
+        self.error_rate = error_rate
         copies = read_matcher.copies_for_read_length(read_length, len(self.pattern))
         self.model = fast_compile.build_vntr_matcher_hmm(left_flank, right_flank, self.segments, copies,
                                                          flank_size=flank_size, error_rate=error_rate)
@@ -95,6 +97,33 @@ class LocusDecoder(object):
                 flanking.append(n)
         return covered, sorted(flanking)
 
+    def genotype(self, selected, accuracy_filter=False, is_haploid=False):
+        """The genotype call of ``find_repeat_count_from_alignment_file`` without a coverage estimate
+        (``vntr_finder.py:846-875``) -> dict with the fields of the reference's ``GenotypeResult``."""
+        covered, flanking = self.observed_repeats(selected, accuracy_filter)
+        copy_numbers, max_prob = genotype.genotype_from_illumina_counts(covered, flanking, accuracy_filter, is_haploid)
+        if accuracy_filter:
+            covered = genotype._drop_unsupported(covered)
+        return {"copy_numbers": copy_numbers, "recruited_reads_count": len(selected),
+                "spanning_reads_count": len(covered), "flanking_reads_count": len(flanking),
+                "maximum_likelihood": max_prob}
+
+    def updated_model(self, selected):
+        """One ``--update`` step (``vntr_finder.py:667-698``): re-estimate the repeat-unit profile from
+        the repeat segments of the selected reads and of the reference repeats (decoded on the
+        current model), and rebuild the read matcher (``get_read_matcher_model(..., vpaths)``).
+
+        The reference's loop compares a fitness that it computes from the ORIGINAL selection
+        (``:693``), so it always stops after the first rebuild; this is that rebuild."""
+        ref = [seg.upper() for seg in self.segments]
+        res = self.model.viterbi_batch(ref)
+        vpaths = [(r.sequence, r.vpath) for r in selected]
+        vpaths += [(seq, self._vpath(res, i)) for i, seq in enumerate(ref)]
+        copies = read_matcher.copies_for_read_length(self.read_length, len(self.pattern))
+        flank = self.read_length                      # vntr_finder.py:681-683
+        return read_matcher.get_read_matcher_model(self.left_flank[-flank:], self.right_flank[:flank], None,
+                                                   copies, vpaths, error_rate=self.error_rate)
+
     def frameshift_candidate(self, selected):
         """Most frequent frame-shifting indel state among the selected reads and its count
         (``vntr_finder.py:265-300``); the binomial test on it is ``identify_frameshift``."""
@@ -109,3 +138,26 @@ def decode_many(decoders, reads_per_locus, ctx=None, both_strands=False):
     models = [d.model._device_model() for d in decoders]
     groups = [[d.model._encode(r) for r in reads] for d, reads in zip(decoders, reads_per_locus)]
     return ctx.viterbi_multi(models, groups, both_strands=both_strands)
+
+
+def dominant_copy_numbers_from_spanning_reads(left_flank, right_flank, repeat_segments, spanning_reads,
+                                              error_rate=0.3, accuracy_filter=False, is_haploid=False):
+    """PacBio call site (``vntr_finder.py:534-585``): one model with enough unrolled copies for the
+    longest spanning read (100 bp flanks, ``:109``, ``:549``), every spanning read decoded in one
+    device call (the long-read kernel), genotype from the repeat counts.
+    -> ``(copy_numbers, max_prob, observed_copy_numbers)``."""
+    if len(spanning_reads) < 1:
+        return None, 0, []
+    pattern = repeat_segments[0]
+    longest = max(max(len(r) - 100 for r in spanning_reads), 0)
+    max_copies = int(round(longest / float(len(pattern))))
+    model = fast_compile.build_vntr_matcher_hmm(left_flank, right_flank, list(repeat_segments), max_copies,
+                                                flank_size=100, error_rate=error_rate)
+    res = model.viterbi_batch([r.upper() for r in spanning_reads])
+    states = model.states
+    observed = []
+    for i in range(len(spanning_reads)):
+        p = res.path(i)
+        observed.append(path_utils.get_number_of_repeats_in_vpath([(int(k), states[k]) for k in p]))
+    copy_numbers, max_prob = genotype.dominant_copy_numbers(observed, accuracy_filter, is_haploid)
+    return copy_numbers, max_prob, observed

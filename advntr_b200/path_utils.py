@@ -101,6 +101,15 @@ def get_repeating_pattern_lengths(visited_states):
     return PathSummary(list(visited_states)).unit_lengths
 
 
+def get_repeat_segments_from_visited_states_and_region(visited_states, region):
+    """``hmm_utils.py:144-152``: consecutive pieces of ``region`` with the repeat-unit lengths."""
+    out, at = [], 0
+    for n in get_repeating_pattern_lengths(visited_states):
+        out.append(region[at:at + n])
+        at += n
+    return out
+
+
 def get_flanking_regions_matching_rate(vpath, sequence, left_flank, right_flank, accuracy_filter=False):
     """Fraction of flank match states whose read base equals the flank base; the smaller of the
     two flanks' rates (``hmm_utils.py:209-268``)."""
@@ -151,6 +160,54 @@ def extract_repeating_segments_from_read(sequence, visited_states):
         if is_emitting_state(n):
             pos += 1
     return repeats, runs
+
+
+def get_multiple_alignment_of_viterbi_paths(repeats_sequences, repeats_visited_states):
+    """Column-anchored multiple alignment of repeat segments from their state runs
+    (``hmm_utils.py:23-67``): one column per match index, followed by as many insert columns as
+    the most-inserting segment needs.
+
+    The reference marks EVERY remaining occurrence of a column's state as consumed when it places
+    the first one, so a segment that visits ``I_k`` twice places one base for it and every later
+    base of that segment moves one column to the left (its last base is dropped).  Kept: the
+    re-estimated profile, and with it the tables the reads are decoded against, depend on it."""
+    width = {}                      # 'M7' / 'I3' / 'D2' -> most visits by one segment
+    last_index = 0
+    for run in repeats_visited_states:
+        visits = {}
+        for name in run:
+            label = name.split("_")[0]
+            visits[label] = visits.get(label, 0) + 1
+        for label, n in visits.items():
+            last_index = max(last_index, int(label[1:]))
+            width[label] = max(width.get(label, n), n)
+    columns = []
+    for i in range(last_index + 1):
+        for label in ("M%s" % i, "I%s" % i):
+            columns.extend([label] * width.get(label, 0))
+    rows = []
+    for seq, run in zip(repeats_sequences, repeats_visited_states):
+        pending = [name.split("_")[0] for name in run]
+        row, used = [], 0
+        for label in columns:
+            if label in pending:
+                pending = [None if x == label else x for x in pending]
+                row.append(seq[used])
+                used += 1
+            else:
+                row.append("-")
+        rows.append("".join(row))
+    return rows
+
+
+def get_multiple_alignment_of_repeats_from_reads(sequence_vpath_list):
+    """``hmm_utils.py:94-103``: the repeat segments of every (read, Viterbi path), aligned."""
+    seqs, runs = [], []
+    for sequence, vpath in sequence_vpath_list:
+        repeats, states = extract_repeating_segments_from_read(sequence, _names(vpath))
+        seqs += repeats
+        runs += states
+    return get_multiple_alignment_of_viterbi_paths(seqs, runs)
 
 
 def recruit_read(logp, vpath, min_score_to_count_read, read_sequence, left_flank, right_flank):

@@ -171,6 +171,14 @@ class _OrderedDiGraph(object):
     def number_of_edges(self):
         return sum(len(v) for v in self.succ.values())
 
+    def remove_node(self, n):
+        del self.succ[n]
+        for nbrs in self.succ.values():
+            nbrs.pop(n, None)
+
+    def remove_edge(self, a, b):
+        del self.succ[a][b]
+
     @staticmethod
     def disjoint_union(g, h):
         """G's nodes, G's edges, then H's nodes, H's edges (networkx-1.11 ``union``)."""
@@ -297,15 +305,65 @@ class HiddenMarkovModel(object):
         return self.finite == 0
 
     # --------------------------------------------------------------------- bake
+    def _merge_pass(self, merge):
+        """What ``bake`` does before ordering the states when ``merge`` is 'all' / 'partial'
+        (``hmm.pyx:720-838``).  Every read-matcher model is baked with ``merge=None``; this path serves
+        ``build_reference_repeat_finder_hmm`` (``hmm_utils.py:674``) and ``from_json`` (``:3143``).
+
+        * 'all': states other than start / end without in-edges or without out-edges are removed,
+          repeatedly.  The reference allocates its two degree counters ONCE and keeps adding to
+          them while it re-indexes the surviving states every round (``:720-746``), so from the
+          second round on a state is tested against stale sums; reproduced as is.
+        * rows whose probabilities do not sum to 1 (8 decimals) are renormalised (``:766-784``);
+        * a silent state with a probability-1 out-edge is merged into its successor ('partial': only
+          into silent successors): its in-edges are re-pointed, the state disappears (``:789-828``)."""
+        g = self.graph
+        n0 = len(g.nodes())
+        in_count = np.zeros(n0, dtype=np.int32)
+        out_count = np.zeros(n0, dtype=np.int32)
+        while merge == "all":
+            removed = 0
+            pre = g.nodes()
+            idx = {s: i for i, s in enumerate(pre)}
+            for a, b, _ in list(g.edges()):
+                out_count[idx[a]] += 1
+                in_count[idx[b]] += 1
+            for i, s in enumerate(pre):
+                if s is self.start or s is self.end:
+                    continue
+                if in_count[i] == 0 or out_count[i] == 0:
+                    removed += 1
+                    g.remove_node(s)
+            if removed == 0:
+                break
+        for s in g.nodes():
+            total = round(sum(math.e ** w for w in g.succ[s].values()), 8)
+            if total != 1.0 and s is not self.end:
+                for b in g.succ[s]:
+                    g.succ[s][b] = g.succ[s][b] - _log(total)
+        while True:
+            merged = 0
+            for a, b, w in list(g.edges()):
+                if a not in g.succ or b not in g.succ:
+                    continue
+                if a is self.start or b is self.end:
+                    continue
+                if w == 0.0 and a.is_silent() and (merge == "all" or b.is_silent()):
+                    for x, y, d in list(g.edges()):
+                        if y is a:
+                            merged += 1
+                            g.remove_edge(x, y)
+                            g.add_edge(x, b, d)
+                    g.remove_node(a)
+            if merged == 0:
+                break
+
     def bake(self, verbose=False, merge="All"):
         merge = merge.lower() if merge else None
-        if merge is not None and merge != "none":
-            raise NotImplementedError(
-                "bake(merge=%r): only merge=None is implemented -- every model on adVNTR's "
-                "read-matching path is baked with merge=None (hmm_utils.py:351,418,496,548,"
-                "559,594)" % (merge,))
         self._release_engine()
         g = self.graph
+        if merge in ("all", "partial"):
+            self._merge_pass(merge)
         nodes = g.nodes()
         emitting = sorted((s for s in nodes if not s.is_silent()), key=lambda s: s.name)
         silent = sorted((s for s in nodes if s.is_silent()), key=lambda s: s.name)

@@ -369,8 +369,11 @@ def get_read_matcher_model(left_flanking_region, right_flanking_region, patterns
                            vpaths=None, error_rate=DEFAULT_MAX_ERROR_RATE, profile=None, pom=None):
     """The model every read of a locus is decoded against (``hmm_utils.py:553-595``)."""
     if vpaths:
-        raise NotImplementedError("re-estimating the repeat profile from Viterbi paths "
-                                  "(--update, hmm_utils.py:428-430) is outside the hot path")
+        # --update (vntr_finder.py:667-698): the repeat-unit profile is re-estimated from the repeat
+        # segments the current model found in the selected reads (hmm_utils.py:427-429)
+        from . import path_utils
+        alignment = path_utils.get_multiple_alignment_of_repeats_from_reads(vpaths)
+        profile = repeat_profile(alignment, error_rate)
     pom = pom or _default_backend
     hmm = get_suffix_matcher_hmm(left_flanking_region, error_rate, pom)
     hmm.concatenate(get_variable_number_of_repeats_matcher_hmm(patterns, copies, error_rate, profile, pom))
@@ -442,6 +445,83 @@ def _read_matcher_sparse(hmm, names, pom):
                                             name="Read Matcher", state_names=names, merge=None)
     out.bake(merge=None)
     return out
+
+
+def build_reference_repeat_finder_hmm(patterns, copies=1, pom=None):
+    """Model that segments the REFERENCE copy of a VNTR into its repeat units when a locus is added
+    (``hmm_utils.py:598-680``, used by ``reference_vntr.py:80-87``): ``copies`` unrolled copies of
+    ``patterns[0]`` with fixed 0.98 / 0.01 / 0.01 transitions, random-sequence states before and
+    after, baked with the default ``merge='All'``."""
+    pom = pom or _default_backend
+    State, DiscreteDistribution = pom.State, pom.DiscreteDistribution
+    pattern = patterns[0]
+    R = len(pattern)
+    hmm = pom.HiddenMarkovModel(name="HMM Model")
+    uniform = DiscreteDistribution({"A": 0.25, "C": 0.25, "G": 0.25, "T": 0.25})
+    lead = State(uniform, name="start_random_matches")
+    trail = State(uniform, name="end_random_matches")
+    hmm.add_states([lead, trail])
+    T = hmm.add_transition
+    prev_out = None
+    for k in range(copies):
+        ins = [State(uniform, name="I%s_%s" % (i, k)) for i in range(R + 1)]
+        mat = []
+        for i in range(R):
+            table = {"A": 0.01, "C": 0.01, "G": 0.01, "T": 0.01}
+            table[pattern[i]] = 0.97
+            mat.append(State(DiscreteDistribution(table), name="M%s_%s" % (i + 1, k)))
+        dele = [State(None, name="D%s_%s" % (i + 1, k)) for i in range(R)]
+        gate_in = State(None, name="unit_start_%s" % k)
+        gate_out = State(None, name="unit_end_%s" % k)
+        hmm.add_states(ins + mat + dele + [gate_in, gate_out])
+        if k:
+            T(prev_out, gate_in, 0.5)
+        else:
+            T(hmm.start, gate_in, 0.5)
+            T(hmm.start, lead, 0.5)
+            T(lead, gate_in, 0.5)
+            T(lead, lead, 0.5)
+        T(gate_out, trail, 0.5)
+        if k == copies - 1:
+            T(gate_out, hmm.end, 0.5)
+            T(trail, trail, 0.5)
+            T(trail, hmm.end, 0.5)
+        T(gate_in, mat[0], 0.98)
+        T(gate_in, dele[0], 0.01)
+        T(gate_in, ins[0], 0.01)
+        T(ins[0], ins[0], 0.01)
+        T(ins[0], dele[0], 0.01)
+        T(ins[0], mat[0], 0.98)
+        T(dele[R - 1], gate_out, 0.99)
+        T(dele[R - 1], ins[R], 0.01)
+        T(mat[R - 1], gate_out, 0.99)
+        T(mat[R - 1], ins[R], 0.01)
+        T(ins[R], ins[R], 0.01)
+        T(ins[R], gate_out, 0.99)
+        for i in range(R):
+            T(mat[i], ins[i + 1], 0.01)
+            T(dele[i], ins[i + 1], 0.01)
+            T(ins[i + 1], ins[i + 1], 0.01)
+            if i < R - 1:
+                T(ins[i + 1], mat[i + 1], 0.98)
+                T(ins[i + 1], dele[i + 1], 0.01)
+                T(mat[i], mat[i + 1], 0.98)
+                T(mat[i], dele[i + 1], 0.01)
+                T(dele[i], dele[i + 1], 0.01)
+                T(dele[i], mat[i + 1], 0.98)
+        prev_out = gate_out
+    hmm.bake()
+    return hmm
+
+
+def find_repeat_segments(pattern, estimated_repeats, region_in_ref, pom=None):
+    """``ReferenceVNTR.find_repeat_segments`` (``reference_vntr.py:80-87``): Viterbi-decode the
+    reference region against the repeat finder and cut it at the unit boundaries."""
+    from . import path_utils
+    model = build_reference_repeat_finder_hmm([pattern], copies=estimated_repeats, pom=pom)
+    logp, path = model.viterbi(region_in_ref)
+    visited = [state.name for _, state in path[1:-1]]
+    return path_utils.get_repeat_segments_from_visited_states_and_region(visited, region_in_ref)
 
 
 def copies_for_read_length(read_length, pattern_length):

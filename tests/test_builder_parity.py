@@ -69,8 +69,7 @@ def test_builder_error_behaviour():
         m.viterbi("A")
     with pytest.raises(ValueError, match="must bake model"):
         m.log_probability("A")
-    with pytest.raises(NotImplementedError):
-        m.bake(merge="All")
+    m.bake(merge="All")       # default merge: implemented (tests/test_downstream.py checks its semantics)
 
 
 def test_from_matrix_wires_last_state_to_end():
