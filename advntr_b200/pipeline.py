@@ -1,0 +1,111 @@
+"""Many loci at once: keyword pre-filter -> one batched Viterbi call -> per-locus genotype.
+
+The shape of ``GenomeAnalyzer.find_repeat_counts_from_alignment_file`` (``genome_analyzer.py:273-297``)
+without its file IO: the reference writes the keywords of every target locus, runs the
+``adVNTR-Filtering`` binary over the unmapped reads, then loops over the loci one by one and over
+their reads one by one (``vntr_finder.py:727-767``).  Here
+
+1. the unmapped reads are scanned ONCE on the device against the keywords of all loci
+   (``keyword_filter.KeywordFilter``, same selection and per-locus cap as the binary);
+2. the mapped reads of every locus and both strands of its filtered unmapped reads go to the device
+   in ONE ``advhmm_viterbi_multi_summary`` call; the backtrack kernels reduce every path on the
+   device to the handful of numbers adVNTR reads off it (``advhmm_read_summary``), so no state path
+   crosses the bus;
+3. recruitment (``recruit_read``), the spanning test and the genotype statistics run per locus on
+   those numbers (numpy, no per-read Python).
+
+Decisions are the ones ``LocusDecoder`` makes read by read from full paths (tests/test_pipeline.py
+checks they are identical); BAM access stays with the caller, who passes the mapped reads per locus.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine, genotype, keyword_filter
+from .locus_batch import LocusDecoder, reverse_complement
+
+
+class LocusSpec(object):
+    """What ``ReferenceVNTR`` holds for one locus (``reference_vntr.py:7-40``)."""
+
+    def __init__(self, locus_id, left_flank, right_flank, repeat_segments, scaled_score=None):
+        self.id = int(locus_id)
+        self.left_flank, self.right_flank = left_flank, right_flank
+        self.repeat_segments = list(repeat_segments)
+        self.pattern = self.repeat_segments[0]
+        self.scaled_score = scaled_score
+
+
+class GenotypingRun(object):
+    def __init__(self, loci, read_length=150, keyword_size=15):
+        self.ctx = engine.Context.default()         # the context the models' device tables live on
+        self.read_length = read_length
+        self.loci = list(loci)
+        self.decoders = [LocusDecoder(l.left_flank, l.right_flank, l.repeat_segments, read_length,
+                                      scaled_score=l.scaled_score, locus_id=l.id) for l in self.loci]
+        keywords = [(l.id, sorted(keyword_filter.get_keywords_for_filtering(
+            l.left_flank, l.right_flank, l.repeat_segments, l.pattern, keyword_size=keyword_size))) for l in self.loci]
+        self.filter = keyword_filter.KeywordFilter(keywords, ctx=self.ctx)
+
+    def close(self):
+        self.filter.close()
+
+    # -- step 1 ----------------------------------------------------------------------------------
+    def filter_unmapped(self, names, seqs):
+        """{locus id: [(name, sequence) ...]} as ``get_filtered_read_ids`` hands them to the finders
+        (``genome_analyzer.py:186-197``, ``:289``): the reads the binary lists for the locus, in the
+        order of its read section (sorted by name)."""
+        per_locus, reads = self.filter.filter_reads(list(names), list(seqs))
+        wanted = {vid: set(shown) for vid, _, shown in per_locus}
+        return {vid: [(n, s) for n, s in reads if n in wanted[vid]] for vid in wanted}
+
+    # -- steps 2 + 3 -----------------------------------------------------------------------------
+    def genotype(self, mapped_reads_by_locus, unmapped_names=(), unmapped_seqs=(), accuracy_filter=False,
+                 is_haploid=False):
+        """-> {locus id: dict(copy_numbers, recruited_reads_count, spanning_reads_count,
+        flanking_reads_count, maximum_likelihood, covered_repeats, flanking_repeats)}."""
+        filtered = self.filter_unmapped(unmapped_names, unmapped_seqs) if len(unmapped_names) else {}
+        L = self.read_length
+        batch, goff, layout = [], [0], []
+        for dec in self.decoders:
+            mapped = [r.upper() for r in mapped_reads_by_locus.get(dec.id, ()) if "N" not in r.upper()]
+            unm = [s.upper() for _, s in filtered.get(dec.id, ()) if "N" not in s.upper() and len(s) >= L]
+            batch += mapped
+            for s in unm:
+                batch += [s, reverse_complement(s)]
+            goff.append(len(batch))
+            layout.append((len(mapped), len(unm)))
+        seqs, off = engine.encode_batch(batch)
+        models = [d.model._device_model() for d in self.decoders]
+        res = self.ctx._run(models, np.asarray(goff, dtype=np.int64), seqs, off, False, False, False, None,
+                            want_summary=True)
+        S, logp = res.summaries, res.logp
+        lens = (off[1:] - off[:-1]).astype(np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            right = np.where(S["right_bp"] > 0, S["right_hits"] / S["right_bp"].astype(np.float64), 1.0)
+            left = np.where(S["left_bp"] > 0, S["left_hits"] / S["left_bp"].astype(np.float64), 1.0)
+        rate = np.minimum(right, left)
+        possible = res.path_len >= 0
+        out = {}
+        for dec, (n_mapped, n_unm), a in zip(self.decoders, layout, goff[:-1]):
+            score = dec.min_score_to_select_a_read()
+            idx = np.arange(a, a + n_mapped)
+            if n_unm:                                   # the better strand of every unmapped read
+                f = a + n_mapped + 2 * np.arange(n_unm)
+                best = np.where(logp[f] < logp[f + 1], f + 1, f)
+                best = best[S["repeat_bp"][best] > dec.min_repeat_bp_to_add_read]
+                idx = np.concatenate([idx, best])
+            if score is not None:
+                ok = logp[idx] > score
+            else:
+                ok = (S["n_match"][idx] >= 0.9 * lens[idx]) & (logp[idx] > -lens[idx])
+            sel = idx[ok & (rate[idx] >= 0.9) & possible[idx]]
+            spanning = (rate[sel] >= 0.95) & (S["left_bp"][sel] > 5) & (S["right_bp"][sel] > 5)
+            covered = S["repeats"][sel][spanning].tolist()
+            flanking = [] if accuracy_filter else sorted(S["repeats"][sel][~spanning].tolist())
+            cn, prob = genotype.genotype_from_illumina_counts(covered, flanking, accuracy_filter, is_haploid)
+            kept = genotype._drop_unsupported(covered) if accuracy_filter else covered
+            out[dec.id] = {"copy_numbers": cn, "recruited_reads_count": int(len(sel)),
+                           "spanning_reads_count": len(kept), "flanking_reads_count": len(flanking),
+                           "maximum_likelihood": prob, "covered_repeats": covered, "flanking_repeats": flanking}
+        return out
