@@ -810,6 +810,7 @@ int kfilter_build(advhmm_kfilter* kf, int64_t n, const char* words, const int64_
     while ((1ull << bbits) < bwords) ++bbits;
     std::vector<KfEntry> table(tsize, KfEntry{0, 0, 0, 0, 0, 0});
     std::vector<uint32_t> bloom(bwords, 0);
+    std::vector<uint32_t> l0(kKfL0Bits / 32, 0);
     std::vector<int32_t> loci;
     std::vector<uint8_t> text;
     loci.reserve((size_t)n);
@@ -818,9 +819,10 @@ int kfilter_build(advhmm_kfilter* kf, int64_t n, const char* words, const int64_
         unsigned long long key = 0;
         if (cl.exact) for (char ch : w.codes) key = (key << 3) | (unsigned long long)ch;
         else          for (char ch : w.codes) key = key * kKfBase + ((unsigned long long)ch + 1u);
-        uint32_t a, m;
-        const unsigned long long h = kf_hash(key, cl.salt, a, m);
-        bloom[a >> (32 - bbits)] |= m;
+        uint32_t a;
+        const unsigned long long h = kf_hash(key, cl.salt, a);
+        bloom[a >> (32 - bbits)] |= kf_bloom_mask(a);
+        l0[(a & (kKfL0Bits - 1)) >> 5] |= 1u << (a & 31);
         unsigned long long slot = kf_slot(h, tsize - 1);
         while (table[slot].loci_cnt) slot = (slot + 1) & (tsize - 1);
         KfEntry& e = table[slot];
@@ -835,7 +837,8 @@ int kfilter_build(advhmm_kfilter* kf, int64_t n, const char* words, const int64_
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t o_table = 0, o_bloom = al(table.size() * sizeof(KfEntry));
     const size_t o_loci = o_bloom + al(bloom.size() * 4), o_text = o_loci + al(loci.size() * 4 + 4);
-    const size_t total = o_text + al(text.size() + 16);
+    const size_t o_l0 = o_text + al(text.size() + 16);
+    const size_t total = o_l0 + al(l0.size() * 4);
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(kf->tables.ensure(total));
     unsigned char* dp = kf->tables.as<unsigned char>();
@@ -845,10 +848,12 @@ int kfilter_build(advhmm_kfilter* kf, int64_t n, const char* words, const int64_
         CU_TRY(cudaMemcpyAsync(dp + o_loci, loci.data(), loci.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (!text.empty())
         CU_TRY(cudaMemcpyAsync(dp + o_text, text.data(), text.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(dp + o_l0, l0.data(), l0.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     d.table = reinterpret_cast<const KfEntry*>(dp + o_table);
     d.table_mask = tsize - 1;
     d.bloom = reinterpret_cast<const uint32_t*>(dp + o_bloom);
+    d.l0 = reinterpret_cast<const uint32_t*>(dp + o_l0);
     d.bloom_shift = (uint32_t)(32 - bbits);
     d.loci = reinterpret_cast<const int32_t*>(dp + o_loci);
     d.text = dp + o_text;
@@ -876,7 +881,18 @@ int kfilter_scan_device(advhmm_kfilter* kf, const unsigned char* d_seqs, const i
     kfilter_tile_index_kernel<<<(unsigned)((n_tiles + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_off, n_reads, n_tiles, d_tile);
     CU_TRY(cudaGetLastError());
     ctx->launches++;
-    const size_t smem = (size_t)kf->dev.halo + kKfTile;
+    // warps per CTA: as many as fit next to the first-level bitmap with two (halo + tile) buffers each
+    const size_t per_warp = 2 * ((size_t)kf->dev.halo + kKfTile);
+    const size_t budget = (ctx->smem_optin > 4096 ? ctx->smem_optin - 4096 : 0);
+    int n_warps = budget > (size_t)kKfL0Bytes ? (int)((budget - kKfL0Bytes) / per_warp) : 0;
+    n_warps = std::min(n_warps, kKfMaxWarps);
+    if (n_warps < 1) return set_error(ADVHMM_EUNSUPPORTED, "keyword filter: not enough shared memory for a warp pipeline");
+    const size_t smem = (size_t)kKfL0Bytes + (size_t)n_warps * per_warp;
+    if ((int)smem > ctx->kfilter_smem_set) {
+        CU_TRY(cudaFuncSetAttribute(kfilter_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->kfilter_smem_set = (int)smem;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + n_warps - 1) / n_warps, std::max(ctx->sm_count, 1));
     unsigned long long cap = next_pow2(std::max<unsigned long long>(1 << 16, (unsigned long long)n_reads / 2));
     for (int attempt = 0; attempt < 10; ++attempt, cap <<= 2) {
         const size_t bytes = (size_t)cap * 12 + 256;
@@ -886,10 +902,10 @@ int kfilter_scan_device(advhmm_kfilter* kf, const unsigned char* d_seqs, const i
         int32_t* ovf = reinterpret_cast<int32_t*>(cv + cap);
         CU_TRY(cudaMemsetAsync(ck, 0xff, (size_t)cap * 8, ctx->stream));
         CU_TRY(cudaMemsetAsync(cv, 0, (size_t)cap * 4 + 64, ctx->stream));
-        KfScanArgs sa{kf->dev, d_seqs, d_off, d_tile, n_bases, n_reads, 0, ck, cv, cap - 1, ovf};
+        KfScanArgs sa{kf->dev, d_seqs, d_off, d_tile, n_bases, n_reads, (int32_t)n_tiles, ck, cv, cap - 1, ovf};
         {
             ProfScope prof(ctx, 0);
-            kfilter_scan_kernel<<<(unsigned)n_tiles, kKfThreads, smem, ctx->stream>>>(sa);
+            kfilter_scan_kernel<<<grid, n_warps * 32, smem, ctx->stream>>>(sa);
         }
         CU_TRY(cudaGetLastError());
         ctx->launches++;

@@ -154,6 +154,7 @@ struct advhmm_context {
     int generic_smem_set = 0;
     int banded_f32_smem_set[kMaxRPL + 1] = {0};
     int banded_fwd_smem_set[kMaxRPL + 1] = {0};
+    int kfilter_smem_set = 0;
     std::mutex mu;
 };
 

@@ -304,13 +304,15 @@ banded_fill_kernel(const BandedArgs a)
 // read by lane 0 only); reads longer than 32 * kMaxRPL or models whose image does not fit in
 // shared memory take the generic forward kernel.
 // =============================================================================================
-__device__ __forceinline__ double lse3(double a, double b, double c)
+// not inlined on purpose: one column step evaluates 3 * RPL of these, and with exp / log expanded
+// in place the loop body outgrows the instruction cache (ncu: no_instruction was the top stall)
+__device__ __noinline__ double lse3(double a, double b, double c)
 {
     const double m = fmax(a, fmax(b, c));
     if (m == kNegInf) return kNegInf;
     return m + log(exp(a - m) + exp(b - m) + exp(c - m));
 }
-__device__ __forceinline__ double lse2(double a, double b)
+__device__ __noinline__ double lse2(double a, double b)
 {
     const double m = fmax(a, b);
     if (m == kNegInf) return kNegInf;

@@ -7,21 +7,23 @@
 // the keywords grouped by length ("classes") that is an exact k-mer lookup per class and position,
 // which parallelises over POSITIONS instead of over reads:
 //
-//   * the reads are one flat byte stream (as the caller passes them, no separators).  A CTA owns a
-//     tile of kKfTile bytes; one elected thread stages tile + halo (the k_max-1 bytes before it)
-//     into shared memory with ONE TMA bulk copy (cp.async.bulk, completion on an mbarrier); the
-//     CTA converts it in place to 3-bit symbol codes (A,C,G,T = 0..3, anything else = 4: the
+//   * the reads are one flat byte stream (as the caller passes them, no separators), cut into warp
+//     tiles of kKfTile bytes.  The kernel is persistent (one CTA per SM) and every warp is its own
+//     pipeline: lane 0 stages tile + halo (the k_max-1 bytes before it) into the warp's shared-memory
+//     buffer with ONE TMA bulk copy (cp.async.bulk, completion on the warp's mbarrier) while the
+//     previous tile is scanned (two buffers per warp); no CTA-wide barrier after start-up.  The warp
+//     converts the tile in place to 3-bit symbol codes (A,C,G,T = 0..3, anything else = 4: the
 //     reference's char_to_num, main.cc:43-54; lower case is "anything else" there too).
-//   * a thread scans 80 consecutive end positions (80 B = 20 words per thread: the quarter-warp's
-//     LDS.128 hit disjoint bank groups).  k <= 21: the k-mer is a 3k-bit integer rolled by
+//   * a lane scans 64 consecutive end positions.  k <= 21: the k-mer is a 3k-bit integer rolled by
 //     shift/or (exact key).  k > 21: a 64-bit polynomial rolling hash, verified against the
 //     keyword text on a hit (exact result either way).
-//   * every position probes a blocked Bloom filter (3 bits in one 32-bit word, 64 bits per
-//     keyword, false-positive rate ~1e-3, L2 resident): 8 positions are hashed and their words
-//     loaded before any is tested, so the loads overlap.
+//   * level 0: every position tests one bit of a 64 KB bitmap held in shared memory (copied once
+//     per CTA); level 1: the survivors probe a blocked Bloom filter in global memory (3 bits in one
+//     32-bit word, 64 bits per keyword, L2 resident).  Eight positions are hashed before the first
+//     test, so the probes of a group overlap.
 //   * a Bloom hit takes the slow path: open-addressing table (key, class) -> list of loci that
 //     own the keyword; which read the position belongs to is found by a binary search in seq_off
-//     restricted to the reads that intersect the tile (host-computed tile_first[]); k-mers that
+//     restricted to the reads that intersect the tile (device-computed tile_first[]); k-mers that
 //     would span a read boundary are rejected there -- the main loop carries no boundary logic.
 //   * (read, locus) occurrence counters live in a second open-addressing table (atomicCAS insert,
 //     atomicAdd count): exact for any number of loci per read; a full table is reported to the
@@ -34,12 +36,14 @@
 
 namespace {
 
-constexpr int kKfThreads = 256;
-constexpr int kKfPerThread = 80;
-constexpr int kKfTile = kKfThreads * kKfPerThread;      // 20,480 bytes of text per CTA
+constexpr int kKfMaxWarps = 32;                          // warps of the one persistent CTA per SM
+constexpr int kKfPerThread = 64;
+constexpr int kKfTile = 32 * kKfPerThread;               // 2,048 bytes of text per warp tile
 constexpr int kKfMaxClasses = 16;                        // distinct keyword lengths per filter
 constexpr int kKfMaxK = 4096;                            // longest keyword (halo in shared memory)
 constexpr int kKfGroup = 8;                              // positions hashed before the first test
+constexpr int kKfL0Bits = 1 << 19;                       // first-level filter: 64 KB bitmap in shared memory
+constexpr int kKfL0Bytes = kKfL0Bits / 8;
 constexpr unsigned long long kKfMul = 0x9E3779B97F4A7C15ull;
 constexpr unsigned long long kKfBase = 0x100000001B3ull; // rolling-hash base (odd)
 
@@ -61,6 +65,7 @@ struct KfEntry {                     // 32 bytes = one sector per probe
 struct DevKFilter {
     int n_classes, halo;             // halo: bytes staged before a tile (multiple of 16, >= k_max - 1)
     KfClass cls[kKfMaxClasses];
+    const uint32_t* l0;              // first-level bitmap (kKfL0Bits bits), copied to shared memory by every CTA
     const uint32_t* bloom;
     uint32_t bloom_shift, pad;       // word index = hash >> bloom_shift
     const KfEntry* table;
@@ -74,15 +79,18 @@ __host__ __device__ __forceinline__ int kf_code(unsigned char ch)
     return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
 }
 
-// -> a: 32 well-mixed bits (Bloom word, top bits first); m: the three Bloom bits; returns the full product
-__host__ __device__ __forceinline__ unsigned long long kf_hash(unsigned long long key, unsigned long long salt,
-                                                               uint32_t& a, uint32_t& m)
+// -> a: 32 well-mixed bits (first-level bit = low bits, Bloom word = top bits); returns the full product
+__host__ __device__ __forceinline__ unsigned long long kf_hash(unsigned long long key, unsigned long long salt, uint32_t& a)
 {
     const unsigned long long h = (key ^ salt) * kKfMul;
     a = (uint32_t)(h >> 32);
-    const uint32_t b = (a ^ (uint32_t)h) * 0x85EBCA6Bu;
-    m = (1u << (b >> 27)) | (1u << ((b >> 22) & 31)) | (1u << ((b >> 17) & 31));
     return h;
+}
+// the three Bloom bits (inside one 32-bit word) of a key with mixed hash a
+__host__ __device__ __forceinline__ uint32_t kf_bloom_mask(uint32_t a)
+{
+    const uint32_t b = a * 0x85EBCA6Bu;
+    return (1u << (b >> 27)) | (1u << ((b >> 22) & 31)) | (1u << ((b >> 17) & 31));
 }
 __host__ __device__ __forceinline__ unsigned long long kf_slot(unsigned long long h, unsigned long long mask)
 {
@@ -103,7 +111,7 @@ struct KfScanArgs {
     const int64_t* seq_off;             // [n_reads + 1]
     const int32_t* tile_first;          // [n_tiles + 1]: read that owns the first byte of the tile; last = n_reads - 1
     int64_t n_bases;
-    int32_t n_reads, pad;
+    int32_t n_reads, n_tiles;
     unsigned long long* cnt_keys;       // (read << 32 | locus), ~0ull = empty
     uint32_t* cnt_vals;
     unsigned long long cnt_mask;
@@ -126,7 +134,7 @@ __device__ __forceinline__ void kf_count(const KfScanArgs& a, int r, int32_t loc
 // boundary check, counting.  The k-mer is re-read from shared memory, so the main loop keeps no
 // per-position state alive.
 __device__ __noinline__ void kf_slow_path(const KfScanArgs& a, int c, uint32_t hits, int64_t p_first,
-                                          const unsigned char* __restrict__ sm, int64_t base)
+                                          const unsigned char* __restrict__ sm, int64_t base, int tile)
 {
     const KfClass cl = a.f.cls[c];
     const int k = cl.k;
@@ -137,8 +145,8 @@ __device__ __noinline__ void kf_slow_path(const KfScanArgs& a, int c, uint32_t h
         unsigned long long key = 0;
         if (cl.exact) for (int j = 0; j < k; ++j) key = (key << 3) | s[j];
         else          for (int j = 0; j < k; ++j) key = key * kKfBase + (s[j] + 1u);
-        uint32_t aa, mm;
-        const unsigned long long h = kf_hash(key, cl.salt, aa, mm);
+        uint32_t aa;
+        const unsigned long long h = kf_hash(key, cl.salt, aa);
         unsigned long long slot = kf_slot(h, a.f.table_mask);
         for (;;) {
             const KfEntry* e = a.f.table + slot;
@@ -152,7 +160,7 @@ __device__ __noinline__ void kf_slow_path(const KfScanArgs& a, int c, uint32_t h
                 }
                 if (same) {
                     // the read that owns position p: the last one with seq_off[r] <= p
-                    int lo = a.tile_first[blockIdx.x], hi = a.tile_first[blockIdx.x + 1];
+                    int lo = a.tile_first[tile], hi = a.tile_first[tile + 1];
                     while (lo < hi) {
                         const int mid = (lo + hi + 1) >> 1;
                         if (a.seq_off[mid] <= p) lo = mid; else hi = mid - 1;
@@ -169,84 +177,141 @@ __device__ __noinline__ void kf_slow_path(const KfScanArgs& a, int c, uint32_t h
     }
 }
 
-__global__ void __launch_bounds__(kKfThreads) kfilter_scan_kernel(const __grid_constant__ KfScanArgs a)
+__device__ __forceinline__ void fence_proxy_async_smem()
 {
-    extern __shared__ __align__(16) unsigned char kf_smem[];
-    __shared__ uint64_t bar;
-    const int tid = threadIdx.x;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Persistent, one CTA per SM, and every WARP is its own pipeline: it walks the warp tiles
+// w, w + W, w + 2W, ... (W = warps in the grid), staging tile + halo with its own TMA bulk copy into
+// its own pair of buffers (the next tile is in flight while the current one is scanned) and never
+// meets a CTA-wide barrier after start-up -- a slow path taken by one warp delays nobody else.
+// Dynamic shared memory: [first-level bitmap kKfL0Bytes][warp 0: buffer 0, buffer 1][warp 1: ...]
+__global__ void __launch_bounds__(kKfMaxWarps * 32, 1) kfilter_scan_kernel(const __grid_constant__ KfScanArgs a)
+{
+    extern __shared__ __align__(128) unsigned char kf_smem[];
+    __shared__ uint64_t bars[2 * kKfMaxWarps + 1];             // [2w], [2w+1]: buffers of warp w; last: bitmap
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_warps = blockDim.x >> 5;
     const int halo = a.f.halo;
-    const int64_t tile0 = (int64_t)blockIdx.x * kKfTile;
-    const int64_t base = tile0 - halo;                          // text position of kf_smem[0]
-    const int64_t lo = base < 0 ? 0 : base;
+    const uint32_t buf_bytes = (uint32_t)halo + kKfTile;
+    const uint32_t* l0 = reinterpret_cast<const uint32_t*>(kf_smem);
+    unsigned char* my_bufs = kf_smem + kKfL0Bytes + (size_t)warp * 2 * buf_bytes;
+    uint64_t* my_bars = bars + 2 * warp;
+    uint64_t* l0_bar = bars + 2 * kKfMaxWarps;
     const int64_t n16 = (a.n_bases + 15) & ~(int64_t)15;
-    const int64_t hi = tile0 + kKfTile < n16 ? tile0 + kKfTile : n16;
-    const uint32_t bytes = (uint32_t)(hi - lo);
+
+    auto stage = [&](int t, int b) {                            // lane 0: tile t -> buffer b
+        const int64_t tile0 = (int64_t)t * kKfTile;
+        const int64_t base = tile0 - halo;
+        const int64_t lo = base < 0 ? 0 : base;
+        const int64_t hi = tile0 + kKfTile < n16 ? tile0 + kKfTile : n16;
+        const uint32_t bytes = (uint32_t)(hi - lo);
+        mbar_expect_tx(&my_bars[b], bytes);
+        tma_bulk_g2s(my_bufs + (size_t)b * buf_bytes + (lo - base), a.seqs + lo, bytes, &my_bars[b]);
+    };
     if (tid == 0) {
-        mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, bytes);
-        tma_bulk_g2s(kf_smem + (lo - base), a.seqs + lo, bytes, &bar);
+        for (int i = 0; i < 2 * kKfMaxWarps + 1; ++i) mbar_init(&bars[i], 1);
+        mbar_expect_tx(l0_bar, (uint32_t)kKfL0Bytes);
+        for (uint32_t o = 0; o < (uint32_t)kKfL0Bytes; o += 32768u)
+            tma_bulk_g2s(kf_smem + o, reinterpret_cast<const unsigned char*>(a.f.l0) + o, 32768u, l0_bar);
     }
-    __syncthreads();
-    mbar_wait(&bar, 0);
-    {   // ASCII -> symbol codes, in place; consecutive threads take consecutive 16-byte chunks
-        uint4* v = reinterpret_cast<uint4*>(kf_smem + (lo - base));
-        for (uint32_t i = tid; i < bytes / 16; i += kKfThreads) {
-            uint4 w = v[i];
-            w.x = kf_codes4(w.x); w.y = kf_codes4(w.y); w.z = kf_codes4(w.z); w.w = kf_codes4(w.w);
-            v[i] = w;
-        }
-    }
-    __syncthreads();
-    const int64_t p0 = tile0 + (int64_t)tid * kKfPerThread;     // first end position of this thread
-    if (p0 >= a.n_bases) return;
+    __syncthreads();                                            // barriers initialised
+    const int stride = gridDim.x * n_warps;
+    int tile = blockIdx.x * n_warps + warp;
+    if (lane == 0 && tile < a.n_tiles) stage(tile, 0);
+    mbar_wait(l0_bar, 0);
     const uint32_t* __restrict__ bloom = a.f.bloom;
     const uint32_t bshift = a.f.bloom_shift;
-    const unsigned char* __restrict__ mine = kf_smem + halo + tid * kKfPerThread;
-    for (int c = 0; c < a.f.n_classes; ++c) {
-        const int k = a.f.cls[c].k;
-        const unsigned long long salt = a.f.cls[c].salt;
-        int back = k - 1;                                       // symbols before p0 that enter the first k-mer
-        if (back > p0) back = (int)p0;
-        if (a.f.cls[c].exact) {
-            const unsigned long long mask = a.f.cls[c].key_mask;
-            unsigned long long key = 0;
-            for (int j = -back; j < 0; ++j) key = (key << 3) | mine[j];
-#pragma unroll 1
-            for (int ch = 0; ch < kKfPerThread / 16; ++ch) {
-                const uint4 w4 = *reinterpret_cast<const uint4*>(mine + ch * 16);
-                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                for (int g = 0; g < 16 / kKfGroup; ++g) {
-                    uint32_t words[kKfGroup], masks[kKfGroup];
-#pragma unroll
-                    for (int j = 0; j < kKfGroup; ++j) {
-                        const int b = g * kKfGroup + j;
-                        const uint32_t code = (w[b >> 2] >> ((b & 3) * 8)) & 0xffu;
-                        key = ((key << 3) | code) & mask;
-                        uint32_t aa;
-                        kf_hash(key, salt, aa, masks[j]);
-                        words[j] = __ldg(bloom + (aa >> bshift));
-                    }
-                    uint32_t hits = 0;
-#pragma unroll
-                    for (int j = 0; j < kKfGroup; ++j) hits |= ((words[j] & masks[j]) == masks[j] ? 1u : 0u) << j;
-                    if (hits) kf_slow_path(a, c, hits, p0 + ch * 16 + g * kKfGroup, kf_smem, base);
-                }
-            }
-        } else {
-            const unsigned long long bk = a.f.cls[c].bk;
-            unsigned long long key = 0;
-            int fed = 0;
-            for (int j = -back; j < 0; ++j, ++fed) key = key * kKfBase + (mine[j] + 1u);
-#pragma unroll 1
-            for (int j = 0; j < kKfPerThread; ++j) {
-                key = key * kKfBase + (mine[j] + 1u);
-                if (fed == k) key -= (mine[j - k] + 1u) * bk; else ++fed;
-                uint32_t aa, m;
-                kf_hash(key, salt, aa, m);
-                if ((__ldg(bloom + (aa >> bshift)) & m) == m) kf_slow_path(a, c, 1u, p0 + j, kf_smem, base);
+
+    for (int it = 0; tile < a.n_tiles; tile += stride, ++it) {
+        const int b = it & 1;
+        if (lane == 0 && tile + stride < a.n_tiles) {
+            fence_proxy_async_smem();                           // buffer b^1 was last touched by generic loads/stores
+            stage(tile + stride, b ^ 1);
+        }
+        mbar_wait(&my_bars[b], (it >> 1) & 1);
+        const int64_t tile0 = (int64_t)tile * kKfTile;
+        const int64_t base = tile0 - halo;                      // text position of buf[0]
+        const int64_t lo = base < 0 ? 0 : base;
+        const int64_t hi = tile0 + kKfTile < n16 ? tile0 + kKfTile : n16;
+        const uint32_t bytes = (uint32_t)(hi - lo);
+        unsigned char* buf = my_bufs + (size_t)b * buf_bytes;
+        {   // ASCII -> symbol codes, in place; consecutive lanes take consecutive 16-byte chunks
+            uint4* v = reinterpret_cast<uint4*>(buf + (lo - base));
+            for (uint32_t i = lane; i < bytes / 16; i += 32) {
+                uint4 w = v[i];
+                w.x = kf_codes4(w.x); w.y = kf_codes4(w.y); w.z = kf_codes4(w.z); w.w = kf_codes4(w.w);
+                v[i] = w;
             }
         }
+        __syncwarp();
+        const int64_t p0 = tile0 + (int64_t)lane * kKfPerThread;    // first end position of this lane
+        if (p0 < a.n_bases) {
+            const unsigned char* __restrict__ mine = buf + halo + lane * kKfPerThread;
+            for (int c = 0; c < a.f.n_classes; ++c) {
+                const int k = a.f.cls[c].k;
+                const unsigned long long salt = a.f.cls[c].salt;
+                int back = k - 1;                                   // symbols before p0 that enter the first k-mer
+                if (back > p0) back = (int)p0;
+                if (a.f.cls[c].exact) {
+                    const unsigned long long mask = a.f.cls[c].key_mask;
+                    unsigned long long key = 0;
+                    for (int j = -back; j < 0; ++j) key = (key << 3) | mine[j];
+#pragma unroll 1
+                    for (int ch = 0; ch < kKfPerThread / 16; ++ch) {
+                        const uint4 w4 = *reinterpret_cast<const uint4*>(mine + ch * 16);
+                        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int g = 0; g < 16 / kKfGroup; ++g) {
+                            uint32_t as[kKfGroup];
+                            uint32_t pass = 0;
+#pragma unroll
+                            for (int j = 0; j < kKfGroup; ++j) {      // level 0: shared-memory bitmap
+                                const int bb = g * kKfGroup + j;
+                                const uint32_t code = (w[bb >> 2] >> ((bb & 3) * 8)) & 0xffu;
+                                key = ((key << 3) | code) & mask;
+                                kf_hash(key, salt, as[j]);
+                                const uint32_t bit = as[j] & (kKfL0Bits - 1);
+                                pass |= ((l0[bit >> 5] >> (bit & 31)) & 1u) << j;
+                            }
+                            if (pass) {                               // level 1: blocked Bloom filter in L2
+                                uint32_t words[kKfGroup];
+#pragma unroll
+                                for (int j = 0; j < kKfGroup; ++j)
+                                    words[j] = (pass >> j & 1u) ? __ldg(bloom + (as[j] >> bshift)) : 0u;
+                                uint32_t hits = 0;
+#pragma unroll
+                                for (int j = 0; j < kKfGroup; ++j) {
+                                    const uint32_t m = kf_bloom_mask(as[j]);
+                                    hits |= ((words[j] & m) == m ? 1u : 0u) << j;
+                                }
+                                hits &= pass;
+                                if (hits) kf_slow_path(a, c, hits, p0 + ch * 16 + g * kKfGroup, buf, base, tile);
+                            }
+                        }
+                    }
+                } else {
+                    const unsigned long long bk = a.f.cls[c].bk;
+                    unsigned long long key = 0;
+                    int fed = 0;
+                    for (int j = -back; j < 0; ++j, ++fed) key = key * kKfBase + (mine[j] + 1u);
+#pragma unroll 1
+                    for (int j = 0; j < kKfPerThread; ++j) {
+                        key = key * kKfBase + (mine[j] + 1u);
+                        if (fed == k) key -= (mine[j - k] + 1u) * bk; else ++fed;
+                        uint32_t aa;
+                        kf_hash(key, salt, aa);
+                        const uint32_t bit = aa & (kKfL0Bits - 1);
+                        if ((l0[bit >> 5] >> (bit & 31)) & 1u) {
+                            const uint32_t m = kf_bloom_mask(aa);
+                            if ((__ldg(bloom + (aa >> bshift)) & m) == m) kf_slow_path(a, c, 1u, p0 + j, buf, base, tile);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();                                           // every lane is done with buffer b
     }
 }
 
