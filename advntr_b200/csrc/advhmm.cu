@@ -821,7 +821,7 @@ int kfilter_build(advhmm_kfilter* kf, int64_t n, const char* words, const int64_
         else          for (char ch : w.codes) key = key * kKfBase + ((unsigned long long)ch + 1u);
         uint32_t a;
         const unsigned long long h = kf_hash(key, cl.salt, a);
-        bloom[a >> (32 - bbits)] |= kf_bloom_mask(a);
+        bloom[a >> (32 - bbits)] |= 1u << kf_bloom_bit(h);
         l0[(a & (kKfL0Bits - 1)) >> 5] |= 1u << (a & 31);
         unsigned long long slot = kf_slot(h, tsize - 1);
         while (table[slot].loci_cnt) slot = (slot + 1) & (tsize - 1);
@@ -882,7 +882,7 @@ int kfilter_scan_device(advhmm_kfilter* kf, const unsigned char* d_seqs, const i
     CU_TRY(cudaGetLastError());
     ctx->launches++;
     // warps per CTA: as many as fit next to the first-level bitmap with two (halo + tile) buffers each
-    const size_t per_warp = 2 * ((size_t)kf->dev.halo + kKfTile);
+    const size_t per_warp = 2 * ((size_t)kf->dev.halo + kKfTile) + (size_t)kKfQueue * 4;
     const size_t budget = (ctx->smem_optin > 4096 ? ctx->smem_optin - 4096 : 0);
     int n_warps = budget > (size_t)kKfL0Bytes ? (int)((budget - kKfL0Bytes) / per_warp) : 0;
     n_warps = std::min(n_warps, kKfMaxWarps);

@@ -18,10 +18,12 @@
 //     shift/or (exact key).  k > 21: a 64-bit polynomial rolling hash, verified against the
 //     keyword text on a hit (exact result either way).
 //   * level 0: every position tests one bit of a 64 KB bitmap held in shared memory (copied once
-//     per CTA); level 1: the survivors probe a blocked Bloom filter in global memory (3 bits in one
-//     32-bit word, 64 bits per keyword, L2 resident).  Eight positions are hashed before the first
+//     per CTA); level 1: the survivors test one bit of a bitmap in global memory (64 bits
+//     per keyword, L2 resident).  Eight positions are hashed before the first
 //     test, so the probes of a group overlap.
-//   * a Bloom hit takes the slow path: open-addressing table (key, class) -> list of loci that
+//   * a filter hit is queued in shared memory and resolved when the warp's tile is done, one hit per
+//     lane (resolving it where it occurs would run the whole warp through the lookup for one lane):
+//     open-addressing table (key, class) -> list of loci that
 //     own the keyword; which read the position belongs to is found by a binary search in seq_off
 //     restricted to the reads that intersect the tile (device-computed tile_first[]); k-mers that
 //     would span a read boundary are rejected there -- the main loop carries no boundary logic.
@@ -79,18 +81,18 @@ __host__ __device__ __forceinline__ int kf_code(unsigned char ch)
     return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
 }
 
-// -> a: 32 well-mixed bits (first-level bit = low bits, Bloom word = top bits); returns the full product
+// h = key * M + salt (the salt separates the length classes and rides on the multiply-add for free).
+// a = high word: first-level bit = its low bits, Bloom word = its top bits; the Bloom bit inside the
+// word comes from the top of the low word.
 __host__ __device__ __forceinline__ unsigned long long kf_hash(unsigned long long key, unsigned long long salt, uint32_t& a)
 {
-    const unsigned long long h = (key ^ salt) * kKfMul;
+    const unsigned long long h = key * kKfMul + salt;
     a = (uint32_t)(h >> 32);
     return h;
 }
-// the three Bloom bits (inside one 32-bit word) of a key with mixed hash a
-__host__ __device__ __forceinline__ uint32_t kf_bloom_mask(uint32_t a)
+__host__ __device__ __forceinline__ uint32_t kf_bloom_bit(unsigned long long h)
 {
-    const uint32_t b = a * 0x85EBCA6Bu;
-    return (1u << (b >> 27)) | (1u << ((b >> 22) & 31)) | (1u << ((b >> 17) & 31));
+    return (uint32_t)h >> 27;
 }
 __host__ __device__ __forceinline__ unsigned long long kf_slot(unsigned long long h, unsigned long long mask)
 {
@@ -130,50 +132,62 @@ __device__ __forceinline__ void kf_count(const KfScanArgs& a, int r, int32_t loc
     *a.overflow = 1;
 }
 
-// Bloom hits (bit j of `hits`: end position p_first + j) of class c: exact lookup, read lookup,
-// boundary check, counting.  The k-mer is re-read from shared memory, so the main loop keeps no
-// per-position state alive.
-__device__ __noinline__ void kf_slow_path(const KfScanArgs& a, int c, uint32_t hits, int64_t p_first,
-                                          const unsigned char* __restrict__ sm, int64_t base, int tile)
+constexpr int kKfQueue = 128;                            // pending filter hits per warp and tile
+
+// One filter hit (end position p, length class c): exact lookup, read lookup, boundary check, counting.
+// The k-mer is re-read from the warp's tile buffer, so the scan loop keeps no per-position state.
+__device__ __noinline__ void kf_resolve(const KfScanArgs& a, int c, int64_t p,
+                                        const unsigned char* __restrict__ sm, int64_t base, int tile)
 {
     const KfClass cl = a.f.cls[c];
     const int k = cl.k;
+    if (p >= a.n_bases || p - k + 1 < 0) return;
+    const unsigned char* __restrict__ s = sm + (p - k + 1 - base);     // the k-mer's symbol codes
+    unsigned long long key = 0;
+    if (cl.exact) for (int j = 0; j < k; ++j) key = (key << 3) | s[j];
+    else          for (int j = 0; j < k; ++j) key = key * kKfBase + (s[j] + 1u);
+    uint32_t aa;
+    const unsigned long long h = kf_hash(key, cl.salt, aa);
+    unsigned long long slot = kf_slot(h, a.f.table_mask);
+    for (;;) {
+        const KfEntry* e = a.f.table + slot;
+        const uint32_t cnt = e->loci_cnt;
+        if (cnt == 0) return;                                          // empty slot: not a keyword
+        if (e->key == key && e->cls == (uint32_t)c) {
+            bool same = true;
+            if (!cl.exact) {
+                const uint8_t* __restrict__ t = a.f.text + e->text_off;
+                for (int j = 0; j < k && same; ++j) same = (s[j] == t[j]);
+            }
+            if (same) {
+                // the read that owns position p: the last one with seq_off[r] <= p
+                int lo = a.tile_first[tile], hi = a.tile_first[tile + 1];
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (a.seq_off[mid] <= p) lo = mid; else hi = mid - 1;
+                }
+                if (p - k + 1 >= a.seq_off[lo]) {                      // else it starts in the previous read
+                    const uint32_t off = e->loci_off;
+                    for (uint32_t j = 0; j < cnt; ++j) kf_count(a, lo, a.f.loci[off + j]);
+                }
+                return;                                                // (keyword, class) is unique in the table
+            }
+        }
+        slot = (slot + 1) & a.f.table_mask;
+    }
+}
+
+// Filter hits are rare per lane but not per warp; resolving them where they occur would run the whole
+// warp through the lookup for one lane's sake.  They are queued per warp (bit j of `hits`: end position
+// p_first + j) and resolved together, one hit per lane, when the tile is done.
+__device__ __forceinline__ void kf_enqueue(const KfScanArgs& a, int c, uint32_t hits, int64_t p_first, int64_t tile0,
+                                           uint32_t* q, uint32_t* q_cnt, const unsigned char* sm, int64_t base, int tile)
+{
     for (; hits; hits &= hits - 1) {
         const int64_t p = p_first + (__ffs(hits) - 1);
-        if (p >= a.n_bases || p - k + 1 < 0) continue;
-        const unsigned char* __restrict__ s = sm + (p - k + 1 - base);     // the k-mer's symbol codes
-        unsigned long long key = 0;
-        if (cl.exact) for (int j = 0; j < k; ++j) key = (key << 3) | s[j];
-        else          for (int j = 0; j < k; ++j) key = key * kKfBase + (s[j] + 1u);
-        uint32_t aa;
-        const unsigned long long h = kf_hash(key, cl.salt, aa);
-        unsigned long long slot = kf_slot(h, a.f.table_mask);
-        for (;;) {
-            const KfEntry* e = a.f.table + slot;
-            const uint32_t cnt = e->loci_cnt;
-            if (cnt == 0) break;                                           // empty slot: not a keyword
-            if (e->key == key && e->cls == (uint32_t)c) {
-                bool same = true;
-                if (!cl.exact) {
-                    const uint8_t* __restrict__ t = a.f.text + e->text_off;
-                    for (int j = 0; j < k && same; ++j) same = (s[j] == t[j]);
-                }
-                if (same) {
-                    // the read that owns position p: the last one with seq_off[r] <= p
-                    int lo = a.tile_first[tile], hi = a.tile_first[tile + 1];
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (a.seq_off[mid] <= p) lo = mid; else hi = mid - 1;
-                    }
-                    if (p - k + 1 >= a.seq_off[lo]) {                      // else it starts in the previous read
-                        const uint32_t off = e->loci_off;
-                        for (uint32_t j = 0; j < cnt; ++j) kf_count(a, lo, a.f.loci[off + j]);
-                    }
-                    break;                                                 // (keyword, class) is unique in the table
-                }
-            }
-            slot = (slot + 1) & a.f.table_mask;
-        }
+        const uint32_t i = atomicAdd(q_cnt, 1u);
+        if (i < (uint32_t)kKfQueue) q[i] = (uint32_t)(p - tile0) | ((uint32_t)c << 16);
+        else kf_resolve(a, c, p, sm, base, tile);                      // queue full: resolve on the spot
     }
 }
 
@@ -186,7 +200,7 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 // w, w + W, w + 2W, ... (W = warps in the grid), staging tile + halo with its own TMA bulk copy into
 // its own pair of buffers (the next tile is in flight while the current one is scanned) and never
 // meets a CTA-wide barrier after start-up -- a slow path taken by one warp delays nobody else.
-// Dynamic shared memory: [first-level bitmap kKfL0Bytes][warp 0: buffer 0, buffer 1][warp 1: ...]
+// Dynamic shared memory: [first-level bitmap kKfL0Bytes][warp 0: buffer 0, buffer 1][warp 1: ...][hit queues]
 __global__ void __launch_bounds__(kKfMaxWarps * 32, 1) kfilter_scan_kernel(const __grid_constant__ KfScanArgs a)
 {
     extern __shared__ __align__(128) unsigned char kf_smem[];
@@ -198,6 +212,10 @@ __global__ void __launch_bounds__(kKfMaxWarps * 32, 1) kfilter_scan_kernel(const
     const uint32_t* l0 = reinterpret_cast<const uint32_t*>(kf_smem);
     unsigned char* my_bufs = kf_smem + kKfL0Bytes + (size_t)warp * 2 * buf_bytes;
     uint64_t* my_bars = bars + 2 * warp;
+    __shared__ uint32_t q_cnts[kKfMaxWarps];
+    uint32_t* q = reinterpret_cast<uint32_t*>(kf_smem + kKfL0Bytes + (size_t)n_warps * 2 * buf_bytes) + warp * kKfQueue;
+    uint32_t* q_cnt = &q_cnts[warp];
+    if (lane == 0) *q_cnt = 0;
     uint64_t* l0_bar = bars + 2 * kKfMaxWarps;
     const int64_t n16 = (a.n_bases + 15) & ~(int64_t)15;
 
@@ -264,30 +282,25 @@ __global__ void __launch_bounds__(kKfMaxWarps * 32, 1) kfilter_scan_kernel(const
                         const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                         for (int g = 0; g < 16 / kKfGroup; ++g) {
-                            uint32_t as[kKfGroup];
+                            uint32_t as[kKfGroup], bs[kKfGroup];
                             uint32_t pass = 0;
 #pragma unroll
                             for (int j = 0; j < kKfGroup; ++j) {      // level 0: shared-memory bitmap
                                 const int bb = g * kKfGroup + j;
                                 const uint32_t code = (w[bb >> 2] >> ((bb & 3) * 8)) & 0xffu;
                                 key = ((key << 3) | code) & mask;
-                                kf_hash(key, salt, as[j]);
+                                bs[j] = kf_bloom_bit(kf_hash(key, salt, as[j]));
                                 const uint32_t bit = as[j] & (kKfL0Bits - 1);
                                 pass |= ((l0[bit >> 5] >> (bit & 31)) & 1u) << j;
                             }
-                            if (pass) {                               // level 1: blocked Bloom filter in L2
-                                uint32_t words[kKfGroup];
-#pragma unroll
-                                for (int j = 0; j < kKfGroup; ++j)
-                                    words[j] = (pass >> j & 1u) ? __ldg(bloom + (as[j] >> bshift)) : 0u;
+                            if (pass) {                               // level 1: one-bit Bloom filter in L2
                                 uint32_t hits = 0;
 #pragma unroll
                                 for (int j = 0; j < kKfGroup; ++j) {
-                                    const uint32_t m = kf_bloom_mask(as[j]);
-                                    hits |= ((words[j] & m) == m ? 1u : 0u) << j;
+                                    const uint32_t word = (pass >> j & 1u) ? __ldg(bloom + (as[j] >> bshift)) : 0u;
+                                    hits |= ((word >> bs[j]) & 1u) << j;
                                 }
-                                hits &= pass;
-                                if (hits) kf_slow_path(a, c, hits, p0 + ch * 16 + g * kKfGroup, buf, base, tile);
+                                if (hits) kf_enqueue(a, c, hits, p0 + ch * 16 + g * kKfGroup, tile0, q, q_cnt, buf, base, tile);
                             }
                         }
                     }
@@ -301,17 +314,25 @@ __global__ void __launch_bounds__(kKfMaxWarps * 32, 1) kfilter_scan_kernel(const
                         key = key * kKfBase + (mine[j] + 1u);
                         if (fed == k) key -= (mine[j - k] + 1u) * bk; else ++fed;
                         uint32_t aa;
-                        kf_hash(key, salt, aa);
+                        const uint32_t bb = kf_bloom_bit(kf_hash(key, salt, aa));
                         const uint32_t bit = aa & (kKfL0Bits - 1);
-                        if ((l0[bit >> 5] >> (bit & 31)) & 1u) {
-                            const uint32_t m = kf_bloom_mask(aa);
-                            if ((__ldg(bloom + (aa >> bshift)) & m) == m) kf_slow_path(a, c, 1u, p0 + j, buf, base, tile);
-                        }
+                        if ((l0[bit >> 5] >> (bit & 31)) & 1u)
+                            if ((__ldg(bloom + (aa >> bshift)) >> bb) & 1u) kf_enqueue(a, c, 1u, p0 + j, tile0, q, q_cnt, buf, base, tile);
                     }
                 }
             }
         }
-        __syncwarp();                                           // every lane is done with buffer b
+        __syncwarp();
+        {   // resolve the queued hits of this tile, one per lane
+            const uint32_t n = min(*q_cnt, (uint32_t)kKfQueue);
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t e = q[i];
+                kf_resolve(a, (int)(e >> 16), tile0 + (int64_t)(e & 0xffffu), buf, base, tile);
+            }
+            __syncwarp();
+            if (lane == 0) *q_cnt = 0;
+            __syncwarp();                                       // every lane is done with buffer b
+        }
     }
 }
 
