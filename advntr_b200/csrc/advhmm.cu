@@ -31,6 +31,7 @@
 #include "kernels_kfilter.cuh"
 
 #include <algorithm>
+#include <set>
 #include <unordered_map>
 
 namespace {
@@ -252,14 +253,30 @@ struct ProfScope {
     ~ProfScope() { if (stop) cudaEventRecord(stop, ctx->stream); }
 };
 
+// Dynamic shared memory above 48 KB needs an opt-in that is a property of the KERNEL (per device),
+// not of a context: raise it once per (kernel, device) to the device maximum.  (Tracking the value
+// per context let a second context lower the limit under the first one's feet.)
+template <typename Kernel>
+int allow_max_dynamic_smem(advhmm_context* ctx, Kernel* kernel)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), ctx->device);
+    if (done.count(key)) return ADVHMM_OK;
+    cudaFuncAttributes attr{};
+    CU_TRY(cudaFuncGetAttributes(&attr, kernel));
+    const int room = (int)ctx->smem_optin - (int)attr.sharedSizeBytes;      // static shared memory counts too
+    CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, room));
+    done.insert(key);
+    return ADVHMM_OK;
+}
+
 template <int RPL, int WPB, bool ICMP>
 int launch_banded_variant(advhmm_context* ctx, int grid, int smem, const BandedArgs& args, int slot)
 {
-    if (smem > ctx->banded_smem_set[slot]) {
-        CU_TRY(cudaFuncSetAttribute(banded_fill_kernel<RPL, WPB, ICMP>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        ctx->banded_smem_set[slot] = smem;
-    }
+    (void)slot;
+    if (int rc = allow_max_dynamic_smem(ctx, banded_fill_kernel<RPL, WPB, ICMP>)) return rc;
     banded_fill_kernel<RPL, WPB, ICMP><<<grid, WPB * 32, smem, ctx->stream>>>(args);
     return ADVHMM_OK;
 }
@@ -291,11 +308,7 @@ int launch_banded_fwd_chunk(advhmm_context* ctx, int rpl, int grid, int smem, co
     ProfScope prof(ctx, 0);
 #define ADV_CASE(R)                                                                                   \
     case R:                                                                                           \
-        if (smem > ctx->banded_fwd_smem_set[R]) {                                                     \
-            CU_TRY(cudaFuncSetAttribute(banded_forward_kernel<R, 8>,                                  \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
-            ctx->banded_fwd_smem_set[R] = smem;                                                       \
-        }                                                                                             \
+        if (int rc = allow_max_dynamic_smem(ctx, banded_forward_kernel<R, 8>)) return rc;             \
         banded_forward_kernel<R, 8><<<grid, 8 * 32, smem, ctx->stream>>>(args);                       \
         break;
     switch (rpl) {
@@ -315,11 +328,7 @@ int launch_banded_f32_chunk(advhmm_context* ctx, int rpl, int grid, int smem, co
     // the fp32 image is smaller than the fp64 one, so the fp64 size is a safe dynamic-smem request
 #define ADV_CASE(R)                                                                                   \
     case R:                                                                                           \
-        if (smem > ctx->banded_f32_smem_set[R]) {                                                     \
-            CU_TRY(cudaFuncSetAttribute(banded_fill_f32_kernel<R>,                                    \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
-            ctx->banded_f32_smem_set[R] = smem;                                                       \
-        }                                                                                             \
+        if (int rc = allow_max_dynamic_smem(ctx, banded_fill_f32_kernel<R>)) return rc;               \
         banded_fill_f32_kernel<R><<<grid, 8 * 32, smem, ctx->stream>>>(args);                         \
         break;
     switch (rpl) {
@@ -594,10 +603,9 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     // ---- everything else: generic kernel ------------------------------------------------------
     if (n_generic > 0) {
         const int smem = rows_in_smem ? (int)(gwarps * 2 * gm * sizeof(double)) : 0;
-        if (smem > 48 * 1024 && smem > ctx->generic_smem_set) {
-            CU_TRY(cudaFuncSetAttribute(generic_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU_TRY(cudaFuncSetAttribute(generic_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            ctx->generic_smem_set = smem;
+        if (smem > 48 * 1024) {
+            if (int rc = allow_max_dynamic_smem(ctx, generic_fill_kernel<false>)) return rc;
+            if (int rc = allow_max_dynamic_smem(ctx, generic_fill_kernel<true>)) return rc;
         }
         for (int lo = fam_generic.first_item, end = lo + n_generic; lo < end;) {
             const int hi = next_chunk(lo, end, g_chunk);
@@ -888,10 +896,7 @@ int kfilter_scan_device(advhmm_kfilter* kf, const unsigned char* d_seqs, const i
     n_warps = std::min(n_warps, kKfMaxWarps);
     if (n_warps < 1) return set_error(ADVHMM_EUNSUPPORTED, "keyword filter: not enough shared memory for a warp pipeline");
     const size_t smem = (size_t)kKfL0Bytes + (size_t)n_warps * per_warp;
-    if ((int)smem > ctx->kfilter_smem_set) {
-        CU_TRY(cudaFuncSetAttribute(kfilter_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->kfilter_smem_set = (int)smem;
-    }
+    if (int rc = allow_max_dynamic_smem(ctx, kfilter_scan_kernel)) return rc;
     const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + n_warps - 1) / n_warps, std::max(ctx->sm_count, 1));
     unsigned long long cap = next_pow2(std::max<unsigned long long>(1 << 16, (unsigned long long)n_reads / 2));
     for (int attempt = 0; attempt < 10; ++attempt, cap <<= 2) {

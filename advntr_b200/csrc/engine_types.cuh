@@ -147,14 +147,9 @@ struct advhmm_context {
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];   // [0] banded fill, [1] backtrack
     size_t prof_used[2] = {0, 0};
-    int banded_smem_set[kMaxRPL + 4] = {0};   // dynamic-smem opt-in already applied per kernel variant
     int banded_warps = 8;        // reads per CTA of the banded kernel
     bool int_compare = false;    // integer-pipe compares (ADVHMM_ICMP=1); needs all tables <= 0
     bool launch_int_compare = false;   // ... and every model of the current batch qualifies
-    int generic_smem_set = 0;
-    int banded_f32_smem_set[kMaxRPL + 1] = {0};
-    int banded_fwd_smem_set[kMaxRPL + 1] = {0};
-    int kfilter_smem_set = 0;
     std::mutex mu;
 };
 

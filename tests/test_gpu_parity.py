@@ -307,3 +307,20 @@ def test_empty_batch_and_all_empty_reads(ctx, golden_config1):
     assert len(res) == 6 and np.all(res.logp == g.logp[1])
     assert all(np.array_equal(res.path(i), g.path(1)) for i in range(6))
     dm.close()
+
+
+def test_two_contexts_with_different_model_sizes(golden):
+    """Regression: the dynamic shared-memory opt-in is a property of the kernel, not of a context.
+    A second context decoding a SMALLER model must not lower the limit the first one relies on."""
+    from advntr_b200 import engine
+    big = Golden("divergent")            # 150 bp flanks: the largest image of the golden set
+    small = Golden("small_b")
+    ctx_a, ctx_b = engine.Context(device=0), engine.Context(device=0)
+    dm_a = engine.DeviceModel(ctx_a, big.baked)
+    dm_b = engine.DeviceModel(ctx_b, small.baked)
+    for dm, g in ((dm_a, big), (dm_b, small), (dm_a, big), (dm_b, small)):
+        res = dm.viterbi(g.codes())
+        assert same_bits(res.logp, g.logp)
+        fwd = dm.log_probability(g.codes()[:8])
+        assert np.allclose(fwd, g.forward[:8], rtol=1e-9, atol=0)
+    dm_a.close(); dm_b.close(); ctx_a.close(); ctx_b.close()
