@@ -31,6 +31,7 @@
 #include "kernels_kfilter.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <set>
 #include <unordered_map>
 
@@ -342,6 +343,26 @@ int launch_banded_f32_chunk(advhmm_context* ctx, int rpl, int grid, int smem, co
     return ADVHMM_OK;
 }
 
+constexpr size_t kMaxChunkMarks = 4096;
+
+// after a backtrack launch: snapshot the path cursor and record an event, so that the host-buffer
+// front end can start copying this chunk's paths while the next chunk runs
+int mark_chunk(advhmm_context* ctx, const unsigned long long* d_cursor)
+{
+    if (!ctx->mark_chunks || ctx->n_marks >= kMaxChunkMarks) return ADVHMM_OK;
+    const size_t i = ctx->n_marks;
+    if (i == ctx->chunk_events.size()) {
+        cudaEvent_t ev;
+        CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(ev);
+    }
+    CU_TRY(cudaMemcpyAsync(static_cast<unsigned long long*>(ctx->h_cursors.p) + i, d_cursor, sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaEventRecord(ctx->chunk_events[i], ctx->stream));
+    ctx->n_marks = i + 1;
+    return ADVHMM_OK;
+}
+
 struct OutPtrs {
     double* logp; int32_t* path_len; int64_t* path_off; int32_t* path; int64_t path_cap;
     unsigned long long* cursor;
@@ -350,9 +371,11 @@ struct OutPtrs {
 
 // Runs the whole batch on the context's stream.  All pointers in `out` and d_seqs are device
 // pointers.  seq_off / group_off are HOST arrays (planning metadata).
+// read_base / continue_cursor: the host-buffer front end feeds a large batch as several sub-batches so
+// that the planning of one overlaps the decoding of the previous one; they share the path cursor.
 int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, const int64_t* group_off,
               const uint8_t* d_seqs, const int64_t* seq_off, int n_reads, uint32_t flags,
-              const OutPtrs& out, bool forward, int32_t* d_bad)
+              const OutPtrs& out, bool forward, int32_t* d_bad, int read_base = 0, bool continue_cursor = false)
 {
     const bool want_path = (flags & ADVHMM_WANT_PATH) && !forward;
     const bool want_walk = want_path || (out.summaries && !forward);   // backtrack kernel needed
@@ -378,6 +401,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     pl.pk_words = words;
 
     Family fam_short, fam_long, fam_generic;
+    fam_short.items.reserve(n_out);                 // the common case: every read takes the short-read kernel
+    fam_short.model.reserve(n_out);
     bool all_nonpositive = true;
     for (int gi = 0; gi < n_models; ++gi) {
         advhmm_model* mod = models[gi];
@@ -478,13 +503,13 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     uint32_t* d_pk = ctx->d_pk.as<uint32_t>();
     int32_t* d_rlen = reinterpret_cast<int32_t*>(d_pk + pk_words_al);
     {
-        PackArgs pa{d_seqs, d_seq_off, d_pk_off, d_pk, d_rlen, d_bad, n_out, strands, 0};
+        PackArgs pa{d_seqs, d_seq_off, d_pk_off, d_pk, d_rlen, d_bad, n_out, strands, 0, read_base};
         pa.n_symbols = models[0]->cm.g.K;
         pack_reads_kernel<<<n_out, 32, 0, ctx->stream>>>(pa);
         CU_TRY(cudaGetLastError());
         ctx->launches++;
     }
-    if (want_path) CU_TRY(cudaMemsetAsync(out.cursor, 0, sizeof(unsigned long long), ctx->stream));
+    if (want_path && !continue_cursor) CU_TRY(cudaMemsetAsync(out.cursor, 0, sizeof(unsigned long long), ctx->stream));
 
     // ---- workspace: sized once for all families (they run one after the other on the stream),
     //      chunks end on tile boundaries --------------------------------------------------------
@@ -505,7 +530,11 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         size_t c = std::max<size_t>(ctx->workspace_budget / per_item, floor_items);
         return std::min<size_t>(c, (size_t)n_items);
     };
-    const size_t s_chunk = chunk_of(s_per_item, n_short, (size_t)kBandedWarpsMax * ctx->sm_count);
+    size_t s_chunk = chunk_of(s_per_item, n_short, (size_t)kBandedWarpsMax * ctx->sm_count);
+    // host-buffer calls that return state paths: at least eight chunks when the batch is large, so that
+    // the paths of chunk i travel to the host while chunk i+1 is decoded (run_host)
+    if (ctx->mark_chunks && ctx->host_chunks > 1 && n_short >= ctx->host_chunks * 32768)
+        s_chunk = std::min<size_t>(s_chunk, ((size_t)n_short + ctx->host_chunks - 1) / ctx->host_chunks);
     const size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)kLongWarps);
     const size_t g_chunk = chunk_of(g_per_item, n_generic, (size_t)gwarps);
     // short layout
@@ -571,6 +600,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         if (want_walk) {
             rc = launch_backtrack(lo, hi - lo, rpl, fa.tbw, fa.tbw_stride, fa.acc_tb, (size_t)fa.acc_stride, fa.ftb);
             if (rc) return rc;
+            if (want_path && (rc = mark_chunk(ctx, out.cursor))) return rc;
         }
         lo = hi;
     }
@@ -596,6 +626,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         if (want_walk) {
             int rc = launch_backtrack(lo, hi - lo, kLongRPL, la.tbw, la.tbw_stride, la.acc_tb, la.acc_stride, la.ftb);
             if (rc) return rc;
+            if (want_path && (rc = mark_chunk(ctx, out.cursor))) return rc;
         }
         lo = hi;
     }
@@ -633,6 +664,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
                 generic_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
                 CU_TRY(cudaGetLastError());
                 ctx->launches++;
+                if (want_path) { int rc = mark_chunk(ctx, out.cursor); if (rc) return rc; }
             }
             lo = hi;
         }
@@ -682,13 +714,64 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
                want_sum ? reinterpret_cast<advhmm_read_summary*>(d + o_sum) : nullptr};
     int32_t* d_bad = reinterpret_cast<int32_t*>(d + o_bad);
     CU_TRY(cudaMemsetAsync(d_bad, 0x7f, sizeof(int32_t), ctx->stream));
-    int rc = run_batch(ctx, models, n_models, group_off, ctx->d_seqs.as<uint8_t>(), seq_off, n_reads, flags, op,
-                       forward, d_bad);
+    ctx->n_marks = 0;
+    ctx->mark_chunks = false;
+    static const bool dbg = getenv("ADVHMM_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
+    if (want_path && cap > 0 && !getenv("ADVHMM_NO_OVERLAP")) {
+        if (!ctx->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CU_TRY(ctx->h_cursors.ensure(kMaxChunkMarks * sizeof(unsigned long long)));
+        ctx->mark_chunks = true;
+    }
+    // Large batches of many models go to the device as up to four sub-batches (cut at model boundaries):
+    // planning sub-batch k+1 on the host overlaps decoding sub-batch k on the device.
+    int n_sub = (n_out >= 262144 && n_models >= 8) ? 4 : 1;
+    ctx->host_chunks = n_sub > 1 ? 2 : 8;
+    int rc = ADVHMM_OK;
+    std::vector<int64_t> rebased;
+    if (want_path) CU_TRY(cudaMemsetAsync(op.cursor, 0, sizeof(unsigned long long), ctx->stream));
+    for (int k = 0, g0 = 0; k < n_sub && rc == ADVHMM_OK; ++k) {
+        int g1 = n_models;
+        if (k + 1 < n_sub) {
+            const int64_t want = (int64_t)n_reads * (k + 1) / n_sub;      // reads before the cut
+            g1 = (int)(std::lower_bound(group_off + g0, group_off + n_models, want) - group_off);
+            g1 = std::max(g1, g0);
+        }
+        if (g1 == g0 && k + 1 < n_sub) continue;
+        const int64_t r0 = group_off[g0], r1 = group_off[g1];
+        rebased.assign(group_off + g0, group_off + g1 + 1);
+        for (int64_t& v : rebased) v -= r0;
+        OutPtrs sub = op;
+        sub.logp += r0 * strands; sub.path_len += r0 * strands; sub.path_off += r0 * strands;
+        if (sub.summaries) sub.summaries += r0 * strands;
+        rc = run_batch(ctx, models + g0, g1 - g0, rebased.data(), ctx->d_seqs.as<uint8_t>(), seq_off + r0, (int)(r1 - r0),
+                       flags, sub, forward, d_bad, (int)r0, /*continue_cursor=*/true);
+        g0 = g1;
+    }
+    ctx->mark_chunks = false;
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    const double t_enq = now();
+    // state paths: every finished chunk goes home on the copy stream while the next one is decoded
+    // (chunks run one after the other and allocate from one cursor, so chunk i owns
+    // [cursor after chunk i-1, cursor after chunk i) of the path buffer)
+    unsigned long long copied = 0;
+    for (size_t i = 0; i < ctx->n_marks; ++i) {
+        CU_TRY(cudaEventSynchronize(ctx->chunk_events[i]));
+        const unsigned long long upto = std::min<unsigned long long>(
+            static_cast<const unsigned long long*>(ctx->h_cursors.p)[i], (unsigned long long)cap);
+        if (upto > copied) {
+            CU_TRY(cudaMemcpyAsync(path + copied, ctx->d_paths.as<int32_t>() + copied, (size_t)(upto - copied) * sizeof(int32_t),
+                                   cudaMemcpyDeviceToHost, ctx->copy_stream));
+            copied = upto;
+        }
+    }
+    const double t_marks = now();
     // results back
     CU_TRY(ctx->h_out.ensure(out_bytes));
     CU_TRY(cudaMemcpyAsync(ctx->h_out.p, d, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
+    const double t_sync = now();
     const unsigned char* h = static_cast<const unsigned char*>(ctx->h_out.p);
     int32_t bad;
     memcpy(&bad, h + o_bad, sizeof bad);
@@ -704,11 +787,15 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
         unsigned long long total;
         memcpy(&total, h + o_cursor, sizeof total);
         *path_total = (int64_t)total;
+        if (ctx->copy_stream) CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
         if ((int64_t)total > path_cap)
             return set_error(ADVHMM_ECAPACITY, "path buffer too small: need %lld entries, have %lld",
                              (long long)total, (long long)path_cap);
-        if (total) {
-            CU_TRY(cudaMemcpyAsync(path, ctx->d_paths.p, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (dbg) fprintf(stderr, "[advhmm] host call: enqueue %.2f ms, chunk marks (%zu) %.2f ms, outputs+sync %.2f ms, copy-stream drain %.2f ms, copied %llu of %llu\n",
+                         t_enq - t_start, ctx->n_marks, t_marks - t_enq, t_sync - t_marks, now() - t_sync, copied, total);
+        if (total > copied) {               // whatever the chunk marks did not cover
+            CU_TRY(cudaMemcpyAsync(path + copied, ctx->d_paths.as<int32_t>() + copied, (size_t)(total - copied) * sizeof(int32_t),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
             CU_TRY(cudaStreamSynchronize(ctx->stream));
         }
     }
@@ -991,7 +1078,9 @@ void advhmm_context_destroy(advhmm_context* ctx)
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         for (DevBuf* b : {&ctx->d_seqs, &ctx->d_seq_off, &ctx->d_pk, &ctx->d_meta, &ctx->d_work, &ctx->d_out, &ctx->d_paths, &ctx->d_flags}) b->release();
-        ctx->h_meta.release(); ctx->h_out.release();
+        ctx->h_meta.release(); ctx->h_out.release(); ctx->h_cursors.release();
+        for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->meta_done) cudaEventDestroy(ctx->meta_done);
         for (auto& v : ctx->prof_events)
             for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }

@@ -143,6 +143,14 @@ struct advhmm_context {
     DevBuf d_seqs, d_seq_off, d_pk, d_meta, d_work, d_out, d_paths, d_flags;
     PinnedBuf h_meta, h_out;
     cudaEvent_t meta_done = nullptr;
+    // host-buffer calls: state paths go home chunk by chunk on a second stream while the next chunk
+    // is decoded (marks = cursor snapshots + events recorded after every backtrack launch)
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
+    PinnedBuf h_cursors;
+    size_t n_marks = 0;
+    bool mark_chunks = false;
+    size_t host_chunks = 8;      // chunks a host-buffer call asks run_batch for (path copies overlap decoding)
     // optional per-kernel timing (bench.py roofline): event pairs around every fill launch
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];   // [0] banded fill, [1] backtrack

@@ -76,6 +76,7 @@ struct PackArgs {
     int32_t* rlen;              // [n_out]
     int32_t* bad;               // [1]: first read index with a code >= n_symbols (atomicMin)
     int n_out, strands, n_symbols;
+    int read_base;              // index of this batch's first read in the caller's numbering (error reports)
 };
 
 __global__ void __launch_bounds__(32) pack_reads_kernel(PackArgs a)
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(32) pack_reads_kernel(PackArgs a)
         }
         out[w] = word;
     }
-    if (bad) atomicMin(a.bad, r);
+    if (bad) atomicMin(a.bad, r + a.read_base);
 }
 
 }  // namespace

@@ -324,3 +324,34 @@ def test_two_contexts_with_different_model_sizes(golden):
         fwd = dm.log_probability(g.codes()[:8])
         assert np.allclose(fwd, g.forward[:8], rtol=1e-9, atol=0)
     dm_a.close(); dm_b.close(); ctx_a.close(); ctx_b.close()
+
+
+def test_large_host_batch_is_split_and_streamed(ctx):
+    """A host-buffer call with >= 262,144 reads of >= 8 models is fed to the device as sub-batches
+    (planning overlaps decoding) whose state paths travel home chunk by chunk on a second stream.
+    Same answers as small per-model calls, whatever the split."""
+    from advntr_b200 import engine, synth
+    rng = random.Random(3)
+    models, groups, small = [], [], []
+    for lid in range(1, 13):
+        loc = synth.config2_locus(lid)
+        dm = engine.DeviceModel(ctx, loc.build_model().baked)
+        mapped, unmapped = synth.config2_reads(loc, coverage=12, decoys=6)
+        distinct = [oracle.encode(r) for r in (mapped + unmapped)[:40]]
+        reps = 23000 // len(distinct) + rng.randint(0, 3)
+        models.append(dm)
+        small.append(dm.viterbi(distinct))
+        groups.append(distinct * reps)
+    assert sum(len(g) for g in groups) >= 262144
+    res = ctx.viterbi_multi(models, groups)
+    k = 0
+    for g, ref in zip(groups, small):
+        n = len(ref)
+        want_lp = np.tile(ref.logp, len(g) // n)
+        assert same_bits(res.logp[k:k + len(g)], want_lp)
+        for i in range(0, len(g), 997):                       # a sample of the paths, every replica block
+            assert np.array_equal(res.path(k + i), ref.path(i % n))
+        assert np.array_equal(res.path_len[k:k + len(g)], np.tile(ref.path_len, len(g) // n))
+        k += len(g)
+    for dm in models:
+        dm.close()
