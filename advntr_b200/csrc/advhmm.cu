@@ -282,15 +282,25 @@ int launch_banded_variant(advhmm_context* ctx, int grid, int smem, const BandedA
     return ADVHMM_OK;
 }
 
-int launch_banded_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const BandedArgs& args)
+// Two CTAs of 8 warps per SM (126 registers/thread) as long as two model images fit in shared memory;
+// a larger image (250 bp reads: 250-base flanks, ~770 columns, 160 KB) leaves room for one CTA only, which
+// then carries 16 warps so that the SM still has 4 warps per scheduler.  (10 / 12 warps per CTA need
+// 96 / 80 registers, spill and measured 25-40 % slower; profiles/r1_variants.md.)
+int banded_warps_for(const advhmm_context* ctx, int smem_image)
+{
+    static const bool no_wide = getenv("ADVHMM_NO_WIDE_CTA") != nullptr;     // measurement knob
+    const size_t per_cta = (size_t)smem_image + 4096;          // + static shared memory + the driver's 1 KB
+    return (2 * per_cta <= ctx->smem_optin + 1024 || no_wide) ? ctx->banded_warps : kBandedWarpsMax;
+}
+
+int launch_banded_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const BandedArgs& args, int warps)
 {
     ProfScope prof(ctx, 0);
     int rc = ADVHMM_OK;
     const bool ic = ctx->launch_int_compare;
-    // 8 reads per CTA, 2 CTAs per SM (126 registers/thread).  Wider CTAs (10 / 12 warps, 96 / 80
-    // registers) spill and measured 25-40 % slower on B200; see profiles/r1_variants.md.
 #define ADV_CASE(R)                                                                              \
-    case R: rc = ic ? launch_banded_variant<R, 8, true>(ctx, grid, smem, args, R)                 \
+    case R: rc = warps == kBandedWarpsMax ? launch_banded_variant<R, kBandedWarpsMax, false>(ctx, grid, smem, args, R) \
+               : ic ? launch_banded_variant<R, 8, true>(ctx, grid, smem, args, R)                 \
                     : launch_banded_variant<R, 8, false>(ctx, grid, smem, args, R); break;
     switch (rpl) {
         ADV_CASE(1) ADV_CASE(2) ADV_CASE(3) ADV_CASE(4) ADV_CASE(5)
@@ -414,7 +424,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
             const int len = (int)(seq_off[r + 1] - seq_off[r]);
             Family* f = &fam_generic;
             if (banded) {
-                if (mod->banded_smem > 0 && len <= 32 * kMaxRPL) {
+                if (mod->banded_smem > 0 && len <= (forward ? 32 * kMaxRPL : ctx->short_max_len)) {
                     f = &fam_short;
                     pl.max_P_short = std::max(pl.max_P_short, mod->cm.b.NCpad);
                     pl.max_smem_short = std::max(pl.max_smem_short, mod->banded_smem);
@@ -465,7 +475,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
             pl.order.push_back(f.items[i]);
         }
     };
-    make_tiles(fam_short, ctx->banded_warps, 0);
+    const int short_warps = (forward || fp32) ? 8 : banded_warps_for(ctx, pl.max_smem_short);
+    make_tiles(fam_short, short_warps, 0);
     make_tiles(fam_long, kLongWarps, 1);
     make_tiles(fam_generic, gwarps, 2);
     const int n_short = (int)fam_short.items.size(), n_long = (int)fam_long.items.size();
@@ -595,7 +606,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         fa.ftb = reinterpret_cast<int32_t*>(w + so_ftb);
         int rc = forward ? launch_banded_fwd_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa)
                  : fp32  ? launch_banded_f32_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa)
-                         : launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa);
+                         : launch_banded_chunk(ctx, rpl, tile1 - tile0, pl.max_smem_short, fa, short_warps);
         if (rc) return rc;
         if (want_walk) {
             rc = launch_backtrack(lo, hi - lo, rpl, fa.tbw, fa.tbw_stride, fa.acc_tb, (size_t)fa.acc_stride, fa.ftb);
@@ -1064,6 +1075,8 @@ int advhmm_context_create(int device, void* stream, advhmm_context** out)
         ctx->workspace_budget = std::min<size_t>((size_t)96 << 30, free_b / 2);
         const char* env = getenv("ADVHMM_WORKSPACE_MB");
         if (env && atoll(env) > 0) ctx->workspace_budget = (size_t)atoll(env) << 20;
+        env = getenv("ADVHMM_SHORT_MAX_LEN");
+        if (env && atoi(env) > 0) ctx->short_max_len = std::min(atoi(env), 32 * kMaxRPL);
         env = getenv("ADVHMM_ICMP");
         if (env) ctx->int_compare = atoi(env) != 0;
     }

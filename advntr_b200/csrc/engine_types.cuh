@@ -156,6 +156,7 @@ struct advhmm_context {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];   // [0] banded fill, [1] backtrack
     size_t prof_used[2] = {0, 0};
     int banded_warps = 8;        // reads per CTA of the banded kernel
+    int short_max_len = 32 * kMaxRPL;   // longer reads take the striped long-read kernel (ADVHMM_SHORT_MAX_LEN)
     bool int_compare = false;    // integer-pipe compares (ADVHMM_ICMP=1); needs all tables <= 0
     bool launch_int_compare = false;   // ... and every model of the current batch qualifies
     std::mutex mu;

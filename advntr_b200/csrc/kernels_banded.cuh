@@ -227,7 +227,7 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
 }
 
 template <int RPL, int WPB, bool ICMP>
-__global__ void __launch_bounds__(WPB * 32, 2)
+__global__ void __launch_bounds__(WPB * 32, WPB > 8 ? 1 : 2)
 banded_fill_kernel(const BandedArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];

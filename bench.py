@@ -32,7 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-READ_LEN = 150
+READ_LEN = int(os.environ.get("ADVNTR_BENCH_READ_LEN", "150"))   # 150 = BASELINE config 2; other lengths for side experiments only
 
 
 def parse_args():

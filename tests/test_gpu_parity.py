@@ -355,3 +355,24 @@ def test_large_host_batch_is_split_and_streamed(ctx):
         k += len(g)
     for dm in models:
         dm.close()
+
+
+def test_250bp_reads_large_image_takes_the_16_warp_kernel(ctx):
+    """250 bp reads: 250-base flanks in the model (vntr_finder.py:131), ~770 columns, a 160 KB image:
+    one 16-warp CTA per SM instead of two 8-warp CTAs.  Bit-exact against the oracle."""
+    from advntr_b200 import engine, synth
+    rng = random.Random(250)
+    ru = synth.rand_dna(rng, 24)
+    segs = [synth.substitute(rng, ru, 0.03) for _ in range(5)]
+    loc = synth.Locus(77, synth.rand_dna(rng, 400), synth.rand_dna(rng, 400), segs, read_length=250, flank=250)
+    model = loc.build_model()
+    dm = engine.DeviceModel(ctx, model.baked)
+    assert dm.kind == "banded" and dm.info.smem_bytes > 113 * 1024
+    reads = loc.reads(rng, 70) + [synth.revcomp(r) for r in loc.reads(rng, 10)]
+    reads += [loc.reads(rng, 1, length=L)[0] for L in (161, 200, 249, 251, 300, 320)]
+    codes = [oracle.encode(r) for r in reads]
+    want_lp, want_paths = oracle.OracleModel(model.baked).viterbi(codes)
+    res = dm.viterbi(codes)
+    assert same_bits(res.logp, want_lp)
+    assert_paths_equal([res.path(i) for i in range(len(res))], want_paths)
+    dm.close()
