@@ -22,6 +22,13 @@ DEFAULT_MAX_ERROR_RATE = 0.05     # settings.py:28 (Illumina); 0.3 for PacBio/na
 
 
 # --------------------------------------------------------------------------------- profile
+class _SparseRow(dict):
+    """A transition row of the repeat profile: pairs the alignment never showed read as 0."""
+
+    def __missing__(self, key):
+        return 0
+
+
 def repeat_profile(alignment, error_rate):
     """Transition / emission probabilities of one repeat unit from aligned repeat segments.
 
@@ -122,15 +129,13 @@ def repeat_profile(alignment, error_rate):
             elif len(row) == 2:
                 row[b] = 1.0 / 2
 
+    # profile_hmm.py:150-160 fills in a 0 for every (state, state) pair that was never seen; rows that
+    # answer 0 for a missing key say the same without the (3R+2)^2 dictionary writes per locus
     labels = ["unit_start", "I0"]
     for i in range(1, R + 1):
         labels += ["M%d" % i, "D%d" % i, "I%d" % i]
     labels.append("unit_end")
-    for a in labels:
-        row = transition.setdefault(a, {})
-        for b in labels:
-            row.setdefault(b, 0)
-    return transition, emission
+    return {a: _SparseRow(transition.get(a, ())) for a in labels}, emission
 
 
 def align_repeat_segments(segments):
