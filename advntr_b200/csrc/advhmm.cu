@@ -273,12 +273,11 @@ int allow_max_dynamic_smem(advhmm_context* ctx, Kernel* kernel)
     return ADVHMM_OK;
 }
 
-template <int RPL, int WPB, bool ICMP>
-int launch_banded_variant(advhmm_context* ctx, int grid, int smem, const BandedArgs& args, int slot)
+template <int RPL, int WPB>
+int launch_banded_variant(advhmm_context* ctx, int grid, int smem, const BandedArgs& args)
 {
-    (void)slot;
-    if (int rc = allow_max_dynamic_smem(ctx, banded_fill_kernel<RPL, WPB, ICMP>)) return rc;
-    banded_fill_kernel<RPL, WPB, ICMP><<<grid, WPB * 32, smem, ctx->stream>>>(args);
+    if (int rc = allow_max_dynamic_smem(ctx, banded_fill_kernel<RPL, WPB>)) return rc;
+    banded_fill_kernel<RPL, WPB><<<grid, WPB * 32, smem, ctx->stream>>>(args);
     return ADVHMM_OK;
 }
 
@@ -297,11 +296,9 @@ int launch_banded_chunk(advhmm_context* ctx, int rpl, int grid, int smem, const 
 {
     ProfScope prof(ctx, 0);
     int rc = ADVHMM_OK;
-    const bool ic = ctx->launch_int_compare;
 #define ADV_CASE(R)                                                                              \
-    case R: rc = warps == kBandedWarpsMax ? launch_banded_variant<R, kBandedWarpsMax, false>(ctx, grid, smem, args, R) \
-               : ic ? launch_banded_variant<R, 8, true>(ctx, grid, smem, args, R)                 \
-                    : launch_banded_variant<R, 8, false>(ctx, grid, smem, args, R); break;
+    case R: rc = warps == kBandedWarpsMax ? launch_banded_variant<R, kBandedWarpsMax>(ctx, grid, smem, args) \
+                                          : launch_banded_variant<R, 8>(ctx, grid, smem, args); break;
     switch (rpl) {
         ADV_CASE(1) ADV_CASE(2) ADV_CASE(3) ADV_CASE(4) ADV_CASE(5)
         ADV_CASE(6) ADV_CASE(7) ADV_CASE(8) ADV_CASE(9) ADV_CASE(10)
@@ -413,7 +410,6 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     Family fam_short, fam_long, fam_generic;
     fam_short.items.reserve(n_out);                 // the common case: every read takes the short-read kernel
     fam_short.model.reserve(n_out);
-    bool all_nonpositive = true;
     for (int gi = 0; gi < n_models; ++gi) {
         advhmm_model* mod = models[gi];
         if (!mod || mod->ctx != ctx) return set_error(ADVHMM_EINVAL, "model %d does not belong to this context", gi);
@@ -428,7 +424,6 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
                     f = &fam_short;
                     pl.max_P_short = std::max(pl.max_P_short, mod->cm.b.NCpad);
                     pl.max_smem_short = std::max(pl.max_smem_short, mod->banded_smem);
-                    all_nonpositive = all_nonpositive && mod->cm.b.nonpositive;
                 } else if (!forward) {
                     f = &fam_long;
                     pl.max_P_long = std::max(pl.max_P_long, mod->cm.b.NCpad);
@@ -442,7 +437,6 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
             }
         }
     }
-    ctx->launch_int_compare = ctx->int_compare && all_nonpositive;
     if (fp32 && (!fam_long.items.empty() || !fam_generic.items.empty()))
         return set_error(ADVHMM_EUNSUPPORTED, "fp32 mode is implemented for the short-read banded kernel only "
                                               "(profile-shaped model, reads <= %d bases)", 32 * kMaxRPL);
@@ -1077,8 +1071,6 @@ int advhmm_context_create(int device, void* stream, advhmm_context** out)
         if (env && atoll(env) > 0) ctx->workspace_budget = (size_t)atoll(env) << 20;
         env = getenv("ADVHMM_SHORT_MAX_LEN");
         if (env && atoi(env) > 0) ctx->short_max_len = std::min(atoi(env), 32 * kMaxRPL);
-        env = getenv("ADVHMM_ICMP");
-        if (env) ctx->int_compare = atoi(env) != 0;
     }
     *out = ctx.release();
     return ADVHMM_OK;

@@ -157,8 +157,6 @@ struct advhmm_context {
     size_t prof_used[2] = {0, 0};
     int banded_warps = 8;        // reads per CTA of the banded kernel
     int short_max_len = 32 * kMaxRPL;   // longer reads take the striped long-read kernel (ADVHMM_SHORT_MAX_LEN)
-    bool int_compare = false;    // integer-pipe compares (ADVHMM_ICMP=1); needs all tables <= 0
-    bool launch_int_compare = false;   // ... and every model of the current batch qualifies
     std::mutex mu;
 };
 

@@ -55,52 +55,32 @@ __device__ __forceinline__ void static_for(F&& f)
     }
 }
 
-template <int SH, bool ICMP>
+template <int SH>
 __device__ __forceinline__ double max3_first(double a0, double a1, double a2, uint32_t& bits)
 {
     double m;
-    if (ICMP) {
-        // All DP values are <= 0 (sums of log-probabilities; checked when the model is compiled),
-        // so a > b  <=>  bits(a) < bits(b) as unsigned 64-bit integers (+0.0 is the largest value
-        // and the smallest pattern, -inf the smallest value and the largest non-NaN pattern).
-        // The compares then run on the integer pipe and leave the fp64 pipe to the adds.
-        asm("{\n\t"
-            ".reg .pred p1, p2;\n\t"
-            ".reg .b64 t, x0, x1, x2;\n\t"
-            "mov.b64 x0, %2;\n\t"
-            "mov.b64 x1, %3;\n\t"
-            "mov.b64 x2, %4;\n\t"
-            "setp.lt.u64 p1, x1, x0;\n\t"
-            "selp.b64 t, x1, x0, p1;\n\t"
-            "@p1 or.b32 %1, %1, %5;\n\t"
-            "setp.lt.u64 p2, x2, t;\n\t"
-            "selp.b64 t, x2, t, p2;\n\t"
-            "@p2 or.b32 %1, %1, %6;\n\t"
-            "mov.b64 %0, t;\n\t"
-            "}"
-            : "=d"(m), "+r"(bits)
-            : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
-    } else {
-        // written in PTX so that each compare costs one DSETP, one 64-bit select and one predicated OR
-        asm("{\n\t"
-            ".reg .pred p1, p2;\n\t"
-            ".reg .f64 t;\n\t"
-            "setp.gt.f64 p1, %3, %2;\n\t"
-            "selp.f64 t, %3, %2, p1;\n\t"
-            "@p1 or.b32 %1, %1, %5;\n\t"
-            "setp.gt.f64 p2, %4, t;\n\t"
-            "selp.f64 %0, %4, t, p2;\n\t"
-            "@p2 or.b32 %1, %1, %6;\n\t"
-            "}"
-            : "=d"(m), "+r"(bits)
-            : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
-    }
+    // written in PTX so that each compare costs one DSETP, one 64-bit select and one predicated add.
+    // (A variant that compares the bit patterns on the integer pipe -- every DP value is <= 0, so the
+    // order of the patterns is the reverse order of the values -- measured 20 % slower: it overloads
+    // the ALU pipe that already carries the selects; profiles/r1_variants.md.)
+    asm("{\n\t"
+        ".reg .pred p1, p2;\n\t"
+        ".reg .f64 t;\n\t"
+        "setp.gt.f64 p1, %3, %2;\n\t"
+        "selp.f64 t, %3, %2, p1;\n\t"
+        "@p1 or.b32 %1, %1, %5;\n\t"
+        "setp.gt.f64 p2, %4, t;\n\t"
+        "selp.f64 %0, %4, t, p2;\n\t"
+        "@p2 or.b32 %1, %1, %6;\n\t"
+        "}"
+        : "=d"(m), "+r"(bits)
+        : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
     return m;
 }
 
 // ALIGNED: the read length is a multiple of RPL, so the last read position is the last row of a
 // lane and its values can be stored from fixed registers.
-template <int RPL, bool ALIGNED, bool ICMP>
+template <int RPL, bool ALIGNED>
 __device__ __forceinline__ void banded_sweep(const int NC, const int P, const int nl, const int ln, const int jn,
                                              const int lane, const uint32_t s_base, const uint32_t symbits,
                                              const int acc_col, uint32_t* __restrict__ tbw,
@@ -159,8 +139,8 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
             const double2 e = lds128(e_t[j] + cb);             // {eI, eM}
             eIr[j] = e.x;
             const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-            nM[j] = max3_first<6 * (j % 5) + 2, ICMP>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
-            nD[j] = max3_first<6 * (j % 5) + 4, ICMP>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
+            nM[j] = max3_first<6 * (j % 5) + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
+            nD[j] = max3_first<6 * (j % 5) + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
         });
         if (lane == 0) {                                       // first read position: from row 0
             const double2 f = lds128(e_t[0] + v1_delta + cb);
@@ -184,7 +164,7 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
         double uI = uI0, uM = uM0, uD = uD0;
         static_for<0, RPL>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
-            double vI = max3_first<6 * (j % 5), ICMP>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
+            double vI = max3_first<6 * (j % 5)>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
             if (j == 0 && lane == 0) vI = eIr[0];
             uI = vI; uM = nM[j]; uD = nD[j];
             cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
@@ -226,7 +206,7 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
     }
 }
 
-template <int RPL, int WPB, bool ICMP>
+template <int RPL, int WPB>
 __global__ void __launch_bounds__(WPB * 32, WPB > 8 ? 1 : 2)
 banded_fill_kernel(const BandedArgs a)
 {
@@ -280,9 +260,9 @@ banded_fill_kernel(const BandedArgs a)
     double* __restrict__ vfin = a.vfin + slot * a.vfin_stride;
     const uint32_t s_base = smem_u32(smem_raw);
     if (jn == RPL - 1)
-        banded_sweep<RPL, true, ICMP>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
+        banded_sweep<RPL, true>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
     else
-        banded_sweep<RPL, false, ICMP>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
+        banded_sweep<RPL, false>(NC, P, nl, ln, jn, lane, s_base, symbits, M->acc_col, tbw, acc_tb, vfin);
     __syncwarp();
 
     // ---- final-only silent states on the last row (hub reductions across the warp) ---------
@@ -806,8 +786,8 @@ banded_long_kernel(const LongArgs a)
                 const double2 e = ldg128(img_e + eoff[j] + cb);
                 eIr[j] = e.x;
                 const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-                nM[j] = max3_first<6 * (j % 5) + 2, false>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
-                nD[j] = max3_first<6 * (j % 5) + 4, false>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
+                nM[j] = max3_first<6 * (j % 5) + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
+                nD[j] = max3_first<6 * (j % 5) + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
             });
             const bool first_row = (lane == 0 && s == 0);
             if (first_row) {
@@ -829,7 +809,7 @@ banded_long_kernel(const LongArgs a)
             double uI = uI0, uM = uM0, uD = uD0;
             static_for<0, RPL>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                double vI = max3_first<6 * (j % 5), false>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
+                double vI = max3_first<6 * (j % 5)>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
                 if (j == 0 && first_row) vI = eIr[0];
                 uI = vI; uM = nM[j]; uD = nD[j];
                 cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];

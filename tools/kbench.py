@@ -1,5 +1,5 @@
 """Kernel-variant timing on the config-2 workload (device-resident buffers, CUDA events around
-every fill launch).  Variant selection: ADVHMM_WPB={8,10,12}, ADVHMM_ICMP={0,1}."""
+every fill launch).  ADVHMM_LIB selects a library built with other -D variant flags."""
 import ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -35,6 +35,6 @@ for _ in range(steps): step(F)
 e1.record(stream); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 fm, fn, bm, bn = ctx.profile_read()
-print("lib=%s prec=%s WPB=%s ICMP=%s loci=%d reads=%d: step %.2f ms (%.2f Mreads/s, %.0f GCUPS) fill %.2f ms/step (%d launches) backtrack %.2f ms/step | logp checksum %r" % (
-    os.path.basename(engine.LIB_PATH), os.environ.get("ADVHMM_PRECISION", "fp64"), os.environ.get("ADVHMM_WPB", "8"), os.environ.get("ADVHMM_ICMP", "0"), n_loci, R, ms, R / ms / 1e3, wl["cells"] / ms / 1e6,
+print("lib=%s prec=%s loci=%d reads=%d: step %.2f ms (%.2f Mreads/s, %.0f GCUPS) fill %.2f ms/step (%d launches) backtrack %.2f ms/step | logp checksum %r" % (
+    os.path.basename(engine.LIB_PATH), os.environ.get("ADVHMM_PRECISION", "fp64"), n_loci, R, ms, R / ms / 1e3, wl["cells"] / ms / 1e6,
     fm / steps, fn // steps, bm / steps, float(d_logp.sum().item())))
