@@ -296,3 +296,46 @@ def state_classes(names, emis=None):
             base = int(np.argmax(emis[i]))
         out[i] = kind | (part << 3) | (base << 5)
     return out
+
+
+def rescore_paths(baked, codes, paths):
+    """Fold ``(v + t) + e`` along state paths with the model's own baked tables, in the reference's
+    operation order (``hmm.pyx:2035-2042, 2056-2083``).  For a path Viterbi returned this reproduces its
+    log-probability bit for bit: a check of paths that needs no second decoder and works at any batch
+    size.  Raises ``AssertionError`` if a path does not run from the start to the end state, uses a
+    transition that is not in the model, or does not emit exactly its read.
+    ``codes`` / ``paths``: per read, uint8 symbol codes / int state indices.  -> float64 scores."""
+    import numpy as np
+    m, S = baked["n_states"], baked["silent_start"]
+    W = np.full((m, m), -np.inf)
+    dst = np.repeat(np.arange(m), np.diff(baked["in_off"]))
+    W[baked["in_src"], dst] = baked["in_logp"]
+    emis = baked["emis"]
+    count = len(paths)
+    plen = np.fromiter((len(p) for p in paths), dtype=np.int64, count=count)
+    lens = np.fromiter((len(c) for c in codes), dtype=np.int64, count=count)
+    P = np.full((count, int(plen.max())), -1, dtype=np.int64)
+    for i, p in enumerate(paths):
+        P[i, :plen[i]] = p
+    sym = np.zeros((count, int(lens.max()) + 1), dtype=np.int64)
+    for i, c in enumerate(codes):
+        sym[i, :lens[i]] = c
+    rows = np.arange(count)
+    assert (P[:, 0] == baked["start_index"]).all(), "a path does not begin in the start state"
+    assert (P[rows, plen - 1] == baked["end_index"]).all(), "a path does not finish in the end state"
+    v = np.zeros(count)
+    pos = np.zeros(count, dtype=np.int64)
+    for k in range(1, P.shape[1]):
+        live = k < plen
+        a = np.where(live, P[:, k - 1], 0)
+        b = np.where(live, P[:, k], 0)
+        t = W[a, b]
+        assert np.isfinite(t[live]).all(), "a path uses a transition the model does not have"
+        nv = v + np.where(live, t, 0.0)
+        emitting = live & (b < S)
+        e = emis[np.where(emitting, b, 0), sym[rows, np.minimum(pos, lens)]]
+        nv = np.where(emitting, nv + e, nv)
+        v = np.where(live, nv, v)
+        pos = pos + emitting
+    assert (pos == lens).all(), "a path does not emit exactly its read"
+    return v

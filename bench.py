@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-loci", type=int, default=0, help="loci in the CPU sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify-loci", type=int, default=48,
+                    help="re-score the state paths of the first N loci on the host (0: skip)")
     return ap.parse_args()
 
 
@@ -310,6 +312,28 @@ def run_ours(args):
     if n_paths > path_cap or int((d_plen < 0).sum().item()) != 0:
         raise SystemExit("path buffer too small or impossible reads in the synthetic workload")
 
+    # ---- self-check (outside every timed region): the state paths of the first loci, re-scored with
+    #      the models' own tables, must give the returned log-probabilities bit for bit -------------
+    verified = None
+    if rank == 0 and args.verify_loci > 0:
+        from advntr_b200 import path_utils
+        nv = min(args.verify_loci, len(models))
+        r_hi = int(goff[nv])
+        h_lp = d_logp[:r_hi].cpu().numpy()
+        h_pl = d_plen[:r_hi].cpu().numpy()
+        h_po = d_poff[:r_hi].cpu().numpy()
+        h_pa = d_path[:n_paths].cpu().numpy()
+        ok = True
+        for g in range(nv):
+            a, b = int(goff[g]), int(goff[g + 1])
+            codes = [wl["seqs"][off[r]:off[r + 1]] for r in range(a, b)]
+            paths = [h_pa[h_po[r]:h_po[r] + h_pl[r]] for r in range(a, b)]
+            sc = path_utils.rescore_paths(wl["baked"][g], codes, paths)
+            ok = ok and bool(np.array_equal(sc.view(np.int64), h_lp[a:b].view(np.int64)))
+        verified = {"loci": nv, "reads": r_hi, "paths_rescored_bit_exact": ok}
+        if not ok:
+            raise SystemExit("self-check failed: re-scored paths do not reproduce the log-probabilities")
+
     # ---- value: inputs resident in HBM, CUDA events on the launching stream ---------------------
     ctx.profile(True)
     ctx.profile_read()
@@ -412,6 +436,8 @@ def run_ours(args):
                 "fp32_mode": {"value": R * world / (extra["fp32_ms"] * 1e-3), "unit": "reads/s",
                               "note": "optional ADVHMM_FP32 mode, device-resident, full paths; tolerance "
                                       "and RU-count concordance in tests/test_gpu_parity.py::test_fp32_mode"}}
+        if verified:
+            line["verified"] = verified
         line["roofline"] = roofline(ctx, wl, fill_ms, fill_n, bt_ms, bt_n, ms, K)
         if world == 1 and not args.no_cpu_baseline:
             procs = host_cores()

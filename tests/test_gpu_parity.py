@@ -376,3 +376,32 @@ def test_250bp_reads_large_image_takes_the_16_warp_kernel(ctx):
     assert same_bits(res.logp, want_lp)
     assert_paths_equal([res.path(i) for i in range(len(res))], want_paths)
     dm.close()
+
+
+def test_path_scores_reproduce_logp_at_scale(ctx):
+    """Size-independent property at bench scale (no oracle): 300 config-2 loci, ~46,000 reads in one
+    device call; every returned state path, re-scored with the model's tables, gives the returned
+    log-probability bit for bit, starts in the start state, ends in the end state and emits the read."""
+    from advntr_b200 import engine, path_utils, synth
+    models, groups, bakeds = [], [], []
+    for lid in range(1, 301):
+        loc = synth.config2_locus(lid)
+        b = loc.build_model().baked if lid % 50 == 0 else None
+        if b is None:
+            from advntr_b200 import fast_compile
+            b = fast_compile.build_vntr_matcher_hmm(loc.left, loc.right, loc.segments, loc.copies, flank_size=150).baked
+        flat, lengths = synth.config2_read_codes(loc)
+        cuts = np.concatenate([[0], np.cumsum(lengths)])
+        groups.append([flat[cuts[i]:cuts[i + 1]] for i in range(len(lengths))])
+        models.append(engine.DeviceModel(ctx, b))
+        bakeds.append(b)
+    res = ctx.viterbi_multi(models, groups)
+    assert (res.path_len > 0).all()
+    first = 0
+    for b, g in zip(bakeds, groups):
+        v = path_utils.rescore_paths(b, g, [res.path(first + i) for i in range(len(g))])
+        assert same_bits(v, res.logp[first:first + len(g)])
+        first += len(g)
+    assert first > 40000
+    for dm in models:
+        dm.close()
