@@ -38,3 +38,22 @@ def test_consumers_match_reference_values(golden):
         assert s.n_emitted == len(read)
         if read:
             assert path_utils.get_flanking_regions_matching_rate(vpath, read, left, right) == want[i, 4]
+
+
+def test_rescore_paths_reproduces_reference_logp(golden):
+    """The reference's own paths, re-scored with the baked tables in its operation order, give its own
+    log-probabilities bit for bit (the size-independent check bench.py and the GPU tests rely on)."""
+    import oracle
+    keep = [i for i in range(len(golden.reads)) if golden.path(i) is not None]
+    codes = [oracle.encode(golden.reads[i]) for i in keep]
+    scores = path_utils.rescore_paths(golden.baked, codes, [golden.path(i) for i in keep])
+    assert np.array_equal(scores.view(np.int64), golden.logp[keep].view(np.int64))
+    # and it notices a corrupted path
+    bad = [np.array(golden.path(i)) for i in keep]
+    victim = max(range(len(bad)), key=lambda i: len(bad[i]))
+    bad[victim][len(bad[victim]) // 2] = bad[victim][len(bad[victim]) // 2 - 1]
+    try:
+        noticed = path_utils.rescore_paths(golden.baked, codes, bad)[victim] != golden.logp[keep][victim]
+    except AssertionError:
+        noticed = True
+    assert noticed
