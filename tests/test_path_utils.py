@@ -51,7 +51,8 @@ def test_rescore_paths_reproduces_reference_logp(golden):
     # and it notices a corrupted path
     bad = [np.array(golden.path(i)) for i in keep]
     victim = max(range(len(bad)), key=lambda i: len(bad[i]))
-    bad[victim][len(bad[victim]) // 2] = bad[victim][len(bad[victim]) // 2 - 1]
+    k = next(k for k in range(len(bad[victim]) // 2, len(bad[victim])) if bad[victim][k] != bad[victim][k - 1])
+    bad[victim][k] = bad[victim][k - 1]
     try:
         noticed = path_utils.rescore_paths(golden.baked, codes, bad)[victim] != golden.logp[keep][victim]
     except AssertionError:
