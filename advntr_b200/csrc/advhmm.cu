@@ -469,7 +469,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
             pl.order.push_back(f.items[i]);
         }
     };
-    const int short_warps = (forward || fp32) ? 8 : banded_warps_for(ctx, pl.max_smem_short);
+    const int rpl_short = std::max(1, (fam_short.max_len + 31) / 32);
+    const int short_warps = (forward || fp32 || rpl_short >= 8) ? 8 : banded_warps_for(ctx, pl.max_smem_short);
     make_tiles(fam_short, short_warps, 0);
     make_tiles(fam_long, kLongWarps, 1);
     make_tiles(fam_generic, gwarps, 2);

@@ -207,7 +207,10 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
 }
 
 template <int RPL, int WPB>
-__global__ void __launch_bounds__(WPB * 32, WPB > 8 ? 1 : 2)
+// 8..10 rows per lane (reads of 225..320 bases) need 184..210 registers: one 8-warp CTA per SM without
+// spills beats sixteen warps at 128 registers with spills (+11 % at 250 bp, +33 % at 300 bp); up to 7 rows
+// the 128-register build wins (profiles/r1_variants.md)
+__global__ void __launch_bounds__(WPB * 32, (WPB > 8 || RPL >= 8) ? 1 : 2)
 banded_fill_kernel(const BandedArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
