@@ -405,3 +405,50 @@ def test_path_scores_reproduce_logp_at_scale(ctx):
     assert first > 40000
     for dm in models:
         dm.close()
+
+
+@pytest.mark.parametrize("seed", [101, 202, 303])
+def test_random_loci_random_reads_vs_oracle(ctx, seed):
+    """Differential test over model SHAPES: random flank lengths (incl. very short), repeat-unit lengths
+    1..80, 1..12 unrolled copies, both error rates, divergent repeat segments; reads of length 0..330:
+    windows of the locus, pure repeats, homopolymers, random sequence, either strand.  Every model must
+    decode bit-identically to the C restatement of the reference, whichever kernel it is routed to."""
+    from advntr_b200 import engine, read_matcher, synth
+    rng = random.Random(seed)
+    kinds = set()
+    for _ in range(8):
+        R = rng.choice((1, 2, 3, 5, 8, 13, 21, 34, 55, 80))
+        copies = rng.randint(1, 12 if R < 30 else 4)
+        Ll, Lr = rng.choice((1, 2, 7, 30, 100, 150)), rng.choice((1, 3, 12, 60, 150))
+        eps = rng.choice((0.05, 0.3))
+        ru = synth.rand_dna(rng, R)
+        nseg = rng.randint(1, 6)
+        segs = [synth.substitute(rng, ru, rng.choice((0.0, 0.05, 0.3))) for _ in range(nseg)]
+        left, right = synth.rand_dna(rng, Ll), synth.rand_dna(rng, Lr)
+        if rng.random() < 0.2:
+            left = "A" * Ll                                  # homopolymer flank: ties everywhere
+        model = read_matcher.get_read_matcher_model(left, right, segs, copies, error_rate=eps)
+        locus = left + "".join(segs) * 3 + right
+        reads = ["", rng.choice("ACGT"), ru * rng.randint(1, 40), "A" * rng.randint(1, 200), "ACGT" * rng.randint(1, 70)]
+        for _ in range(35):
+            n = rng.choice((1, 2, 3, 10, 31, 32, 33, 64, 100, 150, 151, 159, 160, 161, 200, 250, 256, 300, 320, 321, 330))
+            if rng.random() < 0.6 and len(locus) > 2:
+                s = rng.randrange(0, len(locus))
+                r = synth.sequencing_errors(rng, (locus * (n // len(locus) + 2))[s:s + n + 8], 0.02, 0.01, 0.01)[:n]
+            else:
+                r = synth.rand_dna(rng, n)
+            reads.append(synth.revcomp(r) if rng.random() < 0.3 else r)
+        reads = [r[:330] for r in reads]
+        codes = [oracle.encode(r) for r in reads]
+        want_lp, want_paths = oracle.OracleModel(model.baked).viterbi(codes)
+        dm = engine.DeviceModel(ctx, model.baked)
+        kinds.add(dm.kind)
+        res = dm.viterbi(codes)
+        assert same_bits(res.logp, want_lp), (seed, R, copies, Ll, Lr, eps)
+        assert_paths_equal([res.path(i) for i in range(len(res))], want_paths, "R=%d C=%d L=%d/%d" % (R, copies, Ll, Lr))
+        gen = dm.viterbi(codes[:12], force_generic=True)
+        assert same_bits(gen.logp, want_lp[:12])
+        fwd = dm.log_probability(codes[:10])
+        assert np.allclose(fwd, oracle.OracleModel(model.baked).log_probability(codes[:10]), rtol=1e-9, atol=0)
+        dm.close()
+    assert "banded" in kinds
