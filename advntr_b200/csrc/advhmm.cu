@@ -472,6 +472,21 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     const int rpl_short = std::max(1, (fam_short.max_len + 31) / 32);
     const int short_warps = (forward || fp32 || rpl_short >= 8) ? 8 : banded_warps_for(ctx, pl.max_smem_short);
     make_tiles(fam_short, short_warps, 0);
+    // long reads differ several-fold in length: within a model, longest first, so that the tail of a
+    // launch is made of the cheap reads (CTAs start in order); results go back by read id anyway
+    if (fam_long.items.size() > 1) {
+        std::vector<int32_t> idx(fam_long.items.size());
+        for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int32_t)i;
+        auto len_of = [&](int32_t i) { const int64_t r = fam_long.items[i] / strands; return seq_off[r + 1] - seq_off[r]; };
+        std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) {
+            if (fam_long.model[x] != fam_long.model[y]) return fam_long.model[x] < fam_long.model[y];
+            return len_of(x) > len_of(y);
+        });
+        std::vector<int32_t> items(idx.size()), model(idx.size());
+        for (size_t i = 0; i < idx.size(); ++i) { items[i] = fam_long.items[idx[i]]; model[i] = fam_long.model[idx[i]]; }
+        fam_long.items.swap(items);
+        fam_long.model.swap(model);
+    }
     make_tiles(fam_long, kLongWarps, 1);
     make_tiles(fam_generic, gwarps, 2);
     const int n_short = (int)fam_short.items.size(), n_long = (int)fam_long.items.size();
@@ -541,7 +556,11 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     // the paths of chunk i travel to the host while chunk i+1 is decoded (run_host)
     if (ctx->mark_chunks && ctx->host_chunks > 1 && n_short >= ctx->host_chunks * 32768)
         s_chunk = std::min<size_t>(s_chunk, ((size_t)n_short + ctx->host_chunks - 1) / ctx->host_chunks);
-    const size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)kLongWarps);
+    size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)kLongWarps);
+    {   // whole waves: two CTAs of kLongWarps reads per SM
+        const size_t wave = (size_t)2 * kLongWarps * std::max(ctx->sm_count, 1);
+        if (l_chunk > wave && l_chunk < (size_t)n_long) l_chunk = l_chunk / wave * wave;
+    }
     const size_t g_chunk = chunk_of(g_per_item, n_generic, (size_t)gwarps);
     // short layout
     const size_t so_tbw = 0, so_vfin = al(s_chunk * 32 * Ps * nw_short * 4);
