@@ -194,8 +194,8 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
 #pragma unroll 1
     for (int t = 0; t < t_steady; ++t) step(t, std::true_type{});
     // unrolled x3 for reads up to 160 bp (+4.5 % measured, 2..6 alike, 8 outgrows the instruction cache);
-    // the wider variants already spill and stay rolled
-#pragma unroll (RPL <= 5 ? kStepUnroll : 1)
+    // 6 and 7 rows per lane spill at 128 registers and stay rolled; 8..10 rows (255 registers) take x2 (+1..2 %)
+#pragma unroll (RPL <= 5 ? kStepUnroll : RPL >= 8 ? 2 : 1)
     for (int t = t_steady; t < t_down; ++t) step(t, std::false_type{});
 #pragma unroll 1
     for (int t = t_down; t < steps; ++t) step(t, std::true_type{});
