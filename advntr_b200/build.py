@@ -1,4 +1,5 @@
-"""Build the CUDA engine (``libadvhmm.so``) in-tree with nvcc for sm_100a.
+"""Build the CUDA engine (``libadvhmm.so``, nvcc, sm_100a) and the host-side BAM reader
+(``libadvbam.so``, g++ + zlib) in-tree.
 
 ``python -m advntr_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles
 without a GPU.  The library is the only thing that can decode: nothing in the package
@@ -20,6 +21,11 @@ LIB = os.path.join(PKG, "libadvhmm.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "1886"]
+
+
+BAM_SRC = os.path.join(PKG, "csrc", "bam_ingest.cpp")
+BAM_DEPS = [BAM_SRC, os.path.join(os.path.dirname(PKG), "include", "advbam.h")]
+BAM_LIB = os.path.join(PKG, "libadvbam.so")
 
 
 def nvcc_path() -> str:
@@ -44,5 +50,17 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_bam_library(force: bool = False) -> str:
+    """The read-ingest library (BGZF / BAM / BAI reader, include/advbam.h): host C++ only."""
+    if not force and os.path.exists(BAM_LIB) and \
+            all(os.path.getmtime(d) <= os.path.getmtime(BAM_LIB) for d in BAM_DEPS if os.path.exists(d)):
+        return BAM_LIB
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", BAM_LIB, BAM_SRC,
+                           "-lz", "-lpthread"])
+    return BAM_LIB
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_bam_library(force="--force" in sys.argv))

@@ -15,21 +15,26 @@ their reads one by one (``vntr_finder.py:727-767``).  Here
    those numbers (numpy, no per-read Python).
 
 Decisions are the ones ``LocusDecoder`` makes read by read from full paths (tests/test_pipeline.py
-checks they are identical); BAM access stays with the caller, who passes the mapped reads per locus.
+checks they are identical).  The caller either passes the mapped reads per locus (``genotype``) or an
+indexed BAM file (``genotype_alignment_file``): then the region fetches, the read-level tests of
+``select_illumina_reads`` and the unmapped-read extraction run in ``libadvbam.so`` (``bam_ingest.py``)
+and the mapped reads reach the engine as code arrays without passing through Python strings.
 """
 from __future__ import annotations
 
 import numpy as np
 
-from . import engine, genotype, keyword_filter
+from . import bam_ingest, engine, genotype, keyword_filter
 from .locus_batch import LocusDecoder, reverse_complement
 
 
 class LocusSpec(object):
     """What ``ReferenceVNTR`` holds for one locus (``reference_vntr.py:7-40``)."""
 
-    def __init__(self, locus_id, left_flank, right_flank, repeat_segments, scaled_score=None):
+    def __init__(self, locus_id, left_flank, right_flank, repeat_segments, scaled_score=None, chromosome=None,
+                 start_point=None):
         self.id = int(locus_id)
+        self.chromosome, self.start_point = chromosome, start_point   # only for genotype_alignment_file
         self.left_flank, self.right_flank = left_flank, right_flank
         self.repeat_segments = list(repeat_segments)
         self.pattern = self.repeat_segments[0]
@@ -46,6 +51,14 @@ class GenotypingRun(object):
         keywords = [(l.id, sorted(keyword_filter.get_keywords_for_filtering(
             l.left_flank, l.right_flank, l.repeat_segments, l.pattern, keyword_size=keyword_size))) for l in self.loci]
         self.filter = keyword_filter.KeywordFilter(keywords, ctx=self.ctx)
+
+    @classmethod
+    def from_alignment_file(cls, loci, alignment_file, keyword_size=15):
+        """Read length = median of the first five records, as ``select_illumina_reads`` sets it
+        (``vntr_finder.py:714-718``)."""
+        with bam_ingest.AlignmentFile(alignment_file) as f:
+            read_length = bam_ingest.median_head_read_length(f)
+        return cls(loci, read_length=read_length, keyword_size=keyword_size)
 
     def close(self):
         self.filter.close()
@@ -76,6 +89,46 @@ class GenotypingRun(object):
             goff.append(len(batch))
             layout.append((len(mapped), len(unm)))
         seqs, off = engine.encode_batch(batch)
+        return self._call(seqs, off, goff, layout, accuracy_filter, is_haploid)
+
+    def genotype_alignment_file(self, alignment_file, accuracy_filter=False, is_haploid=False, threads=0):
+        """``find_repeat_counts_from_alignment_file`` (``genome_analyzer.py:273-297``) for an indexed BAM:
+        unmapped reads -> keyword filter, one region fetch per locus -> the read-level tests of
+        ``select_illumina_reads`` (``vntr_finder.py:727-737``, ``utils.py:20-38``), everything decoded in
+        one device call.  Every locus needs ``chromosome`` and ``start_point``."""
+        L = self.read_length
+        with bam_ingest.AlignmentFile(alignment_file) as f:
+            names, useqs = bam_ingest.extract_unmapped_reads(f, threads=threads)
+            filtered = self.filter_unmapped(names, useqs) if names else {}
+            mapped, strands, goff, layout, n = [], [], [0], [], 0
+            for dec, spec in zip(self.decoders, self.loci):
+                end = spec.start_point + sum(len(seg) for seg in spec.repeat_segments)     # reference_vntr.py:66
+                m = bam_ingest.select_mapped_illumina(f, spec.chromosome, spec.start_point, end, L)
+                unm = [s.upper() for _, s in filtered.get(dec.id, ()) if "N" not in s.upper() and len(s) >= L]
+                for s in unm:
+                    strands += [s, reverse_complement(s)]
+                mapped.append(m)
+                n += len(m["names"]) + 2 * len(unm)
+                goff.append(n)
+                layout.append((len(m["names"]), len(unm)))
+        u_codes, u_off = engine.encode_batch(strands)
+        chunks, lens, cur = [], [], 0
+        for m, (_, n_unm) in zip(mapped, layout):
+            chunks.append(m["codes"])
+            lens.append(np.diff(m["off"]))
+            chunks.append(u_codes[u_off[cur]:u_off[cur + 2 * n_unm]])
+            lens.append(np.diff(u_off[cur:cur + 2 * n_unm + 1]))
+            cur += 2 * n_unm
+        off = np.zeros(n + 1, dtype=np.int64)
+        if n:
+            np.cumsum(np.concatenate(lens), out=off[1:])
+        seqs = np.ascontiguousarray(np.concatenate(chunks + [np.zeros(1, dtype=np.uint8)]))
+        out = self._call(seqs, off, goff, layout, accuracy_filter, is_haploid)
+        for m, spec in zip(mapped, self.loci):
+            out[spec.id]["vntr_bp_in_mapped_reads"] = m["vntr_bp"]
+        return out
+
+    def _call(self, seqs, off, goff, layout, accuracy_filter, is_haploid):
         models = [d.model._device_model() for d in self.decoders]
         res = self.ctx._run(models, np.asarray(goff, dtype=np.int64), seqs, off, False, False, False, None,
                             want_summary=True)
