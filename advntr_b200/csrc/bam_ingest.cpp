@@ -467,6 +467,81 @@ void head_records(advbam_file* f, int32_t n, advbam_reads& out) {
     }
 }
 
+void append_batch(advbam_reads& d, const advbam_reads& s) {
+    auto cat = [](auto& a, const auto& b) { a.insert(a.end(), b.begin(), b.end()); };
+    auto cat_off = [](std::vector<int64_t>& a, const std::vector<int64_t>& b) {
+        int64_t base = a.back();
+        for (size_t i = 1; i < b.size(); ++i) a.push_back(base + b[i]);
+    };
+    cat(d.flag, s.flag);
+    cat(d.mapq, s.mapq);
+    cat(d.has_qual, s.has_qual);
+    cat(d.tid, s.tid);
+    cat(d.pos, s.pos);
+    cat(d.ref_end, s.ref_end);
+    cat(d.seq, s.seq);
+    cat(d.qual, s.qual);
+    cat(d.names, s.names);
+    cat(d.cigar, s.cigar);
+    cat_off(d.seq_off, s.seq_off);
+    cat_off(d.name_off, s.name_off);
+    cat_off(d.cigar_off, s.cigar_off);
+}
+
+// Whole file with an index: the linear index holds virtual offsets of record STARTS all over the
+// file, so the file is cut there into independent ranges; every thread inflates and parses its own
+// ranges (no sequential stage), the batches are joined in file order.  The part behind the last
+// indexed record (the unplaced reads) has no known record starts and is one range.
+bool scan_file_by_index(advbam_file* f, uint32_t require, uint32_t exclude, int n_threads, advbam_reads& out) {
+    std::vector<uint64_t> cuts;
+    for (const RefIndex& ri : f->index)
+        for (uint64_t v : ri.linear)
+            if (v > f->first_record) cuts.push_back(v);
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    if (cuts.size() < 2) return false;
+    // thin the cut points to about 8 ranges per thread, evenly spaced in the compressed file
+    std::vector<uint64_t> bounds{f->first_record};
+    size_t want = (size_t)n_threads * 8;
+    uint64_t span = (uint64_t)f->size / want + 1, next_at = (f->first_record >> 16) + span;
+    for (uint64_t v : cuts)
+        if ((v >> 16) >= next_at) {
+            bounds.push_back(v);
+            next_at = (v >> 16) + span;
+        }
+    bounds.push_back(~(uint64_t)0);                     // to the end of the file
+    size_t n_ranges = bounds.size() - 1;
+    std::vector<advbam_reads> parts(n_ranges);
+    std::vector<std::string> errors(n_ranges);
+    std::atomic<size_t> next_range{0};
+    auto work = [&]() {
+        std::vector<uint8_t> rec;
+        for (;;) {
+            size_t i = next_range.fetch_add(1);
+            if (i >= n_ranges) return;
+            try {
+                Cursor cur(f);
+                cur.seek(bounds[i]);
+                while (cur.tell() < bounds[i + 1] && next_record(cur, rec)) {
+                    RecordHead h = parse_head(rec.data());
+                    if (!record_is_sane(h, rec.size())) throw Failure(ADVBAM_E_FORMAT, "damaged BAM record in " + f->path);
+                    if ((h.flag & require) == require && (h.flag & exclude) == 0) append_record(parts[i], h, rec.data(), rec.size());
+                }
+            } catch (const std::exception& e) {
+                errors[i] = e.what();
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    for (const std::string& e : errors)
+        if (!e.empty()) throw Failure(ADVBAM_E_FORMAT, e);
+    for (const advbam_reads& p : parts) append_batch(out, p);
+    return true;
+}
+
 // whole file: windows of blocks inflated by a pool of threads, records parsed from the joined stream
 void scan_file(advbam_file* f, uint32_t require, uint32_t exclude, int n_threads, advbam_reads& out) {
     if (n_threads <= 0) {
@@ -474,6 +549,7 @@ void scan_file(advbam_file* f, uint32_t require, uint32_t exclude, int n_threads
         n_threads = e ? std::atoi(e) : (int)std::thread::hardware_concurrency();
     }
     n_threads = std::max(1, std::min(n_threads, 64));
+    if (n_threads > 1 && f->has_index && scan_file_by_index(f, require, exclude, n_threads, out)) return;
     const size_t kWindow = 2048;                        // blocks per window: <= 128 MiB inflated
     int64_t coff = (int64_t)(f->first_record >> 16);
     size_t skip = (size_t)(f->first_record & 0xffff);
