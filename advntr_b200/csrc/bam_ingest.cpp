@@ -488,10 +488,45 @@ void append_batch(advbam_reads& d, const advbam_reads& s) {
     cat_off(d.cigar_off, s.cigar_off);
 }
 
+int resolve_threads(int n_threads) {
+    if (n_threads <= 0) {
+        const char* e = std::getenv("ADVBAM_THREADS");
+        n_threads = e ? std::atoi(e) : (int)std::thread::hardware_concurrency();
+    }
+    return std::max(1, std::min(n_threads, 64));
+}
+
+// run body(i) for i in [0, n) on up to n_threads threads; the first exception is rethrown
+template <class Body>
+void parallel_for(size_t n, int n_threads, Body&& body) {
+    std::atomic<size_t> next{0};
+    std::string error;
+    std::atomic<bool> failed{false};
+    auto work = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n || failed.load()) return;
+            try {
+                body(i);
+            } catch (const std::exception& e) {
+                if (!failed.exchange(true)) error = e.what();
+            }
+        }
+    };
+    int nt = (int)std::min<size_t>((size_t)n_threads, n);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (failed.load()) throw Failure(ADVBAM_E_FORMAT, error);
+}
+
+void scan_windowed(advbam_file* f, uint64_t start, uint32_t require, uint32_t exclude, int n_threads, advbam_reads& out);
+
 // Whole file with an index: the linear index holds virtual offsets of record STARTS all over the
 // file, so the file is cut there into independent ranges; every thread inflates and parses its own
-// ranges (no sequential stage), the batches are joined in file order.  The part behind the last
-// indexed record (the unplaced reads) has no known record starts and is one range.
+// ranges (no sequential stage), the batches are joined in file order.  The part behind the last cut
+// (the unplaced reads at the end of the file) has no known record starts: scan_windowed.
 bool scan_file_by_index(advbam_file* f, uint32_t require, uint32_t exclude, int n_threads, advbam_reads& out) {
     std::vector<uint64_t> cuts;
     for (const RefIndex& ri : f->index)
@@ -509,59 +544,39 @@ bool scan_file_by_index(advbam_file* f, uint32_t require, uint32_t exclude, int 
             bounds.push_back(v);
             next_at = (v >> 16) + span;
         }
-    bounds.push_back(~(uint64_t)0);                     // to the end of the file
-    size_t n_ranges = bounds.size() - 1;
+    size_t n_ranges = bounds.size() - 1;                // the last bound starts the tail
     std::vector<advbam_reads> parts(n_ranges);
-    std::vector<std::string> errors(n_ranges);
-    std::atomic<size_t> next_range{0};
-    auto work = [&]() {
+    parallel_for(n_ranges, n_threads, [&](size_t i) {
         std::vector<uint8_t> rec;
-        for (;;) {
-            size_t i = next_range.fetch_add(1);
-            if (i >= n_ranges) return;
-            try {
-                Cursor cur(f);
-                cur.seek(bounds[i]);
-                while (cur.tell() < bounds[i + 1] && next_record(cur, rec)) {
-                    RecordHead h = parse_head(rec.data());
-                    if (!record_is_sane(h, rec.size())) throw Failure(ADVBAM_E_FORMAT, "damaged BAM record in " + f->path);
-                    if ((h.flag & require) == require && (h.flag & exclude) == 0) append_record(parts[i], h, rec.data(), rec.size());
-                }
-            } catch (const std::exception& e) {
-                errors[i] = e.what();
-            }
+        Cursor cur(f);
+        cur.seek(bounds[i]);
+        while (cur.tell() < bounds[i + 1] && next_record(cur, rec)) {
+            RecordHead h = parse_head(rec.data());
+            if (!record_is_sane(h, rec.size())) throw Failure(ADVBAM_E_FORMAT, "damaged BAM record in " + f->path);
+            if ((h.flag & require) == require && (h.flag & exclude) == 0) append_record(parts[i], h, rec.data(), rec.size());
         }
-    };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
-    work();
-    for (auto& t : pool) t.join();
-    for (const std::string& e : errors)
-        if (!e.empty()) throw Failure(ADVBAM_E_FORMAT, e);
+    });
     for (const advbam_reads& p : parts) append_batch(out, p);
+    scan_windowed(f, bounds.back(), require, exclude, n_threads, out);
     return true;
 }
 
-// whole file: windows of blocks inflated by a pool of threads, records parsed from the joined stream
-void scan_file(advbam_file* f, uint32_t require, uint32_t exclude, int n_threads, advbam_reads& out) {
-    if (n_threads <= 0) {
-        const char* e = std::getenv("ADVBAM_THREADS");
-        n_threads = e ? std::atoi(e) : (int)std::thread::hardware_concurrency();
-    }
-    n_threads = std::max(1, std::min(n_threads, 64));
-    if (n_threads > 1 && f->has_index && scan_file_by_index(f, require, exclude, n_threads, out)) return;
+// From virtual offset `start` to the end of the file, without knowing record starts: windows of
+// blocks are inflated in place by all threads into one stream (each block's slice is known from its
+// ISIZE trailer), a walk over the 4-byte record lengths finds the record starts, and the records are
+// parsed in parallel in runs of kRun.
+void scan_windowed(advbam_file* f, uint64_t start, uint32_t require, uint32_t exclude, int n_threads, advbam_reads& out) {
     const size_t kWindow = 2048;                        // blocks per window: <= 128 MiB inflated
-    int64_t coff = (int64_t)(f->first_record >> 16);
-    size_t skip = (size_t)(f->first_record & 0xffff);
+    const size_t kRun = 8192;                           // records per parsing task
+    int64_t coff = (int64_t)(start >> 16);
+    size_t skip = (size_t)(start & 0xffff);
     std::vector<uint8_t> stream;                        // unparsed tail of the last window + this window
     std::vector<int64_t> boff, bsz;
-    std::vector<size_t> dst;
+    std::vector<size_t> dst, rec_at;
     while (coff < (int64_t)f->size) {
         boff.clear();
         bsz.clear();
         dst.clear();
-        // block boundaries and inflated sizes (ISIZE trailer) of the window: every block gets its own
-        // slice of the stream, so the threads inflate in place
         size_t total = stream.size();
         while (boff.size() < kWindow && coff < (int64_t)f->size) {
             int64_t bs = bgzf_block_size(f->data + coff, f->size - (size_t)coff);
@@ -574,40 +589,45 @@ void scan_file(advbam_file* f, uint32_t require, uint32_t exclude, int n_threads
             total += isize;
             coff += bs;
         }
-        size_t nb = boff.size();
         dst.push_back(total);
         stream.resize(total);
-        std::atomic<size_t> nextb{0};
-        std::atomic<int64_t> failed{-1};
-        auto work = [&]() {
-            for (;;) {
-                size_t i = nextb.fetch_add(1);
-                if (i >= nb) return;
-                size_t cap = dst[i + 1] - dst[i];
-                if (bgzf_inflate(f->data + boff[i], bsz[i], stream.data() + dst[i], cap) != (int)cap) failed.store(boff[i]);
-            }
-        };
-        int nt = (int)std::min<size_t>((size_t)n_threads, nb);
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-        work();
-        for (auto& t : pool) t.join();
-        if (failed.load() >= 0) throw Failure(ADVBAM_E_FORMAT, "damaged BGZF block at byte " + std::to_string(failed.load()) + " of " + f->path);
-        size_t q = std::min(skip, stream.size());       // the header's share of the first block(s)
+        parallel_for(boff.size(), n_threads, [&](size_t i) {
+            size_t cap = dst[i + 1] - dst[i];
+            if (bgzf_inflate(f->data + boff[i], bsz[i], stream.data() + dst[i], cap) != (int)cap)
+                throw Failure(ADVBAM_E_FORMAT, "damaged BGZF block at byte " + std::to_string(boff[i]) + " of " + f->path);
+        });
+        size_t q = std::min(skip, stream.size());       // bytes before `start` in its block
         skip -= q;
+        rec_at.clear();
         while (stream.size() - q >= 4) {
             uint32_t bs = le32(stream.data() + q);
             if (bs < 32 || bs > (1u << 30)) throw Failure(ADVBAM_E_FORMAT, "implausible BAM record length in " + f->path);
             if (stream.size() - q - 4 < bs) break;
-            const uint8_t* b = stream.data() + q + 4;
-            RecordHead h = parse_head(b);
-            if (!record_is_sane(h, bs)) throw Failure(ADVBAM_E_FORMAT, "damaged BAM record in " + f->path);
-            if ((h.flag & require) == require && (h.flag & exclude) == 0) append_record(out, h, b, bs);
+            rec_at.push_back(q);
             q += 4 + (size_t)bs;
         }
+        size_t n_runs = (rec_at.size() + kRun - 1) / kRun;
+        std::vector<advbam_reads> parts(n_runs);
+        parallel_for(n_runs, n_threads, [&](size_t run) {
+            size_t hi = std::min(rec_at.size(), (run + 1) * kRun);
+            for (size_t k = run * kRun; k < hi; ++k) {
+                const uint8_t* b = stream.data() + rec_at[k] + 4;
+                size_t bs = le32(b - 4);
+                RecordHead h = parse_head(b);
+                if (!record_is_sane(h, bs)) throw Failure(ADVBAM_E_FORMAT, "damaged BAM record in " + f->path);
+                if ((h.flag & require) == require && (h.flag & exclude) == 0) append_record(parts[run], h, b, bs);
+            }
+        });
+        for (const advbam_reads& p : parts) append_batch(out, p);
         stream.erase(stream.begin(), stream.begin() + (std::ptrdiff_t)q);
     }
     if (!stream.empty()) throw Failure(ADVBAM_E_FORMAT, "truncated BAM record at the end of " + f->path);
+}
+
+void scan_file(advbam_file* f, uint32_t require, uint32_t exclude, int n_threads, advbam_reads& out) {
+    n_threads = resolve_threads(n_threads);
+    if (n_threads > 1 && f->has_index && scan_file_by_index(f, require, exclude, n_threads, out)) return;
+    scan_windowed(f, f->first_record, require, exclude, n_threads, out);
 }
 
 template <class F>
