@@ -10,7 +10,9 @@ the DNN pre-filter stay outside (out of scope).
 """
 from __future__ import annotations
 
-from . import engine, fast_compile, genotype, path_utils, read_matcher
+import os
+
+from . import engine, fast_compile, genotype, path_utils, pomegranate, read_matcher
 
 
 class SelectedRead(object):
@@ -30,7 +32,8 @@ def reverse_complement(seq):
 
 class LocusDecoder(object):
     def __init__(self, left_flank, right_flank, repeat_segments, read_length=150, scaled_score=None,
-                 error_rate=read_matcher.DEFAULT_MAX_ERROR_RATE, flank_size=150, locus_id=None):
+                 error_rate=read_matcher.DEFAULT_MAX_ERROR_RATE, flank_size=150, locus_id=None,
+                 trained_hmms_dir=None):
         self.id = locus_id
         self.left_flank, self.right_flank = left_flank, right_flank
         self.segments = list(repeat_segments)
@@ -40,6 +43,20 @@ class LocusDecoder(object):
         self.min_repeat_bp_to_add_read = 2            # vntr_finder.py:66-69
         self.error_rate = error_rate
         copies = read_matcher.copies_for_read_length(read_length, len(self.pattern))
+        # get_vntr_matcher_hmm (vntr_finder.py:116-137) with settings.USE_TRAINED_HMMS: a model stored
+        # by an earlier run is reloaded (from_json bakes it with merge='All', so it is NOT the same
+        # state set as a fresh build -- as in the reference), otherwise built and stored
+        stored = None if trained_hmms_dir is None else \
+            os.path.join(trained_hmms_dir, "%s_%s.json" % (locus_id, read_length))
+        if stored is not None and os.path.isfile(stored):
+            self.model = pomegranate.HiddenMarkovModel.from_json(stored)
+            return
+        if stored is not None:                       # the graph-level builder: only it can serialise
+            self.model = read_matcher.build_vntr_matcher_hmm(left_flank, right_flank, self.segments, copies,
+                                                             flank_size=flank_size, error_rate=error_rate)
+            with open(stored, "w") as outfile:
+                outfile.write(self.model.to_json())
+            return
         self.model = fast_compile.build_vntr_matcher_hmm(left_flank, right_flank, self.segments, copies,
                                                          flank_size=flank_size, error_rate=error_rate)
 

@@ -252,6 +252,7 @@ class HiddenMarkovModel(object):
         self.finite = 0
         self.keymap = []
         self._state_names = set()
+        self._pseudo = {}      # (a, b) -> edge pseudocount (hmm.pyx:432-434); only to_json reads it
         self._baked = None     # dict of numpy arrays (see bake)
         self._engine = None    # lazily created device model handle
 
@@ -271,6 +272,7 @@ class HiddenMarkovModel(object):
                 self.add_state(s)
 
     def add_transition(self, a, b, probability, pseudocount=None, group=None):
+        self._pseudo[(a, b)] = pseudocount or probability
         self.graph.add_edge(a, b, _log(probability))
 
     def add_transitions(self, a, b, probabilities, pseudocounts=None, groups=None):
@@ -286,12 +288,14 @@ class HiddenMarkovModel(object):
 
     def add_model(self, other):
         self.graph = _OrderedDiGraph.disjoint_union(self.graph, other.graph)
+        self._pseudo.update(other._pseudo)
 
     def concatenate(self, other, suffix="", prefix=""):
         other.name = "{}{}{}".format(prefix, other.name, suffix)
         for s in other.states:
             s.name = "{}{}{}".format(prefix, s.name, suffix)
         self.graph = _OrderedDiGraph.disjoint_union(self.graph, other.graph)
+        self._pseudo.update(other._pseudo)
         self.add_transition(self.end, other.start, 1.00)
         self.end = other.end
 
@@ -354,6 +358,7 @@ class HiddenMarkovModel(object):
                             merged += 1
                             g.remove_edge(x, y)
                             g.add_edge(x, b, d)
+                            self._pseudo[(x, b)] = max(self._pseudo.get((a, b), 0.0), self._pseudo.get((x, y), 0.0))
                     g.remove_node(a)
             if merged == 0:
                 break
@@ -581,15 +586,48 @@ class HiddenMarkovModel(object):
     def to_json(self, separators=(",", " : "), indent=4):
         """Same document layout as ``hmm.pyx:3023-3095`` (edges as probabilities)."""
         idx = {s: i for i, s in enumerate(self.states)}
-        edges = [(idx[a], idx[b], math.e ** w, math.e ** w, None)
+        edges = [(idx[a], idx[b], math.e ** w, self._pseudo.get((a, b), math.e ** w), None)
                  for a, b, w in self.graph.edges()]
+        groups = {}                                   # states sharing one distribution OBJECT are tied
+        for i, st in enumerate(self.states[:self.silent_start]):
+            groups.setdefault(id(st.distribution), []).append(i)
+        ties = [(i, j) for i, st in enumerate(self.states[:self.silent_start])
+                for j in groups[id(st.distribution)] if j != i]          # hmm.pyx:895-925, :284-291
         return json.dumps({
             "class": "HiddenMarkovModel", "name": self.name,
             "start": json.loads(self.start.to_json()), "end": json.loads(self.end.to_json()),
             "states": [json.loads(s.to_json()) for s in self.states],
             "end_index": self.end_index, "start_index": self.start_index,
-            "silent_index": self.silent_start, "edges": edges, "distribution ties": [],
+            "silent_index": self.silent_start, "edges": edges, "distribution ties": ties,
         }, separators=separators, indent=indent)
+
+    @classmethod
+    def from_json(cls, s, verbose=False):
+        """``hmm.pyx:3098-3144`` (how ``get_vntr_matcher_hmm`` loads a stored model,
+        ``vntr_finder.py:125-129``): a JSON string or the name of a JSON file.  As in the reference the
+        new model keeps its own fresh ``<name>-start`` / ``<name>-end`` states next to the stored ones
+        and is baked with the DEFAULT ``merge='All'``, which removes those two orphans again and
+        merges silent states with a probability-1 out-edge -- so a stored read matcher comes back
+        with fewer silent states than it was built with, in the reference and here alike."""
+        try:
+            d = json.loads(s)
+        except Exception:
+            try:
+                with open(s, "r") as infile:
+                    d = json.load(infile)
+            except Exception:
+                raise IOError("String must be properly formatted JSON or filename of properly formatted JSON.")
+        model = cls(str(d["name"]))
+        states = [State.from_json(json.dumps(j)) for j in d["states"]]
+        for i, j in d["distribution ties"]:
+            states[i].tie(states[j])
+        model.add_states(states)
+        model.start = states[d["start_index"]]
+        model.end = states[d["end_index"]]
+        for start, end, probability, pseudocount, group in d["edges"]:
+            model.add_transition(states[start], states[end], probability, pseudocount, group)
+        model.bake(verbose=verbose)
+        return model
 
     def __del__(self):
         try:

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 from advntr_b200 import genotype, locus_batch, path_utils, read_matcher
+from advntr_b200 import pomegranate as pom
 from conftest import GOLDEN, same_bits
 from test_builder_parity import _exp_log_reproduce
 
@@ -274,3 +275,72 @@ def test_find_repeat_segments_on_device():
     logp, path = model.viterbi(inp["region"])
     assert same_bits([logp], z["logp"]) and [k for k, _ in path] == list(z["paths"])
     assert read_matcher.find_repeat_segments(inp["pattern"], inp["copies"], inp["region"]) == inp["segments"]
+
+
+def _stored_model():
+    z = np.load(os.path.join(GOLDEN, "stored_model.npz"))
+    import gzip
+    return z, gzip.decompress(z["json_gz"].tobytes()).decode(), json.loads(str(z["inputs"]))
+
+
+def test_stored_model_json_round_trip_equals_the_reference():
+    """vntr_finder.py:116-137: ``to_json`` of a freshly built read matcher is the reference's text byte
+    for byte, and ``from_json`` of it (baked with the default merge='All', hmm.pyx:3143) gives the
+    reference's reloaded tables -- fewer silent states than the stored model -- and the same text again."""
+    import hashlib
+    z, text, inp = _stored_model()
+    built = read_matcher.get_read_matcher_model(inp["left"], inp["right"], inp["segments"], inp["copies"])
+    assert len(built.states) == int(z["n_states_stored"])
+    assert built.to_json() == text
+    again = pom.HiddenMarkovModel.from_json(text)
+    b = again.baked
+    assert [s.name for s in again.states] == str(z["names"]).split("\n")
+    assert list(z["scalars"]) == [b["n_states"], b["silent_start"], b["start_index"], b["end_index"], b["finite"]]
+    assert b["n_states"] < len(built.states)
+    assert np.array_equal(b["in_off"], z["in_off"]) and np.array_equal(b["in_src"], z["in_src"])
+    assert same_bits(b["in_logp"], z["in_logp"]) and same_bits(b["emis"], z["emis"])
+    assert hashlib.sha256(again.to_json().encode()).hexdigest() == str(z["json_again_sha"])
+    lp, vps = _oracle_decoder(again)(inp["reads"])
+    assert same_bits(lp, z["logp"])
+    off = z["path_off"]
+    for i, vp in enumerate(vps):
+        assert [k for k, _ in vp] == list(z["paths"][off[i]:off[i + 1]])
+
+
+def test_stored_model_from_a_file_and_bad_input(tmp_path):
+    z, text, inp = _stored_model()
+    path = tmp_path / "7_150.json"
+    path.write_text(text)
+    again = pom.HiddenMarkovModel("unused").from_json(str(path))     # vntr_finder.py:127-128 calls it on an instance
+    assert len(again.states) == int(z["scalars"][0])
+    with pytest.raises(IOError):
+        pom.HiddenMarkovModel.from_json("neither json nor a file")
+
+
+@pytest.mark.gpu
+def test_stored_model_decodes_on_device():
+    z, text, inp = _stored_model()
+    again = pom.HiddenMarkovModel.from_json(text)
+    res = again.viterbi_batch(inp["reads"])
+    assert same_bits(res.logp, z["logp"])
+    off = z["path_off"]
+    for i in range(len(inp["reads"])):
+        assert np.array_equal(res.path(i), z["paths"][off[i]:off[i + 1]])
+    assert again.viterbi(inp["reads"][0])[0] == z["logp"][0]
+
+
+def test_locus_decoder_stores_and_reloads_its_model(tmp_path):
+    """get_vntr_matcher_hmm with USE_TRAINED_HMMS (vntr_finder.py:116-137): the first run stores
+    '<id>_<read_length>.json', later runs load it."""
+    z, text, inp = _stored_model()
+    args = (inp["left"], inp["right"], inp["segments"])
+    first = locus_batch.LocusDecoder(*args, read_length=40, flank_size=60, locus_id=7, trained_hmms_dir=str(tmp_path))
+    stored = tmp_path / "7_40.json"
+    assert stored.is_file()
+    fresh = read_matcher.build_vntr_matcher_hmm(*args, read_matcher.copies_for_read_length(40, 14), flank_size=60)
+    assert stored.read_text() == fresh.to_json()
+    assert [s.name for s in first.model.states] == [s.name for s in fresh.states]
+    second = locus_batch.LocusDecoder(*args, read_length=40, flank_size=60, locus_id=7, trained_hmms_dir=str(tmp_path))
+    reloaded = pom.HiddenMarkovModel.from_json(stored.read_text())
+    assert [s.name for s in second.model.states] == [s.name for s in reloaded.states]
+    assert len(second.model.states) < len(first.model.states)
