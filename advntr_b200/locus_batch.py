@@ -178,3 +178,28 @@ def dominant_copy_numbers_from_spanning_reads(left_flank, right_flank, repeat_se
         observed.append(path_utils.get_number_of_repeats_in_vpath([(int(k), states[k]) for k in p]))
     copy_numbers, max_prob = genotype.dominant_copy_numbers(observed, accuracy_filter, is_haploid)
     return copy_numbers, max_prob, observed
+
+
+def repeat_count_from_pacbio_alignment_file(alignment_file, chromosome, start_point, left_flank, right_flank,
+                                            repeat_segments, unaligned_spanning_reads=(), error_rate=0.3,
+                                            accuracy_filter=False, is_haploid=False):
+    """``find_repeat_count_from_pacbio_alignment_file`` (``vntr_finder.py:640-651``) for an indexed BAM:
+    the mapped reads that span the locus are cut to the modelled region by the CIGAR walk of
+    ``check_if_pacbio_mapped_read_spans_vntr`` (``bam_ingest.spanning_pacbio_segments``, native), joined
+    with spanning reads found among the unaligned ones (their flank alignment, pairwise2, is not part of
+    this repo: pass the cut sequences), and genotyped.  -> the fields of the reference's ``GenotypeResult``."""
+    from . import bam_ingest
+    vntr_end = start_point + sum(len(seg) for seg in repeat_segments)            # reference_vntr.py:66
+    own = not isinstance(alignment_file, bam_ingest.AlignmentFile)
+    f = bam_ingest.AlignmentFile(alignment_file) if own else alignment_file
+    try:
+        mapped = [seq for _, seq, _ in bam_ingest.spanning_pacbio_segments(f, chromosome, start_point, vntr_end)]
+    finally:
+        if own:
+            f.close()
+    spanning = mapped + list(unaligned_spanning_reads)                           # :646
+    copy_numbers, max_prob, observed = dominant_copy_numbers_from_spanning_reads(
+        left_flank, right_flank, repeat_segments, spanning, error_rate, accuracy_filter, is_haploid)
+    return {"copy_numbers": copy_numbers, "recruited_reads_count": len(spanning),
+            "spanning_reads_count": len(spanning), "flanking_reads_count": 0, "maximum_likelihood": max_prob,
+            "observed_repeats": observed}

@@ -413,3 +413,44 @@ def test_genotypes_from_an_alignment_file_equal_genotypes_from_read_lists(tmp_pa
                       sorted(got[lid]["copy_numbers"]) == truth[lid])
     assert right_calls >= len(truth) - 3
     run.close()
+
+
+@pytest.mark.gpu
+def test_pacbio_genotype_from_an_alignment_file(tmp_path):
+    """Long reads aligned with indels: BAM -> CIGAR walk (native) -> long-read kernel -> genotype, equal to
+    the oracle's cut of the same records fed as read lists, and the simulated alleles come out."""
+    from advntr_b200 import locus_batch, synth
+    rng = random.Random(12)
+    R, nref = 30, 8
+    ru = synth.rand_dna(rng, R)
+    left, right = synth.rand_dna(rng, 600), synth.rand_dna(rng, 600)
+    base = 20000
+    vntr_start = base + len(left)
+    alleles = (6, 11)
+    reads = []
+    for k in range(24):
+        copies = alleles[k % 2]
+        # the read covers the whole allele; its alignment to the reference (nref copies) puts the copy
+        # number difference into one insertion or deletion inside the repeat
+        seq = left + ru * copies + right
+        noisy = synth.sequencing_errors(rng, seq, 0.01, 0.0, 0.0)
+        if len(noisy) != len(seq):
+            continue
+        half = len(left) + R * min(copies, nref) // 2
+        if copies >= nref:
+            ops = [(0, half), (1, R * (copies - nref)), (0, len(seq) - half - R * (copies - nref))]
+        else:
+            ops = [(0, half), (2, R * (nref - copies)), (0, len(seq) - half)]
+        ops = [(op, n) for op, n in ops if n]
+        reads.append(bam_writer.Read("pb%d" % k, rng.choice([0, 16]), 0, base, 60, ops, noisy, None))
+    path = str(tmp_path / "pb.bam")
+    bam_writer.write_bam(path, [("chr1", 100000)], reads)
+    got = locus_batch.repeat_count_from_pacbio_alignment_file(path, "chr1", vntr_start, left, right, [ru] * nref,
+                                                              error_rate=0.05)
+    _, _, records = bam_oracle.read_bam(path)
+    cut = [s for _, s, _ in bam_oracle.pacbio_spanning_segments(records, 0, vntr_start, vntr_start + R * nref)]
+    assert len(cut) == len(reads) and all(len(s) > 200 for s in cut)
+    want = locus_batch.dominant_copy_numbers_from_spanning_reads(left, right, [ru] * nref, cut, error_rate=0.05)
+    assert (got["copy_numbers"], got["maximum_likelihood"], got["observed_repeats"]) == want
+    assert got["spanning_reads_count"] == len(reads)
+    assert sorted(got["copy_numbers"]) == sorted(alleles)
