@@ -63,15 +63,22 @@ __device__ __forceinline__ double max3_first(double a0, double a1, double a2, ui
     // (A variant that compares the bit patterns on the integer pipe -- every DP value is <= 0, so the
     // order of the patterns is the reverse order of the values -- measured 20 % slower: it overloads
     // the ALU pipe that already carries the selects; profiles/r1_variants.md.)
+    //
+    // Evaluation order: in every use a0 is the candidate coming from an I slot, which is the value
+    // that arrives last (the I slots chain down the rows of a column and across lanes), so a1 and a2
+    // are compared first and the late value meets their winner in ONE compare + select.  The winner
+    // is still the first maximal candidate in in-edge order: a2 replaces a1 only if strictly
+    // greater, and their winner replaces a0 only if strictly greater.
+    // bits: (1 << SH) = "not a0", (2 << SH) = "a2 beat a1" (meaningful only with the first bit set).
     asm("{\n\t"
         ".reg .pred p1, p2;\n\t"
         ".reg .f64 t;\n\t"
-        "setp.gt.f64 p1, %3, %2;\n\t"
-        "selp.f64 t, %3, %2, p1;\n\t"
-        "@p1 or.b32 %1, %1, %5;\n\t"
-        "setp.gt.f64 p2, %4, t;\n\t"
-        "selp.f64 %0, %4, t, p2;\n\t"
+        "setp.gt.f64 p2, %4, %3;\n\t"
+        "selp.f64 t, %4, %3, p2;\n\t"
         "@p2 or.b32 %1, %1, %6;\n\t"
+        "setp.gt.f64 p1, t, %2;\n\t"
+        "selp.f64 %0, t, %2, p1;\n\t"
+        "@p1 or.b32 %1, %1, %5;\n\t"
         "}"
         : "=d"(m), "+r"(bits)
         : "d"(a0), "d"(a1), "d"(a2), "n"(1u << SH), "n"(2u << SH));
@@ -485,12 +492,12 @@ __device__ __forceinline__ float max3_first_f32(float a0, float a1, float a2, ui
     asm("{\n\t"
         ".reg .pred p1, p2;\n\t"
         ".reg .f32 t;\n\t"
-        "setp.gt.f32 p1, %3, %2;\n\t"
-        "selp.f32 t, %3, %2, p1;\n\t"
-        "@p1 or.b32 %1, %1, %5;\n\t"
-        "setp.gt.f32 p2, %4, t;\n\t"
-        "selp.f32 %0, %4, t, p2;\n\t"
+        "setp.gt.f32 p2, %4, %3;\n\t"
+        "selp.f32 t, %4, %3, p2;\n\t"
         "@p2 or.b32 %1, %1, %6;\n\t"
+        "setp.gt.f32 p1, t, %2;\n\t"
+        "selp.f32 %0, t, %2, p1;\n\t"
+        "@p1 or.b32 %1, %1, %5;\n\t"
         "}"
         : "=f"(m), "+r"(bits)
         : "f"(a0), "f"(a1), "f"(a2), "n"(1u << SH), "n"(2u << SH));
@@ -963,10 +970,10 @@ __device__ __forceinline__ void banded_walk(const DevBanded* __restrict__ M, con
             emit(s);
             const int ln = (r - 1) / rpl, j = (r - 1) - ln * rpl;   // ln = stripe * 32 + lane
             const uint32_t t = tbw[((size_t)ln * P + c) * nw + j / 5] >> (6 * (j % 5));
-            // two bits per slot: bit0 = second candidate beat the first, bit1 = third beat both
-            const int kI = (t & 2u) ? 2 : (int)(t & 1u);
-            const int kM = (t & 8u) ? 2 : (int)((t >> 2) & 1u);
-            const int kD = (t & 32u) ? 2 : (int)((t >> 4) & 1u);
+            // two bits per slot (max3_first): bit0 = the first candidate lost, bit1 = the third beat the second
+            const int kI = (t & 1u) ? 1 + (int)((t >> 1) & 1u) : 0;
+            const int kM = (t & 4u) ? 1 + (int)((t >> 3) & 1u) : 0;
+            const int kD = (t & 16u) ? 1 + (int)((t >> 5) & 1u) : 0;
             if (sl == SLOT_D) {
                 if (c == M->acc_col) c = acc_tb[r - 1];
                 else { sl = kD; c -= 1; }
