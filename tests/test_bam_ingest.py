@@ -454,3 +454,57 @@ def test_pacbio_genotype_from_an_alignment_file(tmp_path):
     assert (got["copy_numbers"], got["maximum_likelihood"], got["observed_repeats"]) == want
     assert got["spanning_reads_count"] == len(reads)
     assert sorted(got["copy_numbers"]) == sorted(alleles)
+
+
+def test_damaged_records_are_refused_not_crashed_on(tmp_path):
+    """Random damage INSIDE valid BGZF blocks (checksums recomputed, so only the record parser can notice):
+    every call either works or raises ValueError; the process survives."""
+    import struct
+    import zlib
+    reads = make_reads(5, n_per_locus=12)
+    good = str(tmp_path / "good.bam")
+    bam_writer.write_bam(good, REFS, reads, block_size=3000)
+    data = open(good, "rb").read()
+    index = open(good + ".bai", "rb").read()
+    blocks, q = [], 0
+    while q < len(data):
+        size = struct.unpack_from("<H", data, q + 16)[0] + 1
+        blocks.append(zlib.decompressobj(-15).decompress(data[q + 18:q + size - 8]))
+        q += size
+    rng = random.Random(77)
+    outcomes = {"ok": 0, "refused": 0}
+    for trial in range(60):
+        hurt = [bytearray(b) for b in blocks]
+        for _ in range(rng.randint(1, 4)):
+            b = rng.randrange(1, len(hurt) - 1)                  # keep the header block and the end marker
+            if not hurt[b]:
+                continue
+            k = rng.randrange(len(hurt[b]))
+            hurt[b][k] = rng.choice([0, 0xff, hurt[b][k] ^ (1 << rng.randrange(8)), rng.randrange(256)])
+        path = str(tmp_path / ("hurt%d.bam" % trial))
+        with open(path, "wb") as fh:
+            for b in hurt:
+                co = zlib.compressobj(6, zlib.DEFLATED, -15)
+                comp = co.compress(bytes(b)) + co.flush()
+                fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp +
+                         struct.pack("<II", zlib.crc32(bytes(b)), len(b)))
+        with open(path + ".bai", "wb") as fh:
+            fh.write(index)                                      # offsets stay valid only if sizes did; fine either way
+        try:
+            with bam_ingest.AlignmentFile(path) as f:
+                for threads in (1, 3):
+                    b = f.scan_batch(threads=threads)
+                    [r.query_name for r in b]
+                for t, s, e in LOCI:
+                    fb = f.fetch_batch(REFS[t][0], s - 300, e + 300)
+                    fb.spanning_segments(s, e)
+                    try:
+                        fb.select_illumina(s, e, 150)
+                    except TypeError:
+                        pass
+            outcomes["ok"] += 1
+        except ValueError:
+            outcomes["refused"] += 1
+        except UnicodeDecodeError:
+            outcomes["ok"] += 1                                  # a damaged name: parsed, just not text
+    assert outcomes["ok"] + outcomes["refused"] == 60 and outcomes["refused"] > 0
