@@ -5,8 +5,9 @@ reads on both strands).  ``LocusDecoder`` keeps the same decisions -- which stra
 unmapped read wins, which reads are recruited, which are spanning -- but feeds all reads of
 the locus (or of many loci, ``decode_many``) to the engine at once and applies the path
 consumers to the returned paths.  The statistics applied to the repeat counts afterwards (genotype likelihood,
-frameshift test) are in ``genotype.py``; BAM / FASTA input, PacBio flank alignment (pairwise2) and
-the DNN pre-filter stay outside (out of scope).
+frameshift test) are in ``genotype.py``; BAM input is in ``bam_ingest.py`` (``pipeline.py`` chains it);
+the flank alignment of UNALIGNED PacBio reads (pairwise2) and the DNN pre-filter stay outside
+(out of scope).
 """
 from __future__ import annotations
 
