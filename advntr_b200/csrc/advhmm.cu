@@ -554,7 +554,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     size_t s_chunk = chunk_of(s_per_item, n_short, (size_t)kBandedWarpsMax * ctx->sm_count);
     // host-buffer calls that return state paths: at least eight chunks when the batch is large, so that
     // the paths of chunk i travel to the host while chunk i+1 is decoded (run_host)
-    if (ctx->mark_chunks && ctx->host_chunks > 1 && n_short >= ctx->host_chunks * 32768)
+    if (ctx->mark_chunks && ctx->host_chunks > 1 && n_short >= ctx->host_chunks * 16384)
         s_chunk = std::min<size_t>(s_chunk, ((size_t)n_short + ctx->host_chunks - 1) / ctx->host_chunks);
     size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)kLongWarps);
     {   // whole waves: two CTAs of kLongWarps reads per SM
@@ -722,7 +722,6 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
     if (n_bases > 0 && !seqs) return set_error(ADVHMM_EINVAL, "seqs is null");
 
     CU_TRY(ctx->d_seqs.ensure((size_t)n_bases + 16));
-    if (n_bases) CU_TRY(cudaMemcpyAsync(ctx->d_seqs.p, seqs, (size_t)n_bases, cudaMemcpyHostToDevice, ctx->stream));
     // outputs: logp | path_len | path_off | cursor | bad
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t o_logp = 0, o_plen = al((size_t)n_out * 8), o_poff = o_plen + al((size_t)n_out * 4);
@@ -749,21 +748,46 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
         CU_TRY(ctx->h_cursors.ensure(kMaxChunkMarks * sizeof(unsigned long long)));
         ctx->mark_chunks = true;
     }
-    // Large batches of many models go to the device as up to four sub-batches (cut at model boundaries):
+    // Large batches of many models go to the device as up to five sub-batches (cut at model boundaries):
     // planning sub-batch k+1 on the host overlaps decoding sub-batch k on the device.
-    int n_sub = (n_out >= 262144 && n_models >= 8) ? 4 : 1;
-    ctx->host_chunks = n_sub > 1 ? 2 : 8;
+    // The first sub-batch is small (1/16 of the reads): nothing runs on the device while it is planned.
+    const int n_sub = (n_out >= 262144 && n_models >= 8) ? 5 : 1;
+    std::vector<int> cut{0};                            // model index where sub-batch k starts
+    for (int k = 0; k + 1 < n_sub; ++k) {
+        const int64_t want = (int64_t)n_reads * (1 + 4 * k) / 16;         // reads before the cut: 1/16, 5/16, 9/16, 13/16
+        const int g = (int)(std::lower_bound(group_off + cut.back(), group_off + n_models, want) - group_off);
+        if (g > cut.back() && g < n_models) cut.push_back(g);
+    }
+    cut.push_back(n_models);
+    const int n_cut = (int)cut.size() - 1;
+    // Sequences: the first sub-batch's bases travel on the compute stream, the others on the copy stream
+    // while the first is being decoded; every later sub-batch waits for its own bases only.
+    const bool split_h2d = n_cut > 1;
+    if (split_h2d && !ctx->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < n_cut && n_bases; ++k) {
+        const int64_t b0 = k == 0 ? 0 : seq_off[group_off[cut[k]]];
+        const int64_t b1 = k + 1 == n_cut ? n_bases : seq_off[group_off[cut[k + 1]]];
+        cudaStream_t st = (k == 0 || !split_h2d) ? ctx->stream : ctx->copy_stream;
+        if (b1 > b0)
+            CU_TRY(cudaMemcpyAsync(ctx->d_seqs.as<uint8_t>() + b0, seqs + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+        if (k > 0 && split_h2d) {
+            while ((int)ctx->h2d_events.size() < n_cut) {
+                cudaEvent_t ev;
+                CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                ctx->h2d_events.push_back(ev);
+            }
+            CU_TRY(cudaEventRecord(ctx->h2d_events[k], ctx->copy_stream));
+        }
+    }
     int rc = ADVHMM_OK;
     std::vector<int64_t> rebased;
     if (want_path) CU_TRY(cudaMemsetAsync(op.cursor, 0, sizeof(unsigned long long), ctx->stream));
-    for (int k = 0, g0 = 0; k < n_sub && rc == ADVHMM_OK; ++k) {
-        int g1 = n_models;
-        if (k + 1 < n_sub) {
-            const int64_t want = (int64_t)n_reads * (k + 1) / n_sub;      // reads before the cut
-            g1 = (int)(std::lower_bound(group_off + g0, group_off + n_models, want) - group_off);
-            g1 = std::max(g1, g0);
-        }
-        if (g1 == g0 && k + 1 < n_sub) continue;
+    for (int k = 0; k < n_cut && rc == ADVHMM_OK; ++k) {
+        const int g0 = cut[k], g1 = cut[k + 1];
+        // state paths leave in chunks while the next chunk is decoded; the last sub-batch is cut finer,
+        // because its last chunk is the one copy nothing overlaps
+        ctx->host_chunks = n_cut > 1 ? (k + 1 == n_cut ? 3 : 1) : 8;       // every extra launch costs ~0.2 ms of tail
+        if (k > 0 && split_h2d) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->h2d_events[k], 0));
         const int64_t r0 = group_off[g0], r1 = group_off[g1];
         rebased.assign(group_off + g0, group_off + g1 + 1);
         for (int64_t& v : rebased) v -= r0;
@@ -772,7 +796,6 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
         if (sub.summaries) sub.summaries += r0 * strands;
         rc = run_batch(ctx, models + g0, g1 - g0, rebased.data(), ctx->d_seqs.as<uint8_t>(), seq_off + r0, (int)(r1 - r0),
                        flags, sub, forward, d_bad, (int)r0, /*continue_cursor=*/true);
-        g0 = g1;
     }
     ctx->mark_chunks = false;
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
@@ -792,23 +815,46 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
         }
     }
     const double t_marks = now();
-    // results back
+    // results back: straight into the caller's arrays when those are page-locked, else through the
+    // context's pinned staging buffer and a host copy
+    auto pinned = [](const void* p) {
+        if (!p) return true;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool direct = pinned(logp) && pinned(want_path || want_sum ? path_len : nullptr) &&
+                        pinned(want_path ? path_off : nullptr) && pinned(want_sum ? summaries : nullptr);
     CU_TRY(ctx->h_out.ensure(out_bytes));
-    CU_TRY(cudaMemcpyAsync(ctx->h_out.p, d, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (direct) {
+        CU_TRY(cudaMemcpyAsync(logp, d + o_logp, (size_t)n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((want_path || want_sum) && path_len)
+            CU_TRY(cudaMemcpyAsync(path_len, d + o_plen, (size_t)n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_path) CU_TRY(cudaMemcpyAsync(path_off, d + o_poff, (size_t)n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_sum)
+            CU_TRY(cudaMemcpyAsync(summaries, d + o_sum, (size_t)n_out * sizeof(advhmm_read_summary), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(static_cast<unsigned char*>(ctx->h_out.p) + o_cursor, d + o_cursor, 512, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CU_TRY(cudaMemcpyAsync(ctx->h_out.p, d, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     const double t_sync = now();
     const unsigned char* h = static_cast<const unsigned char*>(ctx->h_out.p);
     int32_t bad;
     memcpy(&bad, h + o_bad, sizeof bad);
     if (bad != 0x7f7f7f7f) return set_error(ADVHMM_ESYMBOL, "read %d contains a symbol code outside the model alphabet", bad);
-    memcpy(logp, h + o_logp, (size_t)n_out * 8);
-    if (want_sum) {
-        memcpy(summaries, h + o_sum, (size_t)n_out * sizeof(advhmm_read_summary));
-        if (path_len && !want_path) memcpy(path_len, h + o_plen, (size_t)n_out * 4);
+    if (!direct) {
+        memcpy(logp, h + o_logp, (size_t)n_out * 8);
+        if (want_sum) {
+            memcpy(summaries, h + o_sum, (size_t)n_out * sizeof(advhmm_read_summary));
+            if (path_len && !want_path) memcpy(path_len, h + o_plen, (size_t)n_out * 4);
+        }
     }
     if (want_path) {
-        memcpy(path_len, h + o_plen, (size_t)n_out * 4);
-        memcpy(path_off, h + o_poff, (size_t)n_out * 8);
+        if (!direct) {
+            memcpy(path_len, h + o_plen, (size_t)n_out * 4);
+            memcpy(path_off, h + o_poff, (size_t)n_out * 8);
+        }
         unsigned long long total;
         memcpy(&total, h + o_cursor, sizeof total);
         *path_total = (int64_t)total;
@@ -1105,6 +1151,7 @@ void advhmm_context_destroy(advhmm_context* ctx)
         for (DevBuf* b : {&ctx->d_seqs, &ctx->d_seq_off, &ctx->d_pk, &ctx->d_meta, &ctx->d_work, &ctx->d_out, &ctx->d_paths, &ctx->d_flags}) b->release();
         ctx->h_meta.release(); ctx->h_out.release(); ctx->h_cursors.release();
         for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
+        for (cudaEvent_t ev : ctx->h2d_events) cudaEventDestroy(ev);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->meta_done) cudaEventDestroy(ctx->meta_done);
         for (auto& v : ctx->prof_events)

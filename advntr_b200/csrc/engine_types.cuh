@@ -147,6 +147,7 @@ struct advhmm_context {
     // is decoded (marks = cursor snapshots + events recorded after every backtrack launch)
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
+    std::vector<cudaEvent_t> h2d_events;     // sequences of sub-batch k are on the device (run_host)
     PinnedBuf h_cursors;
     size_t n_marks = 0;
     bool mark_chunks = false;
