@@ -101,9 +101,8 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
     const uint32_t v1_delta = (uint32_t)(kImgV1 - kImgE) * P;
 
     double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
-    int accarg[RPL];
 #pragma unroll
-    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; accarg[j] = 0; }
+    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; }
     double bI = kNegInf, bM = kNegInf, bD = kNegInf;   // row above my block, previous column
     const bool store_last = ALIGNED && lane == ln;
     // lane-skewed views: index them with the step t (column c = t - lane).  The empty asm keeps
@@ -164,7 +163,9 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
 #pragma unroll
             for (int j = 0; j < RPL; ++j) {
                 const double cand = nD[j] + aw;
-                if (cand > acc[j]) { acc[j] = cand; accarg[j] = c; }
+                // the source column goes straight to the workspace (the last improvement is the one that
+                // stays): no register per row, a predicated store instead of a select
+                if (cand > acc[j]) { acc[j] = cand; acc_tb[j] = (uint16_t)c; }
             }
         }
         // I slots chain down the rows of this column
@@ -206,11 +207,8 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
     for (int t = t_steady; t < t_down; ++t) step(t, std::false_type{});
 #pragma unroll 1
     for (int t = t_down; t < steps; ++t) step(t, std::true_type{});
-    // which unit_end fed the collector, per read position (read by the backtrack only)
-    if (lane < nl) {
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) acc_tb[j] = (uint16_t)accarg[j];
-    }
+    // (which unit_end fed the collector, per read position, was stored as it changed: acc_tb, read by
+    // the backtrack only and only for rows whose collector value is finite)
 }
 
 template <int RPL, int WPB>
