@@ -365,6 +365,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - te0) * 1e3
         assert h_total.value == n_paths
+        # the host-buffer call returns what the device-resident call computed, bit for bit
+        assert torch.equal(h_logp.view(torch.int64), d_logp.cpu().view(torch.int64))
+        assert torch.equal(h_plen, d_plen.cpu())
     # ---- extra (reported, not the headline): on-device reducers instead of paths; fp32 mode ----
     extra = {}
     if not args.no_e2e:

@@ -452,3 +452,49 @@ def test_random_loci_random_reads_vs_oracle(ctx, seed):
         assert np.allclose(fwd, oracle.OracleModel(model.baked).log_probability(codes[:10]), rtol=1e-9, atol=0)
         dm.close()
     assert "banded" in kinds
+
+
+def test_host_call_with_page_locked_result_arrays(ctx):
+    """Scores, path offsets and summaries go straight into the caller's arrays when those are page-locked
+    (no staging copy); same bits as the pageable route, with and without state paths."""
+    import ctypes as C
+    import torch
+    from advntr_b200 import engine, synth
+    lib = engine.load_library()
+    models, groups = [], []
+    for lid in (3, 4, 5):
+        loc = synth.config2_locus(lid)
+        dm = engine.DeviceModel(ctx, loc.build_model().baked)
+        mapped, unmapped = synth.config2_reads(loc, coverage=10, decoys=5)
+        models.append(dm)
+        groups.append([oracle.encode(r) for r in mapped + unmapped])
+    want = ctx.viterbi_multi(models, groups)                        # numpy arrays: pageable route
+    flat = [c for g in groups for c in g]
+    seqs, off = engine.pack_reads(flat)
+    goff = np.zeros(len(groups) + 1, dtype=np.int64)
+    np.cumsum([len(g) for g in groups], out=goff[1:])
+    R = len(flat)
+    cap = int(want.paths.size) + 64
+    h_seqs = torch.from_numpy(seqs).pin_memory()
+    h_logp = torch.empty(R, dtype=torch.float64).pin_memory()
+    h_plen = torch.empty(R, dtype=torch.int32).pin_memory()
+    h_poff = torch.empty(R, dtype=torch.int64).pin_memory()
+    h_path = torch.empty(cap, dtype=torch.int32).pin_memory()
+    total = C.c_int64(0)
+    handles = (C.c_void_p * len(models))(*[m._h for m in models])
+    engine._check(lib.advhmm_viterbi_multi(ctx._h, handles, len(models), goff.ctypes.data, h_seqs.data_ptr(),
+                                           off.ctypes.data, R, engine.WANT_PATH, h_logp.data_ptr(), h_plen.data_ptr(),
+                                           h_poff.data_ptr(), h_path.data_ptr(), cap, C.byref(total)))
+    assert same_bits(h_logp.numpy(), want.logp)
+    assert np.array_equal(h_plen.numpy(), want.path_len)
+    assert total.value == want.paths.size
+    for i in range(0, R, 7):
+        a = int(h_poff[i])
+        assert np.array_equal(h_path.numpy()[a:a + int(h_plen[i])], want.path(i))
+    # scores only (no paths): the same route without the path arrays
+    h_logp.zero_()
+    engine._check(lib.advhmm_viterbi_multi(ctx._h, handles, len(models), goff.ctypes.data, h_seqs.data_ptr(),
+                                           off.ctypes.data, R, 0, h_logp.data_ptr(), None, None, None, 0, None))
+    assert same_bits(h_logp.numpy(), want.logp)
+    for dm in models:
+        dm.close()
