@@ -1,6 +1,6 @@
 """End-to-end demo on synthetic data: what `advntr genotype` does for Illumina reads, minus BAM IO.
 
-    python tools/demo_genotype.py [n_loci=24] [coverage=30]
+    python tools/demo_genotype.py [n_loci=24] [coverage=30] [--bam]
 
 For every locus a diploid sample is simulated (two alleles with their own repeat counts, 150 bp reads
 with sequencing errors; a fifth of the reads is "unmapped" and arrives on either strand, mixed with
@@ -12,6 +12,11 @@ random decoys).  Then, as genome_analyzer.py:273-297 does:
   3. every locus is genotyped from the repeat counts of its recruited reads.
 
 Prints one line per locus (id, pattern length, truth, call, likelihood, reads used) and a summary.
+
+With ``--bam`` the sample is first written as a coordinate-sorted BAM + BAI (tests/bam_writer.py: mapped
+reads at their loci on a synthetic chromosome, unmapped reads at the end of the file) and genotyped
+from that file: region fetches, read-level tests and unmapped-read extraction in libadvbam
+(``GenotypingRun.genotype_alignment_file``).
 """
 import os
 import random
@@ -21,8 +26,10 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from advntr_b200 import pipeline, synth
 
-n_loci = int(sys.argv[1]) if len(sys.argv) > 1 else 24
-coverage = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+use_bam = "--bam" in sys.argv
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+n_loci = int(argv[0]) if len(argv) > 0 else 24
+coverage = int(argv[1]) if len(argv) > 1 else 30
 rng = random.Random(2026)
 
 loci, mapped, names, seqs, truth = [], {}, [], [], {}
@@ -34,7 +41,8 @@ for lid in range(1, n_loci + 1):
     a = rng.randint(2, top)
     b = a if rng.random() < 0.4 else rng.randint(2, top)
     truth[lid] = tuple(sorted((a, b)))
-    loci.append(pipeline.LocusSpec(lid, left, right, [ru] * max(2, 100 // R)))
+    loci.append(pipeline.LocusSpec(lid, left, right, [ru] * max(2, 100 // R), chromosome="chr1",
+                                   start_point=10000 * lid + len(left)))
     mapped[lid] = []
     for copies in (a, b):
         allele = left + ru * copies + right
@@ -52,10 +60,28 @@ for _ in range(20 * n_loci):
     names.append("u%06d" % len(names))
     seqs.append(synth.rand_dna(rng, 150))
 
+bam_path = None
+if use_bam:
+    import tempfile
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import bam_writer
+    records = []
+    for spec in loci:
+        end = spec.start_point + sum(map(len, spec.repeat_segments))
+        for k, read in enumerate(mapped[spec.id]):
+            pos = rng.randint(spec.start_point - 140, end - 5)       # placement only matters for the region test
+            records.append(bam_writer.Read("m%d_%d" % (spec.id, k), rng.choice([0, 16]), 0, pos, 60, "%dM" % len(read),
+                                           read, [rng.randint(25, 40) for _ in read]))
+    records.sort(key=lambda r: r.pos)
+    records += [bam_writer.Read(n, 4, -1, -1, 0, "", s, [30] * len(s)) for n, s in zip(names, seqs)]
+    bam_path = os.path.join(tempfile.mkdtemp(), "sample.bam")
+    bam_writer.write_bam(bam_path, [("chr1", 10000 * (n_loci + 2))], records)
+    print("wrote %s (%d records, %.1f MB)" % (bam_path, len(records), os.path.getsize(bam_path) / 1e6))
+
 t0 = time.time()
-run = pipeline.GenotypingRun(loci)
+run = pipeline.GenotypingRun.from_alignment_file(loci, bam_path) if use_bam else pipeline.GenotypingRun(loci)
 t1 = time.time()
-calls = run.genotype(mapped, names, seqs)
+calls = run.genotype_alignment_file(bam_path) if use_bam else run.genotype(mapped, names, seqs)
 t2 = time.time()
 right_calls = 0
 for spec in loci:
