@@ -563,9 +563,8 @@ banded_fill_f32_kernel(const BandedArgs a)
     const uint32_t v1_delta = (uint32_t)(kImgFV1 - kImgFE) * P;
 
     float cI[RPL], cM[RPL], cD[RPL], acc[RPL];
-    int accarg[RPL];
 #pragma unroll
-    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNI; accarg[j] = 0; }
+    for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNI; }
     float bI = kNI, bM = kNI, bD = kNI;
 
     const int steps = NC + nl - 1;
@@ -606,7 +605,7 @@ banded_fill_f32_kernel(const BandedArgs a)
 #pragma unroll
             for (int j = 0; j < RPL; ++j) {
                 const float cand = nD[j] + aw;
-                if (cand > acc[j]) { acc[j] = cand; accarg[j] = c; }
+                if (cand > acc[j]) { acc[j] = cand; acc_tb[j] = (uint16_t)c; }   // stored as it changes (see banded_sweep)
             }
         }
         float uI = uI0, uM = uM0, uD = uD0;
@@ -627,10 +626,6 @@ banded_fill_f32_kernel(const BandedArgs a)
                 if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
             vfin_t[t] = fI; vfin_t[P + t] = fM; vfin_t[2 * P + t] = fD;
         }
-    }
-    if (lane < nl) {
-#pragma unroll
-        for (int j = 0; j < RPL; ++j) acc_tb[j] = (uint16_t)accarg[j];
     }
     __syncwarp();
     const int NF = M->NF;
@@ -748,9 +743,8 @@ banded_long_kernel(const LongArgs a)
         uint16_t* __restrict__ acc_tb = a.acc_tb + slot * a.acc_stride + (size_t)s * H + lane * RPL;
 
         double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
-        int accarg[RPL];
 #pragma unroll
-        for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; accarg[j] = 0; }
+        for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; }
         double bI = kNegInf, bM = kNegInf, bD = kNegInf;
 
         if (s > 0) {                           // ring block 0 = carried values of columns 0..31
@@ -811,7 +805,7 @@ banded_long_kernel(const LongArgs a)
 #pragma unroll
                 for (int j = 0; j < RPL; ++j) {
                     const double cand = nD[j] + aw;
-                    if (cand > acc[j]) { acc[j] = cand; accarg[j] = c; }
+                    if (cand > acc[j]) { acc[j] = cand; acc_tb[j] = (uint16_t)c; }   // stored as it changes (see banded_sweep)
                 }
             }
             double uI = uI0, uM = uM0, uD = uD0;
@@ -835,10 +829,6 @@ banded_long_kernel(const LongArgs a)
                     if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
                 vfin[c] = fI; vfin[(size_t)P + c] = fM; vfin[(size_t)2 * P + c] = fD;
             }
-        }
-        if (lane < nl) {
-#pragma unroll
-            for (int j = 0; j < RPL; ++j) acc_tb[j] = (uint16_t)accarg[j];
         }
         __syncwarp();
     }
