@@ -552,8 +552,9 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         return std::min<size_t>(c, (size_t)n_items);
     };
     size_t s_chunk = chunk_of(s_per_item, n_short, (size_t)kBandedWarpsMax * ctx->sm_count);
-    // host-buffer calls that return state paths: at least eight chunks when the batch is large, so that
-    // the paths of chunk i travel to the host while chunk i+1 is decoded (run_host)
+    // host-buffer calls that return state paths: run_host asks for host_chunks chunks (8 for a single batch,
+    // 3 for the last sub-batch of a split one), so that the paths of chunk i travel to the host while chunk
+    // i+1 is decoded
     if (ctx->mark_chunks && ctx->host_chunks > 1 && n_short >= ctx->host_chunks * 16384)
         s_chunk = std::min<size_t>(s_chunk, ((size_t)n_short + ctx->host_chunks - 1) / ctx->host_chunks);
     size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)kLongWarps);
