@@ -508,3 +508,27 @@ def test_damaged_records_are_refused_not_crashed_on(tmp_path):
         except UnicodeDecodeError:
             outcomes["ok"] += 1                                  # a damaged name: parsed, just not text
     assert outcomes["ok"] + outcomes["refused"] == 60 and outcomes["refused"] > 0
+
+
+def test_committed_bam_fixture():
+    """tests/golden/tiny.bam (+ .bai) with the answers the plain-Python reader gave when it was made
+    (tests/golden/make_golden_bam.py): the byte-level format is pinned independently of today's writer."""
+    import json
+    from conftest import GOLDEN
+    want = json.load(open(os.path.join(GOLDEN, "tiny_bam_expected.json")))
+    with bam_ingest.AlignmentFile(os.path.join(GOLDEN, "tiny.bam")) as f:
+        assert list(f.references) == want["references"] and list(f.lengths) == want["lengths"]
+        assert len(f.scan_batch()) == want["n_records"]
+        got_head = [[r.query_name, r.flag, r.reference_start, r.reference_end, r.seq, r.mapq] for r in f.head(5)]
+        assert got_head == want["head"]
+        for case in want["fetch"]:
+            t, s, e = case["region"]
+            assert [r.query_name for r in f.fetch(want["references"][t], s, e)] == case["names"]
+        for case in want["select"]:
+            t, s, e = case["region"]
+            got = bam_ingest.select_mapped_illumina(f, want["references"][t], s, e, 150)
+            assert got["names"] == case["names"] and got["vntr_bp"] == case["vntr_bp"]
+            seqs = ["".join("ACGT"[c] for c in got["codes"][got["off"][i]:got["off"][i + 1]]) for i in range(len(got["names"]))]
+            assert seqs == case["sequences"]
+        names, seqs = bam_ingest.extract_unmapped_reads(f)
+        assert [list(x) for x in zip(names, seqs)] == want["unmapped"]
