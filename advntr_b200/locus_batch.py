@@ -17,11 +17,12 @@ from . import engine, fast_compile, genotype, path_utils, pomegranate, read_matc
 
 
 class SelectedRead(object):
-    """``vntr_finder.py:49-60``."""
+    """``vntr_finder.py:45-52``."""
 
-    def __init__(self, sequence, logp, vpath, is_mapped=True, query_name=None):
+    def __init__(self, sequence, logp, vpath, is_mapped=True, query_name=None, mapq=None, reference_start=None):
         self.sequence, self.logp, self.vpath = sequence, logp, vpath
         self.is_mapped, self.query_name = is_mapped, query_name
+        self.mapq, self.reference_start = mapq, reference_start
 
 
 _COMP = str.maketrans("ACGT", "TGCA")
@@ -100,6 +101,32 @@ class LocusDecoder(object):
             if path_utils.recruit_read(res.logp[k], vp, score, s, self.left_flank, self.right_flank) and \
                     repeat_bp > self.min_repeat_bp_to_add_read:
                 selected.append(SelectedRead(s, float(res.logp[k]), vp, False))
+        return selected
+
+    def select_reads_from_alignment_file(self, alignment_file, chromosome, start_point, unmapped_filtered_reads=()):
+        """``select_illumina_reads(alignment_file, unmapped_filtered_reads)`` (``vntr_finder.py:701-773``)
+        with its file access: the region fetch and the read-level tests run in ``libadvbam``
+        (``bam_ingest.select_mapped_illumina``); mapped reads keep ``mapq``, ``reference_start`` and
+        ``query_name`` as the reference's ``SelectedRead`` does.  ``find_frameshift_from_alignment_file``
+        (``:776-780``) is ``frameshift_candidate(select_reads_from_alignment_file(...))``."""
+        from . import bam_ingest
+        own = not isinstance(alignment_file, bam_ingest.AlignmentFile)
+        f = bam_ingest.AlignmentFile(alignment_file) if own else alignment_file
+        try:
+            end = start_point + sum(len(seg) for seg in self.segments)
+            m = bam_ingest.select_mapped_illumina(f, chromosome, start_point, end, self.read_length)
+        finally:
+            if own:
+                f.close()
+        mapped = ["".join("ACGT"[c] for c in m["codes"][m["off"][i]:m["off"][i + 1]]) for i in range(len(m["names"]))]
+        selected = self.select_reads(mapped, unmapped_filtered_reads)
+        by_seq = {}
+        for i, seq in enumerate(mapped):
+            by_seq.setdefault(seq, []).append(i)
+        for read in selected:
+            if read.is_mapped:
+                i = by_seq[read.sequence].pop(0)      # select_reads keeps the order of the mapped reads
+                read.query_name, read.mapq, read.reference_start = m["names"][i], int(m["mapq"][i]), int(m["reference_start"][i])
         return selected
 
     def observed_repeats(self, selected, accuracy_filter=False):

@@ -532,3 +532,40 @@ def test_committed_bam_fixture():
             assert seqs == case["sequences"]
         names, seqs = bam_ingest.extract_unmapped_reads(f)
         assert [list(x) for x in zip(names, seqs)] == want["unmapped"]
+
+
+@pytest.mark.gpu
+def test_one_locus_selection_and_frameshift_from_an_alignment_file(tmp_path):
+    """LocusDecoder.select_reads_from_alignment_file == select_reads on the reads the oracle's loop hands
+    over, with the mapped reads' names / mapq / positions attached."""
+    from test_pipeline import _sample
+    from advntr_b200 import locus_batch
+    loci, mapped, names, seqs, truth = _sample(n_loci=2, seed=21)
+    lid, left, right, segs = loci[0]
+    rng = random.Random(6)
+    start = 5000 + len(left)
+    reads = []
+    for k, read in enumerate(mapped[lid]):
+        pos = rng.randint(start - 140, start + sum(map(len, segs)) - 5)
+        reads.append(bam_writer.Read("m%d" % k, rng.choice([0, 16]), 0, pos, rng.choice([60, 60, 60, 0]), "150M", read,
+                                     [rng.randint(25, 40) for _ in read]))
+    reads.sort(key=lambda r: r.pos)
+    path = str(tmp_path / "one.bam")
+    bam_writer.write_bam(path, [("chr1", 50000)], reads)
+    dec = locus_batch.LocusDecoder(left, right, segs, read_length=150, locus_id=lid)
+    unm = [s for s in seqs[:40]]
+    got = dec.select_reads_from_alignment_file(path, "chr1", start, unm)
+    _, _, records = bam_oracle.read_bam(path)
+    sel, _ = bam_oracle.select_illumina_mapped(records, 0, start, start + sum(map(len, segs)), 150)
+    want = dec.select_reads([s for _, s in sel], unm)
+    assert [(r.sequence, r.logp, r.is_mapped) for r in got] == [(r.sequence, r.logp, r.is_mapped) for r in want]
+    by_name = {r.query_name: r for r, _ in sel}
+    n_mapped = 0
+    for r in got:
+        if r.is_mapped:
+            n_mapped += 1
+            src = by_name[r.query_name]
+            assert src.seq == r.sequence and src.mapq == r.mapq and src.reference_start == r.reference_start
+            assert r.mapq > 0
+    assert n_mapped > 10
+    assert dec.frameshift_candidate(got) == dec.frameshift_candidate(want)
