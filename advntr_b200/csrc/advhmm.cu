@@ -410,9 +410,18 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     Family fam_short, fam_long, fam_generic;
     fam_short.items.reserve(n_out);                 // the common case: every read takes the short-read kernel
     fam_short.model.reserve(n_out);
+    // every read belongs to exactly one group: reads outside every group would never be decoded and
+    // their result slots would be returned uninitialised
+    if (group_off[0] != 0 || group_off[n_models] != n_reads)
+        return set_error(ADVHMM_EINVAL, "group_off must start at 0 and end at n_reads (%lld .. %lld, n_reads %d)",
+                         (long long)group_off[0], (long long)group_off[n_models], n_reads);
     for (int gi = 0; gi < n_models; ++gi) {
         advhmm_model* mod = models[gi];
         if (!mod || mod->ctx != ctx) return set_error(ADVHMM_EINVAL, "model %d does not belong to this context", gi);
+        // reads are packed 2 bits per symbol and validated against ONE alphabet size per call
+        if (mod->cm.g.K != models[0]->cm.g.K)
+            return set_error(ADVHMM_EINVAL, "model %d has %d symbols, model 0 has %d: one alphabet per call", gi,
+                             mod->cm.g.K, models[0]->cm.g.K);
         const int64_t r0 = group_off[gi], r1 = group_off[gi + 1];
         if (r0 < 0 || r1 < r0 || r1 > n_reads) return set_error(ADVHMM_EINVAL, "bad group_off at model %d", gi);
         const bool banded = mod->d_banded && !(flags & ADVHMM_FORCE_GENERIC);
@@ -1149,7 +1158,7 @@ void advhmm_context_destroy(advhmm_context* ctx)
     if (ctx->device >= 0) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
-        for (DevBuf* b : {&ctx->d_seqs, &ctx->d_seq_off, &ctx->d_pk, &ctx->d_meta, &ctx->d_work, &ctx->d_out, &ctx->d_paths, &ctx->d_flags}) b->release();
+        for (DevBuf* b : {&ctx->d_seqs, &ctx->d_seq_off, &ctx->d_pk, &ctx->d_meta, &ctx->d_work, &ctx->d_out, &ctx->d_paths, &ctx->d_flags, &ctx->d_badflag}) b->release();
         ctx->h_meta.release(); ctx->h_out.release(); ctx->h_cursors.release();
         for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
         for (cudaEvent_t ev : ctx->h2d_events) cudaEventDestroy(ev);
@@ -1325,13 +1334,27 @@ int advhmm_viterbi_multi_summary(advhmm_context* ctx, advhmm_model* const* model
         return set_error(ADVHMM_EINVAL, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU_TRY(cudaSetDevice(ctx->device));
-    CU_TRY(ctx->d_flags.ensure(256));
-    int32_t* d_bad = ctx->d_flags.as<int32_t>();
+    CU_TRY(ctx->d_badflag.ensure(256));
+    int32_t* d_bad = ctx->d_badflag.as<int32_t>();
     CU_TRY(cudaMemsetAsync(d_bad, 0x7f, sizeof(int32_t), ctx->stream));
     OutPtrs op{logp, path_len, path_off, path, want_path ? path_cap : 0,
                reinterpret_cast<unsigned long long*>(path_total), want_sum ? summaries : nullptr};
     return run_batch(ctx, models, n_models, group_off, seqs, seq_off, n_reads, flags & ~ADVHMM_DEVICE_BUFFERS, op,
                      false, d_bad);
+}
+
+int advhmm_context_bad_symbol(advhmm_context* ctx, int32_t* first_bad_read)
+{
+    if (!ctx || ctx->device < 0 || !first_bad_read) return set_error(ADVHMM_EINVAL, "no device context");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU_TRY(cudaSetDevice(ctx->device));
+    *first_bad_read = -1;
+    if (!ctx->d_badflag.p) return ADVHMM_OK;               // no device-buffer call was made yet
+    int32_t bad = 0x7f7f7f7f;
+    CU_TRY(cudaMemcpyAsync(&bad, ctx->d_badflag.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (bad != 0x7f7f7f7f) *first_bad_read = bad;
+    return ADVHMM_OK;
 }
 
 int advhmm_kfilter_create(advhmm_context* ctx, int64_t n_keywords, const char* keywords, const int64_t* keyword_off,

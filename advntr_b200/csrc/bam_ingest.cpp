@@ -18,6 +18,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -500,7 +501,7 @@ int resolve_threads(int n_threads) {
 template <class Body>
 void parallel_for(size_t n, int n_threads, Body&& body) {
     std::atomic<size_t> next{0};
-    std::string error;
+    std::exception_ptr first;                           // the first worker failure, rethrown unchanged
     std::atomic<bool> failed{false};
     auto work = [&]() {
         for (;;) {
@@ -508,8 +509,8 @@ void parallel_for(size_t n, int n_threads, Body&& body) {
             if (i >= n || failed.load()) return;
             try {
                 body(i);
-            } catch (const std::exception& e) {
-                if (!failed.exchange(true)) error = e.what();
+            } catch (...) {
+                if (!failed.exchange(true)) first = std::current_exception();
             }
         }
     };
@@ -518,7 +519,7 @@ void parallel_for(size_t n, int n_threads, Body&& body) {
     for (int t = 1; t < nt; ++t) pool.emplace_back(work);
     work();
     for (auto& t : pool) t.join();
-    if (failed.load()) throw Failure(ADVBAM_E_FORMAT, error);
+    if (failed.load()) std::rethrow_exception(first);   // a Failure keeps its code, bad_alloc stays bad_alloc
 }
 
 void scan_windowed(advbam_file* f, uint64_t start, uint32_t require, uint32_t exclude, int n_threads, advbam_reads& out);

@@ -141,6 +141,7 @@ struct advhmm_context {
     int64_t launches = 0;
     size_t workspace_budget = 0;
     DevBuf d_seqs, d_seq_off, d_pk, d_meta, d_work, d_out, d_paths, d_flags;
+    DevBuf d_badflag;            // device-buffer calls: first read with a code outside the alphabet
     PinnedBuf h_meta, h_out;
     cudaEvent_t meta_done = nullptr;
     // host-buffer calls: state paths go home chunk by chunk on a second stream while the next chunk

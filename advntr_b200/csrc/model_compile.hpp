@@ -105,9 +105,18 @@ namespace detail {
 inline bool build_generic(const advhmm_model_desc& d, GenericTables& g, std::string& err)
 {
     const int m = d.n_states, S = d.silent_start, K = d.n_symbols;
-    if (m <= 0 || S < 0 || S > m || K < 1 || K > 16 || !d.in_off || d.start_index < 0 ||
+    if (m <= 0 || S < 0 || S > m || !d.in_off || d.start_index < 0 ||
         d.start_index >= m || d.end_index < 0 || d.end_index >= m) {
         err = "malformed model descriptor";
+        return false;
+    }
+    // reads are packed 2 bits per symbol on the device: alphabets of up to four symbols only
+    if (K < 1 || K > 4) {
+        err = "n_symbols must be 1..4 (reads are packed 2 bits per symbol)";
+        return false;
+    }
+    if (d.in_off[0] != 0) {
+        err = "in_off[0] must be 0";
         return false;
     }
     const int E = d.in_off[m];

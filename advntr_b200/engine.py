@@ -23,7 +23,7 @@ KIND_GENERIC, KIND_BANDED = 0, 1
 EXPORTS = (
     "advhmm_context_create", "advhmm_context_destroy", "advhmm_context_synchronize",
     "advhmm_context_stream", "advhmm_context_launch_count", "advhmm_context_profile",
-    "advhmm_context_profile_read", "advhmm_fp64_add_peak",
+    "advhmm_context_profile_read", "advhmm_fp64_add_peak", "advhmm_context_bad_symbol",
     "advhmm_model_create", "advhmm_model_destroy", "advhmm_model_info_get",
     "advhmm_viterbi_batch", "advhmm_log_probability_batch", "advhmm_viterbi_multi",
     "advhmm_viterbi_multi_summary", "advhmm_model_set_state_classes",
@@ -77,6 +77,7 @@ def load_library():
         lib.advhmm_context_profile.argtypes = [vp, C.c_int]
         lib.advhmm_context_profile_read.argtypes = [vp, vp, vp, vp, vp]
         lib.advhmm_fp64_add_peak.argtypes = [vp, vp]
+        lib.advhmm_context_bad_symbol.argtypes = [vp, vp]
         lib.advhmm_model_create.argtypes = [vp, C.POINTER(ModelDesc), C.POINTER(vp)]
         lib.advhmm_model_destroy.argtypes = [vp]
         lib.advhmm_model_destroy.restype = None
@@ -180,6 +181,12 @@ class Context(object):
         _check(self._lib.advhmm_context_profile_read(self._h, C.addressof(fm), C.addressof(fl),
                                                      C.addressof(bm), C.addressof(bl)))
         return fm.value, fl.value, bm.value, bl.value
+
+    def bad_symbol(self):
+        """After a device-buffer call: index of its first read with a code outside the alphabet, or -1."""
+        bad = C.c_int32(-1)
+        _check(self._lib.advhmm_context_bad_symbol(self._h, C.addressof(bad)))
+        return bad.value
 
     def fp64_add_peak(self):
         g = C.c_double(0)

@@ -34,8 +34,13 @@ def reverse_complement(seq):
 
 class LocusDecoder(object):
     def __init__(self, left_flank, right_flank, repeat_segments, read_length=150, scaled_score=None,
-                 error_rate=read_matcher.DEFAULT_MAX_ERROR_RATE, flank_size=150, locus_id=None,
+                 error_rate=read_matcher.DEFAULT_MAX_ERROR_RATE, flank_size=None, locus_id=None,
                  trained_hmms_dir=None):
+        # get_vntr_matcher_hmm builds the matcher with flanking_region_size = read_length
+        # (vntr_finder.py:131-132): a 100 bp or 250 bp library gets 100 / 250-base flank models
+        if flank_size is None:
+            flank_size = read_length
+        self.flank_size = flank_size
         self.id = locus_id
         self.left_flank, self.right_flank = left_flank, right_flank
         self.segments = list(repeat_segments)

@@ -68,7 +68,7 @@ typedef struct advhmm_model_desc {
     int32_t        start_index;
     int32_t        end_index;
     int32_t        finite;       /* 1: logp = v[n][end_index]; 0: best state (hmm.pyx:2089-2098) */
-    int32_t        n_symbols;    /* 1..16 */
+    int32_t        n_symbols;    /* 1..4: reads are packed 2 bits per symbol; one alphabet size per call */
     const int32_t* in_off;       /* [n_states + 1] */
     const int32_t* in_src;       /* [in_off[n_states]] */
     const double*  in_logp;      /* [in_off[n_states]] */
@@ -146,7 +146,10 @@ int advhmm_log_probability_batch(advhmm_model* model,
  * With ADVHMM_DEVICE_BUFFERS every other buffer (seqs, logp, path_len, path_off, path,
  * path_total) is a DEVICE pointer on ctx's device: nothing is copied, the call only queues
  * work on the context's stream and returns; *path_total is a device int64; reads whose path
- * did not fit in path_cap get path_len = -2. */
+ * did not fit in path_cap get path_len = -2.  A code >= n_symbols cannot be reported by the return
+ * value of an asynchronous call: such a read is decoded with the bad code read as symbol 0 and the
+ * index of the first such read is kept on the device; advhmm_context_bad_symbol() fetches it (the host
+ * path returns ADVHMM_ESYMBOL, the reference raises ValueError, hmm.pyx:72-79). */
 #define ADVHMM_DEVICE_BUFFERS 0x100u
 int advhmm_viterbi_multi(advhmm_context* ctx,
                          advhmm_model* const* models, int32_t n_models,
@@ -155,6 +158,10 @@ int advhmm_viterbi_multi(advhmm_context* ctx,
                          uint32_t flags,
                          double* logp, int32_t* path_len, int64_t* path_off,
                          int32_t* path, int64_t path_cap, int64_t* path_total);
+
+/* After an ADVHMM_DEVICE_BUFFERS call: synchronise the context's stream and report the first read of
+ * that call holding a code >= n_symbols (*first_bad_read = -1: none). */
+int advhmm_context_bad_symbol(advhmm_context* ctx, int32_t* first_bad_read);
 
 /* ---- on-device path reducers ----------------------------------------------------------------
  * What adVNTR derives from a Viterbi path (hmm_utils.py:155-286), computed by the backtrack

@@ -247,6 +247,11 @@ def test_fp32_mode(ctx, golden):
         vp = [(int(k), _S(golden.names[k])) for k in res.path(i)]
         same += int(path_utils.get_number_of_repeats_in_vpath(vp) == golden.ru_count[i])
         total += 1
+    # north_star: "RU-count concordance reported" -- shown with `pytest -s` / in the -rA summary,
+    # and bench.py repeats it in extras.fp32_mode.ru_concordance
+    print("fp32 RU-count concordance [%s]: %d/%d = %.2f %%; max |dlogp|/|logp| = %.3g"
+          % (golden.name, same, total, 100.0 * same / max(total, 1),
+             float(np.max(np.abs(res.logp[finite] - golden.logp[finite]) / np.abs(golden.logp[finite])))))
     assert same >= 0.97 * total, "RU-count concordance %d/%d" % (same, total)
 
 
@@ -498,3 +503,106 @@ def test_host_call_with_page_locked_result_arrays(ctx):
     assert same_bits(h_logp.numpy(), want.logp)
     for dm in models:
         dm.close()
+
+
+def test_group_offsets_must_cover_every_read(ctx, golden_config1):
+    """Reads outside every group would never be decoded, yet their result slots would come back as if
+    they had been: the call is refused instead (ADVHMM_EINVAL)."""
+    import ctypes as C
+    from advntr_b200 import engine
+    lib = engine.load_library()
+    dm = engine.DeviceModel(ctx, golden_config1.baked)
+    codes = golden_config1.codes()[:6]
+    seqs, off = engine.pack_reads(codes)
+    handles = (C.c_void_p * 1)(dm._h)
+    logp = np.empty(6)
+    for goff in ([0, 4], [1, 6], [2, 4]):
+        g = np.asarray(goff, dtype=np.int64)
+        rc = lib.advhmm_viterbi_multi(ctx._h, handles, 1, g.ctypes.data, seqs.ctypes.data, off.ctypes.data, 6, 0,
+                                      logp.ctypes.data, None, None, None, 0, None)
+        assert rc == engine.EINVAL, goff
+        assert b"group_off" in lib.advhmm_last_error()
+    g = np.asarray([0, 6], dtype=np.int64)
+    assert lib.advhmm_viterbi_multi(ctx._h, handles, 1, g.ctypes.data, seqs.ctypes.data, off.ctypes.data, 6, 0,
+                                    logp.ctypes.data, None, None, None, 0, None) == 0
+    assert same_bits(logp, golden_config1.logp[:6])
+    dm.close()
+
+
+def test_one_alphabet_per_call_and_at_most_four_symbols(ctx, golden_config1):
+    """Reads are packed 2 bits per symbol and validated against one alphabet size per call."""
+    from advntr_b200 import engine
+    two = {"n_states": 3, "silent_start": 1, "start_index": 1, "end_index": 2, "finite": 1,
+           "in_off": np.array([0, 2, 2, 3], dtype=np.int32), "in_src": np.array([0, 1, 0], dtype=np.int32),
+           "in_logp": np.log(np.array([0.5, 1.0, 0.5])), "emis": np.log(np.array([[0.5, 0.5]]))}
+    small = engine.DeviceModel(ctx, two)
+    assert small.n_symbols == 2
+    big = engine.DeviceModel(ctx, golden_config1.baked)
+    c = [np.array([0, 1, 0], dtype=np.uint8)]
+    lp, paths = oracle.OracleModel(two).viterbi(c)
+    assert same_bits(small.viterbi(c).logp, lp)
+    with pytest.raises(engine.EngineError) as ei:
+        ctx.viterbi_multi([big, small], [c, c])
+    assert ei.value.code == engine.EINVAL
+    five = dict(two, emis=np.log(np.full((1, 5), 0.2)))
+    with pytest.raises(engine.EngineError) as ei:
+        engine.DeviceModel(ctx, five)
+    assert ei.value.code == engine.EINVAL
+    small.close(); big.close()
+
+
+def test_bad_symbol_in_device_buffer_mode_is_reported(ctx, golden_config1):
+    """ADVHMM_DEVICE_BUFFERS calls are asynchronous: a code outside the alphabet cannot fail the call, it
+    is reported by advhmm_context_bad_symbol() (the host path returns ADVHMM_ESYMBOL)."""
+    import ctypes as C
+    import torch
+    from advntr_b200 import engine
+    lib = engine.load_library()
+    dm = engine.DeviceModel(ctx, golden_config1.baked)
+    codes = [c.copy() for c in golden_config1.codes()[:5]]
+    handles = (C.c_void_p * 1)(dm._h)
+    goff = np.asarray([0, 5], dtype=np.int64)
+    d_logp = torch.empty(5, dtype=torch.float64, device="cuda")
+    for bad_read in (None, 3):
+        if bad_read is not None:
+            codes[bad_read][7] = 9
+        seqs, off = engine.pack_reads(codes)
+        d_seqs = torch.from_numpy(seqs).cuda()
+        torch.cuda.synchronize()
+        engine._check(lib.advhmm_viterbi_multi(ctx._h, handles, 1, goff.ctypes.data, d_seqs.data_ptr(),
+                                               off.ctypes.data, 5, engine.DEVICE_BUFFERS, d_logp.data_ptr(),
+                                               None, None, None, 0, None))
+        assert ctx.bad_symbol() == (-1 if bad_read is None else bad_read)
+    dm.close()
+
+
+@pytest.mark.parametrize("read_length", [100, 250])
+def test_locus_decoder_uses_read_length_flanks(ctx, read_length):
+    """get_vntr_matcher_hmm builds the matcher with flanking_region_size = read_length
+    (vntr_finder.py:131-132): LocusDecoder for a 100 / 250 bp library must decode against the model
+    with 100 / 250-base flanks.  Reference tables: read_matcher's literal builder (bit-equal to the
+    reference's hmm_utils, tests/test_builder_parity.py); decoding checked against the oracle."""
+    from advntr_b200 import locus_batch, read_matcher, synth
+    rng = random.Random(read_length)
+    ru = synth.rand_dna(rng, 21)
+    left, right = synth.rand_dna(rng, 400), synth.rand_dna(rng, 400)
+    segs = [synth.substitute(rng, ru, 0.03) for _ in range(4)]
+    dec = locus_batch.LocusDecoder(left, right, segs, read_length=read_length)
+    copies = read_matcher.copies_for_read_length(read_length, len(ru))
+    want = read_matcher.get_read_matcher_model(left[-read_length:], right[:read_length], segs, copies)
+    b, w = dec.model.baked, want.baked
+    assert b["n_states"] == w["n_states"] and np.array_equal(b["in_src"], w["in_src"])
+    assert same_bits(b["in_logp"], w["in_logp"]) and same_bits(b["emis"], w["emis"])
+    allele = left + "".join(segs) + right
+    reads = []
+    for _ in range(40):
+        s = rng.randrange(400 - read_length + 5, 400 + 84 - 5)
+        reads.append(synth.sequencing_errors(rng, allele[s:s + read_length + 8], 0.01, 0.001, 0.001)[:read_length])
+    reads += [synth.rand_dna(rng, read_length) for _ in range(6)]
+    lp, paths = oracle.OracleModel(w).viterbi([oracle.encode(r) for r in reads])
+    res = dec.model.viterbi_batch(reads)
+    assert same_bits(res.logp, lp)
+    assert_paths_equal([res.path(i) for i in range(len(res))], paths, "read length %d" % read_length)
+    # and the call site: the flank match-rate / recruitment decisions follow from those paths
+    selected = dec.select_reads(reads[:40])
+    assert len(selected) >= 30
