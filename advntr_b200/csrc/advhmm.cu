@@ -80,6 +80,25 @@ std::vector<double> forward_row0(const GenericTables& g)
 
 namespace {
 
+// the shared-memory image of a banded model (layout: kernels_banded.cuh)
+void pack_banded_image(const BandedTables& b, std::vector<unsigned char>& image)
+{
+    const size_t P = b.NCpad;
+    image.assign((size_t)kImgBytesPerCol * P, 0);
+    double* w10 = reinterpret_cast<double*>(image.data() + (size_t)kImgW * P);
+    double* e2 = reinterpret_cast<double*>(image.data() + (size_t)kImgE * P);
+    double* v12 = reinterpret_cast<double*>(image.data() + (size_t)kImgV1 * P);
+    for (size_t c = 0; c < P; ++c) {
+        for (int k = 0; k < 9; ++k) w10[c * 10 + k] = b.w[(size_t)k * P + c];
+        w10[c * 10 + 9] = b.accw[c];
+        for (int x = 0; x < 4; ++x)
+            for (int sl = 0; sl < 2; ++sl) {       // sl: 0 = I slot, 1 = M slot
+                e2[((size_t)x * P + c) * 2 + sl] = b.e[((size_t)sl * 4 + x) * P + c];
+                v12[((size_t)x * P + c) * 2 + sl] = b.v1[((size_t)sl * 4 + x) * P + c];
+            }
+    }
+}
+
 int upload_model(advhmm_model* mod)
 {
     advhmm_context* ctx = mod->ctx;
@@ -98,19 +117,8 @@ int upload_model(advhmm_model* mod)
     int image_bytes = 0, image_f_bytes = 0;
     if (b.valid) {
         const size_t P = b.NCpad;
-        std::vector<unsigned char> image((size_t)kImgBytesPerCol * P, 0);
-        double* w10 = reinterpret_cast<double*>(image.data() + (size_t)kImgW * P);
-        double* e2 = reinterpret_cast<double*>(image.data() + (size_t)kImgE * P);
-        double* v12 = reinterpret_cast<double*>(image.data() + (size_t)kImgV1 * P);
-        for (size_t c = 0; c < P; ++c) {
-            for (int k = 0; k < 9; ++k) w10[c * 10 + k] = b.w[(size_t)k * P + c];
-            w10[c * 10 + 9] = b.accw[c];
-            for (int x = 0; x < 4; ++x)
-                for (int sl = 0; sl < 2; ++sl) {       // sl: 0 = I slot, 1 = M slot
-                    e2[((size_t)x * P + c) * 2 + sl] = b.e[((size_t)sl * 4 + x) * P + c];
-                    v12[((size_t)x * P + c) * 2 + sl] = b.v1[((size_t)sl * 4 + x) * P + c];
-                }
-        }
+        std::vector<unsigned char> image;
+        pack_banded_image(b, image);
         image_bytes = (int)image.size();
         o_image = bb.add(image);
         // forward first-row table: emitting states of row 1 from the forward row 0 (hmm.pyx:1427-1444)
@@ -150,6 +158,7 @@ int upload_model(advhmm_model* mod)
     const size_t o_dgf = bb.add(nullptr, sizeof(DevGeneric));
     const size_t o_db = bb.add(nullptr, sizeof(DevBanded));
 
+    mod->K = g.K; mod->m = g.m; mod->NCpad = b.valid ? b.NCpad : 0;
     mod->info.kind = ADVHMM_KIND_GENERIC;
     mod->info.n_states = g.m;
     mod->info.n_edges = g.in_off[g.m];
@@ -210,6 +219,279 @@ int upload_model(advhmm_model* mod)
     mod->d_generic = reinterpret_cast<DevGeneric*>(P8(o_dg));
     mod->d_generic_fwd = reinterpret_cast<DevGeneric*>(P8(o_dgf));
     mod->d_banded = b.valid ? reinterpret_cast<DevBanded*>(P8(o_db)) : nullptr;
+    return ADVHMM_OK;
+}
+
+// =============================================================================================
+// locus models: many read-matcher models per call, compiled natively (locus_compile.hpp)
+// =============================================================================================
+static_assert(rm::kImageBytesPerCol == kImgBytesPerCol && rm::kImageE == kImgE && rm::kImageV1 == kImgV1,
+              "locus_compile.hpp and kernels_banded.cuh must agree on the image layout");
+
+rm::VexpFn g_vexp = nullptr;
+void* g_vexp_user = nullptr;
+
+// A locus model that is asked for something outside the banded Viterbi path (generic kernel, forward,
+// fp32) gets the full set of tables of a descriptor-made model: same arrays, same analysis.
+int ensure_full_model(advhmm_model* mod)
+{
+    if (!mod->lean) return ADVHMM_OK;
+    const rm::ShapeStructure& sh = *mod->locus.shape;
+    std::vector<double> in_logp, emis;
+    rm::baked_values(mod->locus, in_logp, emis);
+    advhmm_model_desc d{};
+    d.n_states = sh.m; d.silent_start = sh.S; d.start_index = sh.start; d.end_index = sh.end;
+    d.finite = sh.finite; d.n_symbols = 4;
+    d.in_off = sh.in_off.data(); d.in_src = sh.in_src.data(); d.in_logp = in_logp.data(); d.emis = emis.data();
+    std::string err;
+    if (!compile_model(d, mod->cm, err)) return set_error(ADVHMM_EINVAL, "%s", err.c_str());
+    if (int rc = upload_model(mod)) return rc;
+    mod->lean = false;
+    if (mod->ctx->device >= 0) {
+        std::vector<uint8_t> cls((size_t)sh.m);
+        for (int i = 0; i < sh.m; ++i) {
+            uint8_t c = sh.base_class[i];
+            if (i < sh.S && sh.emis_row[i] < 0) c |= (uint8_t)(mod->locus.flank[(size_t)(-sh.emis_row[i] - 1)] << 5);
+            cls[i] = c;
+        }
+        CU_TRY(cudaMemcpyAsync(mod->d_classes, cls.data(), cls.size(), cudaMemcpyHostToDevice, mod->ctx->stream));
+        CU_TRY(cudaStreamSynchronize(mod->ctx->stream));
+    }
+    return ADVHMM_OK;
+}
+
+int ensure_shape_on_device(advhmm_context* ctx, const rm::ShapeStructure* sh, DevShape** out)
+{
+    auto it = ctx->shape_dev.find(sh);
+    if (it != ctx->shape_dev.end()) { *out = it->second.get(); return ADVHMM_OK; }
+    const BandedTables& b = sh->cm.b;
+    BlobBuilder bb;
+    std::vector<int32_t> st(3 * (size_t)b.NC);
+    for (int t = 0; t < 3; ++t) memcpy(st.data() + (size_t)t * b.NC, b.st[t].data(), sizeof(int32_t) * b.NC);
+    const size_t o_st = bb.add(st), o_acc = bb.add(b.acc_src_col), o_fs = bb.add(b.fin_state);
+    const size_t o_fo = bb.add(b.fin_off), o_fsrc = bb.add(b.fin_src);
+    std::unique_ptr<DevShape> ds(new DevShape);
+    CU_TRY(ds->blob.ensure(bb.bytes.size() + 256));
+    unsigned char* base = ds->blob.as<unsigned char>();
+    CU_TRY(cudaMemcpyAsync(base, bb.bytes.data(), bb.bytes.size(), cudaMemcpyHostToDevice, ctx->upload_stream));
+    CU_TRY(cudaStreamSynchronize(ctx->upload_stream));
+    ds->st = (const int32_t*)(base + o_st); ds->acc_src_col = (const int32_t*)(base + o_acc);
+    ds->fin_state = (const int32_t*)(base + o_fs); ds->fin_off = (const int32_t*)(base + o_fo);
+    ds->fin_src = (const int32_t*)(base + o_fsrc);
+    *out = ds.get();
+    ctx->shape_dev[sh] = std::move(ds);
+    return ADVHMM_OK;
+}
+
+void lean_model_info(advhmm_model* mod, size_t smem_limit)
+{
+    const rm::ShapeStructure& sh = *mod->locus.shape;
+    const BandedTables& b = sh.cm.b;
+    mod->K = 4; mod->m = sh.m; mod->NCpad = b.NCpad;
+    mod->info.kind = ADVHMM_KIND_BANDED;
+    mod->info.n_states = sh.m;
+    mod->info.n_edges = sh.cm.g.in_off[sh.m];
+    mod->info.n_columns = b.NC;
+    mod->info.n_final_states = (int)b.fin_state.size();
+    mod->info.smem_bytes = sh.image_bytes;
+    mod->info.max_in_degree = sh.cm.g.max_in_degree;
+    mod->banded_smem = ((size_t)sh.image_bytes + 4096 <= smem_limit) ? sh.image_bytes : 0;
+}
+
+int create_models_for_loci(advhmm_context* ctx, const advhmm_loci* L, int n_threads, advhmm_model** out)
+{
+    const int N = L->n_loci;
+    const int nt = n_threads > 0 ? n_threads : rm::default_threads();
+    for (int i = 0; i < N; ++i) out[i] = nullptr;
+    static const bool dbg = getenv("ADVHMM_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = now();
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        const double t = now();
+        fprintf(stderr, "[advhmm] create_for_loci: %-28s %8.2f ms\n", what, t - t_mark);
+        t_mark = t;
+    };
+    // ---- 1. per locus, in parallel: repeat-unit profile, emission logs, shape key ---------------
+    std::vector<rm::LocusPrep> prep((size_t)N);
+    rm::parallel_for((size_t)N, nt, [&](size_t i, int) {
+        rm::LocusInput in;
+        in.left = L->left + L->left_off[i];   in.left_len = (int)(L->left_off[i + 1] - L->left_off[i]);
+        in.right = L->right + L->right_off[i]; in.right_len = (int)(L->right_off[i + 1] - L->right_off[i]);
+        in.aln = L->segments + L->seg_off[i];
+        in.n_seq = L->n_segments[i];
+        const int64_t chars = L->seg_off[i + 1] - L->seg_off[i];
+        in.width = in.n_seq > 0 ? (int)(chars / in.n_seq) : 0;
+        in.copies = L->copies[i];
+        in.error_rate = L->error_rate[i];
+        if (in.n_seq < 1 || (int64_t)in.width * in.n_seq != chars) {
+            prep[i].err = "the aligned repeat segments of a locus must have one width";
+            return;
+        }
+        rm::prepare_locus(in, prep[i]);
+    });
+    for (int i = 0; i < N; ++i)
+        if (!prep[i].ok) return set_error(ADVHMM_EINVAL, "locus %d: %s", i, prep[i].err.c_str());
+    lap("profiles");
+    // ---- 2. shapes: the distinct ones are built (or found in the cache) in parallel ----------------
+    std::map<rm::ShapeKey, std::shared_ptr<const rm::ShapeStructure>> shapes;
+    for (int i = 0; i < N; ++i) shapes.emplace(prep[i].key, nullptr);
+    {
+        std::vector<rm::ShapeKey> keys;
+        for (auto& kv : shapes) keys.push_back(kv.first);
+        std::vector<std::shared_ptr<const rm::ShapeStructure>> built(keys.size());
+        std::vector<std::string> errs(keys.size());
+        rm::parallel_for(keys.size(), nt, [&](size_t k, int) { built[k] = rm::get_shape(keys[k], errs[k]); });
+        for (size_t k = 0; k < keys.size(); ++k) {
+            if (!built[k]) return set_error(ADVHMM_EINVAL, "shape (%d, %d, %d, %d): %s", keys[k].Ll, keys[k].Lr, keys[k].R,
+                                            keys[k].C, errs[k].c_str());
+            shapes[keys[k]] = built[k];
+        }
+    }
+    lap("shapes");
+    // ---- 3. parameter chains: distinct (probability, chain) items per locus, two vector exps in all ----
+    std::vector<std::vector<rm::ChainBatch::Item>> items((size_t)N);
+    std::vector<std::vector<int32_t>> slot_item((size_t)N);
+    std::atomic<int> bad{-1};
+    rm::parallel_for((size_t)N, nt, [&](size_t i, int) {
+        const rm::ShapeStructure& sh = *shapes[prep[i].key];
+        const double to_end = 0.7 / (sh.key.C * sh.key.R);
+        const double total = 1 + to_end;
+        auto& its = items[i];
+        auto& si = slot_item[i];
+        si.resize(sh.slots.size());
+        for (size_t s = 0; s < sh.slots.size(); ++s) {
+            const rm::Lab& l = sh.slots[s];
+            const double p = rm::slot_probability(l, sh.key, prep[i].error_rate, prep[i].prof);
+            if (!(p > 0)) { bad.store((int)i); return; }
+            size_t j = 0;
+            for (; j < its.size(); ++j)
+                if (its[j].p == p && its[j].trips == l.trips && its[j].div == l.div) break;
+            if (j == its.size()) its.push_back(rm::ChainBatch::Item{p, l.trips, l.div, total, 0.0});
+            si[s] = (int32_t)j;
+        }
+    });
+    if (bad.load() >= 0)
+        return set_error(ADVHMM_EUNSUPPORTED, "locus %d has a zero-probability transition: its structure differs from its "
+                                              "shape's, build it through advhmm_model_create", bad.load());
+    lap("chain items");
+    rm::ChainBatch chain;
+    std::vector<size_t> first((size_t)N + 1, 0);
+    for (int i = 0; i < N; ++i) first[i + 1] = first[i] + items[i].size();
+    chain.items.reserve(first[N]);
+    for (int i = 0; i < N; ++i) chain.items.insert(chain.items.end(), items[i].begin(), items[i].end());
+    chain.run(g_vexp, g_vexp_user);
+    lap("chains (log / exp)");
+    // ---- 4. handles --------------------------------------------------------------------------------
+    std::vector<std::unique_ptr<advhmm_model>> mods((size_t)N);
+    const size_t smem_limit = ctx->device >= 0 ? ctx->smem_optin : (size_t)232448;
+    rm::parallel_for((size_t)N, nt, [&](size_t i, int) {
+        std::unique_ptr<advhmm_model> mod(new advhmm_model);
+        mod->ctx = ctx;
+        mod->lean = true;
+        mod->locus.shape = shapes[prep[i].key];
+        mod->locus.slot_log.resize(slot_item[i].size());
+        for (size_t s = 0; s < slot_item[i].size(); ++s) mod->locus.slot_log[s] = chain.items[first[i] + slot_item[i][s]].out;
+        mod->locus.emis_tab = std::move(prep[i].emis_tab);
+        mod->locus.flank = std::move(prep[i].flank);
+        lean_model_info(mod.get(), smem_limit);
+        mods[i] = std::move(mod);
+    });
+    lap("handles");
+    // shapes the banded kernel cannot run (none of the read-matcher family so far): full models
+    for (int i = 0; i < N; ++i)
+        if (!mods[i]->locus.shape->banded)
+            if (int rc = ensure_full_model(mods[i].get())) return rc;
+    if (ctx->device >= 0) {
+        // ---- 5. device: one arena for the batch, tables written by all threads into pinned staging
+        //         chunks, one H2D copy per chunk (double-buffered) ----------------------------------
+        CU_TRY(cudaSetDevice(ctx->device));
+        if (!ctx->upload_stream) {
+            CU_TRY(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&ctx->upload_done, cudaEventDisableTiming));
+            // keep freed arenas in the pool: the next batch takes the same memory without a trip to the driver
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        }
+        std::vector<rm::LeanLayout> lay((size_t)N);
+        std::vector<size_t> off((size_t)N + 1, 0);
+        std::vector<DevShape*> dshape((size_t)N, nullptr);
+        for (int i = 0; i < N; ++i) {
+            if (!mods[i]->lean) { off[i + 1] = off[i]; continue; }
+            lay[i] = rm::lean_layout(*mods[i]->locus.shape, sizeof(DevBanded));
+            off[i + 1] = off[i] + lay[i].bytes;
+            if (int rc = ensure_shape_on_device(ctx, mods[i]->locus.shape.get(), &dshape[i])) return rc;
+        }
+        auto arena = std::make_shared<DeviceArena>();
+        arena->device = ctx->device;
+        arena->bytes = off[N];
+        arena->free_stream = ctx->stream;
+        arena->ctx_alive = ctx->alive;
+        if (arena->bytes) CU_TRY(cudaMallocAsync(&arena->p, arena->bytes, ctx->upload_stream));
+        unsigned char* dbase = static_cast<unsigned char*>(arena->p);
+        size_t stage_bytes = (size_t)64 << 20;
+        for (int i = 0; i < N; ++i) stage_bytes = std::max(stage_bytes, lay[i].bytes);
+        for (int k = 0; k < 2; ++k) {
+            CU_TRY(ctx->h_stage[k].ensure(stage_bytes));
+            if (!ctx->stage_done[k]) CU_TRY(cudaEventCreateWithFlags(&ctx->stage_done[k], cudaEventDisableTiming));
+        }
+        std::vector<rm::LeanScratch> scratch((size_t)nt);
+        int chunk = 0;
+        for (int lo = 0; lo < N;) {
+            int hi = lo;
+            while (hi < N && off[hi + 1] - off[lo] <= stage_bytes) ++hi;
+            if (hi == lo) ++hi;
+            const int k = chunk & 1;
+            CU_TRY(cudaEventSynchronize(ctx->stage_done[k]));           // the copy that last read this buffer
+            unsigned char* hbase = static_cast<unsigned char*>(ctx->h_stage[k].p);
+            rm::parallel_for((size_t)(hi - lo), nt, [&](size_t j, int worker) {
+                const int i = lo + (int)j;
+                advhmm_model* mod = mods[i].get();
+                if (!mod->lean) return;
+                const rm::ShapeStructure& sh = *mod->locus.shape;
+                const BandedTables& b = sh.cm.b;
+                const rm::LeanLayout& ly = lay[i];
+                unsigned char* h = hbase + (off[i] - off[lo]);
+                unsigned char* dv = dbase + off[i];
+                memset(h + ly.o_tb1, 0, ly.o_tb0 - ly.o_tb1);            // (alignment padding stays defined)
+                const double logp_empty = rm::fill_lean(mod->locus, scratch[worker], h + ly.o_image,
+                                                        reinterpret_cast<int32_t*>(h + ly.o_tb1),
+                                                        reinterpret_cast<int32_t*>(h + ly.o_tb0),
+                                                        reinterpret_cast<double*>(h + ly.o_finw), h + ly.o_cls);
+                DevBanded db{};
+                db.NC = b.NC; db.P = b.NCpad; db.S = b.S; db.m = sh.m; db.NF = (int)b.fin_state.size();
+                db.end_final = b.end_final; db.acc_col = b.acc_col; db.n_acc = (int)b.acc_src_col.size();
+                db.start = sh.start; db.end = sh.end; db.image_bytes = sh.image_bytes;
+                db.logp_empty = logp_empty;
+                db.image = dv + ly.o_image;
+                db.st = dshape[i]->st; db.acc_src_col = dshape[i]->acc_src_col;
+                db.fin_state = dshape[i]->fin_state; db.fin_off = dshape[i]->fin_off; db.fin_src = dshape[i]->fin_src;
+                db.tb1 = reinterpret_cast<const int32_t*>(dv + ly.o_tb1);
+                db.tb0 = reinterpret_cast<const int32_t*>(dv + ly.o_tb0);
+                db.fin_w = reinterpret_cast<const double*>(dv + ly.o_finw);
+                db.classes = dv + ly.o_cls;
+                memcpy(h + ly.o_desc, &db, sizeof db);
+                mod->d_banded = reinterpret_cast<DevBanded*>(dv + ly.o_desc);
+                mod->d_classes = dv + ly.o_cls;
+                mod->arena = arena;
+            });
+            if (off[hi] > off[lo])
+                CU_TRY(cudaMemcpyAsync(dbase + off[lo], hbase, off[hi] - off[lo], cudaMemcpyHostToDevice, ctx->upload_stream));
+            CU_TRY(cudaEventRecord(ctx->stage_done[k], ctx->upload_stream));
+            lo = hi;
+            ++chunk;
+        }
+        // whatever is queued on the compute stream from here on sees the tables; the compute stream itself
+        // is NOT waited for: a batch that is being decoded keeps running while this one is compiled
+        CU_TRY(cudaEventRecord(ctx->upload_done, ctx->upload_stream));
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->upload_done, 0));
+        CU_TRY(cudaStreamSynchronize(ctx->upload_stream));
+        lap("tables + upload");
+    }
+    for (int i = 0; i < N; ++i) out[i] = mods[i].release();
     return ADVHMM_OK;
 }
 
@@ -419,9 +701,13 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         advhmm_model* mod = models[gi];
         if (!mod || mod->ctx != ctx) return set_error(ADVHMM_EINVAL, "model %d does not belong to this context", gi);
         // reads are packed 2 bits per symbol and validated against ONE alphabet size per call
-        if (mod->cm.g.K != models[0]->cm.g.K)
+        if (mod->K != models[0]->K)
             return set_error(ADVHMM_EINVAL, "model %d has %d symbols, model 0 has %d: one alphabet per call", gi,
-                             mod->cm.g.K, models[0]->cm.g.K);
+                             mod->K, models[0]->K);
+        // a locus model carries the banded Viterbi tables only: the generic kernel, forward and the
+        // fp32 twin need the full set, built on first use
+        if (mod->lean && (forward || (flags & (ADVHMM_FORCE_GENERIC | ADVHMM_FP32))))
+            if (int rc = ensure_full_model(mod)) return rc;
         const int64_t r0 = group_off[gi], r1 = group_off[gi + 1];
         if (r0 < 0 || r1 < r0 || r1 > n_reads) return set_error(ADVHMM_EINVAL, "bad group_off at model %d", gi);
         const bool banded = mod->d_banded && !(flags & ADVHMM_FORCE_GENERIC);
@@ -431,14 +717,14 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
             if (banded) {
                 if (mod->banded_smem > 0 && len <= (forward ? 32 * kMaxRPL : ctx->short_max_len)) {
                     f = &fam_short;
-                    pl.max_P_short = std::max(pl.max_P_short, mod->cm.b.NCpad);
+                    pl.max_P_short = std::max(pl.max_P_short, mod->NCpad);
                     pl.max_smem_short = std::max(pl.max_smem_short, mod->banded_smem);
                 } else if (!forward) {
                     f = &fam_long;
-                    pl.max_P_long = std::max(pl.max_P_long, mod->cm.b.NCpad);
+                    pl.max_P_long = std::max(pl.max_P_long, mod->NCpad);
                 }                                   // forward of long reads: generic kernel
             }
-            if (f == &fam_generic) pl.max_m_generic = std::max(pl.max_m_generic, mod->cm.g.m);
+            if (f == &fam_generic) pl.max_m_generic = std::max(pl.max_m_generic, mod->m);
             f->max_len = std::max(f->max_len, len);
             for (int s = 0; s < strands; ++s) {
                 f->items.push_back((int32_t)(r * strands + s));
@@ -534,7 +820,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     int32_t* d_rlen = reinterpret_cast<int32_t*>(d_pk + pk_words_al);
     {
         PackArgs pa{d_seqs, d_seq_off, d_pk_off, d_pk, d_rlen, d_bad, n_out, strands, 0, read_base};
-        pa.n_symbols = models[0]->cm.g.K;
+        pa.n_symbols = models[0]->K;
         pack_reads_kernel<<<n_out, 32, 0, ctx->stream>>>(pa);
         CU_TRY(cudaGetLastError());
         ctx->launches++;
@@ -729,6 +1015,12 @@ int run_host(advhmm_context* ctx, advhmm_model* const* models, int n_models, con
     if (n_out == 0) return ADVHMM_OK;
     const int64_t n_bases = seq_off[n_reads];
     if (seq_off[0] != 0 || n_bases < 0) return set_error(ADVHMM_EINVAL, "seq_off must start at 0 and be non-decreasing");
+    // (run_batch checks the same, but it sees the sub-batches below with re-based offsets)
+    if (!group_off || group_off[0] != 0 || group_off[n_models] != n_reads)
+        return set_error(ADVHMM_EINVAL, "group_off must start at 0 and end at n_reads: reads outside every group "
+                                        "would not be decoded");
+    for (int g = 0; g < n_models; ++g)
+        if (group_off[g + 1] < group_off[g]) return set_error(ADVHMM_EINVAL, "group_off must be non-decreasing (model %d)", g);
     if (n_bases > 0 && !seqs) return set_error(ADVHMM_EINVAL, "seqs is null");
 
     CU_TRY(ctx->d_seqs.ensure((size_t)n_bases + 16));
@@ -1160,6 +1452,14 @@ void advhmm_context_destroy(advhmm_context* ctx)
         cudaStreamSynchronize(ctx->stream);
         for (DevBuf* b : {&ctx->d_seqs, &ctx->d_seq_off, &ctx->d_pk, &ctx->d_meta, &ctx->d_work, &ctx->d_out, &ctx->d_paths, &ctx->d_flags, &ctx->d_badflag}) b->release();
         ctx->h_meta.release(); ctx->h_out.release(); ctx->h_cursors.release();
+        for (int k = 0; k < 2; ++k) {
+            ctx->h_stage[k].release();
+            if (ctx->stage_done[k]) cudaEventDestroy(ctx->stage_done[k]);
+        }
+        for (auto& kv : ctx->shape_dev) kv.second->blob.release();
+        ctx->alive->store(false);
+        if (ctx->upload_stream) { cudaStreamSynchronize(ctx->upload_stream); cudaStreamDestroy(ctx->upload_stream); }
+        if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
         for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
         for (cudaEvent_t ev : ctx->h2d_events) cudaEventDestroy(ev);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1257,12 +1557,108 @@ int advhmm_model_create(advhmm_context* ctx, const advhmm_model_desc* desc, advh
 void advhmm_model_destroy(advhmm_model* model)
 {
     if (!model) return;
-    if (model->ctx && model->ctx->device >= 0) {
+    if (model->ctx && model->ctx->device >= 0 && model->blob.p) {
         cudaSetDevice(model->ctx->device);
         cudaStreamSynchronize(model->ctx->stream);
         model->blob.release();
     }
+    // (a locus model's tables live in its batch's arena, freed in stream order behind the kernels that read them)
     delete model;
+}
+
+void advhmm_shape_cache_clear(void) { rm::clear_shape_cache(); }
+
+int advhmm_set_vexp(advhmm_vexp_fn fn, void* user)
+{
+    g_vexp = fn;
+    g_vexp_user = user;
+    return ADVHMM_OK;
+}
+
+int advhmm_models_create_for_loci(advhmm_context* ctx, const advhmm_loci* loci, int32_t n_threads, advhmm_model** out)
+{
+    if (!ctx || !loci || !out || loci->n_loci < 0) return set_error(ADVHMM_EINVAL, "null argument");
+    if (loci->n_loci == 0) return ADVHMM_OK;
+    if (!loci->left || !loci->left_off || !loci->right || !loci->right_off || !loci->segments || !loci->seg_off ||
+        !loci->n_segments || !loci->copies || !loci->error_rate)
+        return set_error(ADVHMM_EINVAL, "advhmm_loci has a null column");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        int rc = create_models_for_loci(ctx, loci, n_threads, out);
+        if (rc != ADVHMM_OK)
+            for (int i = 0; i < loci->n_loci; ++i) out[i] = nullptr;
+        return rc;
+    } catch (const std::bad_alloc&) {
+        return set_error(ADVHMM_ENOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        return set_error(ADVHMM_EINVAL, "%s", e.what());
+    }
+}
+
+int advhmm_model_dims_get(const advhmm_model* model, advhmm_model_dims* out)
+{
+    if (!model || !out) return set_error(ADVHMM_EINVAL, "null argument");
+    if (!model->locus.shape) return set_error(ADVHMM_EUNSUPPORTED, "only models made by advhmm_models_create_for_loci keep their tables");
+    const rm::ShapeStructure& sh = *model->locus.shape;
+    out->n_states = sh.m; out->silent_start = sh.S; out->start_index = sh.start; out->end_index = sh.end;
+    out->finite = sh.finite; out->n_symbols = 4;
+    out->n_edges = (int64_t)sh.in_src.size();
+    int64_t chars = 0;
+    for (const rm::Node& n : sh.states) chars += (int64_t)n.name.size() + 1;
+    out->names_bytes = chars;
+    out->shape[0] = sh.key.Ll; out->shape[1] = sh.key.Lr; out->shape[2] = sh.key.R; out->shape[3] = sh.key.C;
+    return ADVHMM_OK;
+}
+
+int advhmm_model_tables_get(const advhmm_model* model, int32_t* in_off, int32_t* in_src, double* in_logp, double* emis,
+                            char* names)
+{
+    if (!model) return set_error(ADVHMM_EINVAL, "null argument");
+    if (!model->locus.shape) return set_error(ADVHMM_EUNSUPPORTED, "only models made by advhmm_models_create_for_loci keep their tables");
+    const rm::ShapeStructure& sh = *model->locus.shape;
+    if (in_off) memcpy(in_off, sh.in_off.data(), sh.in_off.size() * sizeof(int32_t));
+    if (in_src) memcpy(in_src, sh.in_src.data(), sh.in_src.size() * sizeof(int32_t));
+    if (in_logp || emis) {
+        std::vector<double> w, e;
+        rm::baked_values(model->locus, w, e);
+        if (in_logp) memcpy(in_logp, w.data(), w.size() * sizeof(double));
+        if (emis) memcpy(emis, e.data(), e.size() * sizeof(double));
+    }
+    if (names) {
+        char* p = names;
+        for (const rm::Node& n : sh.states) { memcpy(p, n.name.data(), n.name.size()); p += n.name.size(); *p++ = '\n'; }
+    }
+    return ADVHMM_OK;
+}
+
+int advhmm_model_banded_tables_get(advhmm_model* model, unsigned char* image, int64_t image_cap, int32_t* tb1, int32_t* tb0,
+                                   double* fin_w, uint8_t* classes, double* logp_empty, int64_t* image_bytes)
+{
+    if (!model || !image_bytes) return set_error(ADVHMM_EINVAL, "null argument");
+    if (model->lean) {
+        const rm::ShapeStructure& sh = *model->locus.shape;
+        *image_bytes = sh.image_bytes;
+        if (!image) return ADVHMM_OK;
+        if (image_cap < sh.image_bytes) return set_error(ADVHMM_ECAPACITY, "image buffer too small");
+        rm::LeanScratch sc;
+        const double e = rm::fill_lean(model->locus, sc, image, tb1, tb0, fin_w, classes);
+        if (logp_empty) *logp_empty = e;
+        return ADVHMM_OK;
+    }
+    const BandedTables& b = model->cm.b;
+    if (!b.valid) return set_error(ADVHMM_EUNSUPPORTED, "not a banded model");
+    std::vector<unsigned char> img;
+    pack_banded_image(b, img);
+    *image_bytes = (int64_t)img.size();
+    if (!image) return ADVHMM_OK;
+    if (image_cap < (int64_t)img.size()) return set_error(ADVHMM_ECAPACITY, "image buffer too small");
+    memcpy(image, img.data(), img.size());
+    if (tb1) memcpy(tb1, b.tb1.data(), b.tb1.size() * sizeof(int32_t));
+    if (tb0) memcpy(tb0, model->cm.g.tb0.data(), model->cm.g.tb0.size() * sizeof(int32_t));
+    if (fin_w) memcpy(fin_w, b.fin_w.data(), b.fin_w.size() * sizeof(double));
+    if (classes) memset(classes, 0, (size_t)model->cm.g.m);
+    if (logp_empty) *logp_empty = model->cm.g.v0[model->cm.g.end];
+    return ADVHMM_OK;
 }
 
 int advhmm_model_info_get(const advhmm_model* model, advhmm_model_info* out)
@@ -1310,7 +1706,7 @@ int advhmm_model_set_state_classes(advhmm_model* model, const uint8_t* classes)
     if (!model->ctx || model->ctx->device < 0) return ADVHMM_OK;      // host-only context: nothing to upload
     std::lock_guard<std::mutex> lock(model->ctx->mu);
     CU_TRY(cudaSetDevice(model->ctx->device));
-    CU_TRY(cudaMemcpyAsync(model->d_classes, classes, (size_t)model->cm.g.m, cudaMemcpyHostToDevice, model->ctx->stream));
+    CU_TRY(cudaMemcpyAsync(model->d_classes, classes, (size_t)model->m, cudaMemcpyHostToDevice, model->ctx->stream));
     CU_TRY(cudaStreamSynchronize(model->ctx->stream));
     return ADVHMM_OK;
 }

@@ -13,7 +13,7 @@
 #include <utility>
 #include <vector>
 
-#include "model_compile.hpp"
+#include "locus_compile.hpp"
 
 using namespace advhmm;
 
@@ -132,6 +132,36 @@ constexpr int kGenericWarpsMax = 8;
 
 }  // namespace
 
+// one device allocation holding the tables of every model of a batch (advhmm_models_create_for_loci);
+// freed when the last model of the batch is destroyed
+// Allocated and freed with the stream-ordered allocator: the free is queued on the context's compute
+// stream behind the last kernel that read the tables, so destroying the models of one batch neither
+// waits for the device nor stalls the batch that is being decoded (cudaFree would do both).
+struct DeviceArena {
+    int device = -1;
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t free_stream = nullptr;                    // the owning context's compute stream
+    std::shared_ptr<std::atomic<bool>> ctx_alive;          // false once that context (and stream) is gone
+    ~DeviceArena()
+    {
+        if (!p) return;
+        cudaSetDevice(device);
+        if (ctx_alive && ctx_alive->load()) cudaFreeAsync(p, free_stream);
+        else cudaFree(p);
+    }
+};
+
+// structural device tables of a shape, shared by every locus model of that shape on a context
+struct DevShape {
+    DevBuf blob;
+    const int32_t* st = nullptr;
+    const int32_t* acc_src_col = nullptr;
+    const int32_t* fin_state = nullptr;
+    const int32_t* fin_off = nullptr;
+    const int32_t* fin_src = nullptr;
+};
+
 struct advhmm_context {
     int device = -1;             // < 0: host-only context (model analysis without a GPU)
     cudaStream_t stream = nullptr;
@@ -157,6 +187,13 @@ struct advhmm_context {
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];   // [0] banded fill, [1] backtrack
     size_t prof_used[2] = {0, 0};
+    // locus models: per-shape structural tables on this device, pinned staging for batched uploads
+    std::map<const rm::ShapeStructure*, std::unique_ptr<DevShape>> shape_dev;
+    PinnedBuf h_stage[2];
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    cudaStream_t upload_stream = nullptr;    // model tables travel here, next to the decoding of the previous batch
+    cudaEvent_t upload_done = nullptr;
+    std::shared_ptr<std::atomic<bool>> alive = std::make_shared<std::atomic<bool>>(true);
     int banded_warps = 8;        // reads per CTA of the banded kernel
     int short_max_len = 32 * kMaxRPL;   // longer reads take the striped long-read kernel (ADVHMM_SHORT_MAX_LEN)
     std::mutex mu;
@@ -164,7 +201,13 @@ struct advhmm_context {
 
 struct advhmm_model {
     advhmm_context* ctx = nullptr;
-    CompiledModel cm;
+    int K = 4, m = 0, NCpad = 0; // alphabet size, states, padded columns (0: not banded)
+    CompiledModel cm;            // graph analysis of THIS model (models made from a descriptor; locus
+                                 // models share their shape's analysis and fill this only on demand)
+    // locus models (advhmm_models_create_for_loci): the shape + the few KB of numbers of the locus
+    rm::LocusValues locus;
+    bool lean = false;           // device tables = the banded kernel's only (image, first-row tables, row 0)
+    std::shared_ptr<DeviceArena> arena;
     DevBuf blob;                 // all device tables of this model
     DevGeneric* d_generic = nullptr;
     DevGeneric* d_generic_fwd = nullptr;   // same tables, row 0 closed with pair_lse (forward)

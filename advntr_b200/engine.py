@@ -29,6 +29,8 @@ EXPORTS = (
     "advhmm_viterbi_multi_summary", "advhmm_model_set_state_classes",
     "advhmm_kfilter_create", "advhmm_kfilter_destroy", "advhmm_kfilter_scan",
     "advhmm_last_error", "advhmm_abi_version", "advhmm_encode_acgt",
+    "advhmm_set_vexp", "advhmm_models_create_for_loci", "advhmm_shape_cache_clear",
+    "advhmm_model_dims_get", "advhmm_model_tables_get", "advhmm_model_banded_tables_get",
 )
 
 
@@ -50,6 +52,33 @@ class ModelInfo(C.Structure):
                 ("n_columns", C.c_int32), ("n_final_states", C.c_int32), ("smem_bytes", C.c_int32),
                 ("max_in_degree", C.c_int32), ("reserved", C.c_int32)]
 
+
+class LociDesc(C.Structure):
+    """``advhmm_loci``: the columns of a batch of loci (include/advhmm.h)."""
+    _fields_ = [("n_loci", C.c_int32),
+                ("left", C.c_void_p), ("left_off", C.c_void_p),
+                ("right", C.c_void_p), ("right_off", C.c_void_p),
+                ("segments", C.c_void_p), ("seg_off", C.c_void_p),
+                ("n_segments", C.c_void_p), ("copies", C.c_void_p), ("error_rate", C.c_void_p)]
+
+
+class ModelDims(C.Structure):
+    _fields_ = [("n_states", C.c_int32), ("silent_start", C.c_int32), ("start_index", C.c_int32),
+                ("end_index", C.c_int32), ("finite", C.c_int32), ("n_symbols", C.c_int32),
+                ("n_edges", C.c_int64), ("names_bytes", C.c_int64), ("shape", C.c_int32 * 4)]
+
+
+VEXP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+def _numpy_vexp(inp, out, n, user):
+    """The vector exp of the reference: ``numpy.exp`` (``hmm.pyx:514``), on the library's buffers."""
+    a = np.frombuffer((C.c_double * n).from_address(inp), dtype=np.float64)
+    b = np.frombuffer((C.c_double * n).from_address(out), dtype=np.float64)
+    np.exp(a, out=b)
+
+
+_vexp_keepalive = VEXP_FN(_numpy_vexp)
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -95,6 +124,14 @@ def load_library():
         lib.advhmm_abi_version.restype = C.c_int
         lib.advhmm_encode_acgt.argtypes = [C.c_char_p, i64, vp]
         lib.advhmm_encode_acgt.restype = i64
+        lib.advhmm_set_vexp.argtypes = [VEXP_FN, vp]
+        lib.advhmm_models_create_for_loci.argtypes = [vp, C.POINTER(LociDesc), i32, vp]
+        lib.advhmm_shape_cache_clear.restype = None
+        lib.advhmm_model_dims_get.argtypes = [vp, C.POINTER(ModelDims)]
+        lib.advhmm_model_tables_get.argtypes = [vp, vp, vp, vp, vp, vp]
+        lib.advhmm_model_banded_tables_get.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp]
+        # parameter chains go through numpy.exp, as the reference's do (the library's default is libm)
+        lib.advhmm_set_vexp(_vexp_keepalive, None)
         _lib = lib
         return lib
 
@@ -137,6 +174,58 @@ def pack_reads(codes):
     for c, a, b in zip(codes, off[:-1], off[1:]):
         flat[a:b] = c
     return flat, off
+
+
+class LociColumns(object):
+    """Host arrays behind one ``advhmm_loci``: flank codes, aligned repeat segments, copies, error rates."""
+
+    def __init__(self, left, left_off, right, right_off, segments, seg_off, n_segments, copies, error_rate):
+        self.left = np.ascontiguousarray(left, dtype=np.uint8)
+        self.right = np.ascontiguousarray(right, dtype=np.uint8)
+        self.left_off = np.ascontiguousarray(left_off, dtype=np.int64)
+        self.right_off = np.ascontiguousarray(right_off, dtype=np.int64)
+        self.segments = np.ascontiguousarray(segments, dtype=np.uint8)
+        self.seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        self.n_segments = np.ascontiguousarray(n_segments, dtype=np.int32)
+        self.copies = np.ascontiguousarray(copies, dtype=np.int32)
+        self.error_rate = np.ascontiguousarray(error_rate, dtype=np.float64)
+        self.n = len(self.copies)
+
+    @classmethod
+    def from_lists(cls, lefts, rights, segment_lists, copies, error_rates):
+        """``lefts`` / ``rights``: the flank strings that enter the model (already trimmed to the flank size);
+        ``segment_lists``: per locus the aligned repeat segments (equal-length strings over ACGT-)."""
+        n = len(copies)
+
+        def flat_codes(strings):
+            off = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(np.fromiter(map(len, strings), dtype=np.int64, count=n), out=off[1:])
+            raw = "".join(strings).encode("ascii", "replace")
+            out = np.empty(max(len(raw), 1), dtype=np.uint8)
+            bad = load_library().advhmm_encode_acgt(raw, len(raw), out.ctypes.data)
+            if bad >= 0:
+                raise ValueError("flank contains a non-ACGT symbol")
+            return out, off
+        for segs in segment_lists:
+            if len(segs) < 1 or len(set(map(len, segs))) != 1:
+                raise ValueError("the aligned repeat segments of a locus must have one width")
+        left, left_off = flat_codes(lefts)
+        right, right_off = flat_codes(rights)
+        seg_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.fromiter((sum(map(len, segs)) for segs in segment_lists), dtype=np.int64, count=n), out=seg_off[1:])
+        raw = "".join("".join(segs) for segs in segment_lists).upper().encode("ascii", "replace")
+        segments = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, dtype=np.uint8)
+        n_seg = np.fromiter(map(len, segment_lists), dtype=np.int32, count=n)
+        rates = np.full(n, error_rates, dtype=np.float64) if np.isscalar(error_rates) else error_rates
+        return cls(left, left_off, right, right_off, segments, seg_off, n_seg, copies, rates)
+
+    def desc(self, lo=0, hi=None):
+        """The C struct for loci [lo, hi) (a view: the arrays of ``self`` must stay alive)."""
+        hi = self.n if hi is None else hi
+        return LociDesc(hi - lo, self.left.ctypes.data, self.left_off[lo:].ctypes.data,
+                        self.right.ctypes.data, self.right_off[lo:].ctypes.data,
+                        self.segments.ctypes.data, self.seg_off[lo:].ctypes.data,
+                        self.n_segments[lo:].ctypes.data, self.copies[lo:].ctypes.data, self.error_rate[lo:].ctypes.data)
 
 
 class Context(object):
@@ -197,6 +286,16 @@ class Context(object):
         if getattr(self, "_h", None):
             self._lib.advhmm_context_destroy(self._h)
             self._h = None
+
+    def compile_loci(self, columns, n_threads=0, lo=0, hi=None):
+        """``advhmm_models_create_for_loci``: the read-matcher models of a batch of loci, compiled and
+        uploaded natively.  -> list of :class:`DeviceModel`."""
+        hi = columns.n if hi is None else hi
+        n = hi - lo
+        handles = (C.c_void_p * max(n, 1))()
+        d = columns.desc(lo, hi)
+        _check(self._lib.advhmm_models_create_for_loci(self._h, C.byref(d), int(n_threads), handles))
+        return [DeviceModel.from_handle(self, handles[i]) for i in range(n)]
 
     # -- many loci in one call -----------------------------------------------------------
     def viterbi_multi(self, models, groups, both_strands=False, want_path=True,
@@ -300,6 +399,58 @@ class DeviceModel(object):
     @classmethod
     def from_baked(cls, baked, ctx=None):
         return cls(ctx or Context.default(), baked)
+
+    @classmethod
+    def from_handle(cls, ctx, handle):
+        """Wrap an ``advhmm_model*`` made by ``advhmm_models_create_for_loci``."""
+        self = cls.__new__(cls)
+        self._lib = load_library()
+        self.ctx = ctx
+        self._h = C.c_void_p(handle)
+        info = ModelInfo()
+        _check(self._lib.advhmm_model_info_get(self._h, C.byref(info)))
+        self.info = info
+        dims = self.dims()
+        self.n_states = dims.n_states
+        self.n_symbols = dims.n_symbols
+        self.path_extra = dims.n_states - dims.silent_start + 2
+        return self
+
+    def dims(self):
+        d = ModelDims()
+        _check(self._lib.advhmm_model_dims_get(self._h, C.byref(d)))
+        return d
+
+    def tables(self):
+        """The baked arrays (+ state names) of a locus model, as ``pomegranate.bake`` would hold them."""
+        d = self.dims()
+        in_off = np.empty(d.n_states + 1, dtype=np.int32)
+        in_src = np.empty(d.n_edges, dtype=np.int32)
+        in_logp = np.empty(d.n_edges, dtype=np.float64)
+        emis = np.empty((d.silent_start, d.n_symbols), dtype=np.float64)
+        names = C.create_string_buffer(int(d.names_bytes) + 1)
+        _check(self._lib.advhmm_model_tables_get(self._h, in_off.ctypes.data, in_src.ctypes.data, in_logp.ctypes.data,
+                                                 emis.ctypes.data, names))
+        return {"n_states": d.n_states, "silent_start": d.silent_start, "start_index": d.start_index,
+                "end_index": d.end_index, "finite": d.finite, "in_off": in_off, "in_src": in_src,
+                "in_logp": in_logp, "emis": emis, "alphabet": "ACGT",
+                "names": names.raw[:int(d.names_bytes)].decode("ascii").split("\n")[:-1], "shape": tuple(d.shape)}
+
+    def banded_tables(self, n_states, silent_start, n_edges):
+        """Host copies of what the banded kernels read for this model (tests)."""
+        nb = C.c_int64(0)
+        _check(self._lib.advhmm_model_banded_tables_get(self._h, None, 0, None, None, None, None, None, C.addressof(nb)))
+        image = np.zeros(nb.value, dtype=np.uint8)
+        tb1 = np.zeros(4 * silent_start, dtype=np.int32)
+        tb0 = np.zeros(n_states, dtype=np.int32)
+        fin_w = np.full(n_edges, np.nan)
+        classes = np.zeros(n_states, dtype=np.uint8)
+        empty = C.c_double(0)
+        _check(self._lib.advhmm_model_banded_tables_get(self._h, image.ctypes.data, nb.value, tb1.ctypes.data,
+                                                        tb0.ctypes.data, fin_w.ctypes.data, classes.ctypes.data,
+                                                        C.addressof(empty), C.addressof(nb)))
+        return {"image": image, "tb1": tb1, "tb0": tb0, "fin_w": fin_w[~np.isnan(fin_w)], "classes": classes,
+                "logp_empty": empty.value}
 
     @property
     def kind(self):

@@ -24,7 +24,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import bam_ingest, engine, genotype, keyword_filter
+from . import bam_ingest, engine, fast_compile, genotype, keyword_filter
 from .locus_batch import LocusDecoder, reverse_complement
 
 
@@ -48,6 +48,8 @@ class GenotypingRun(object):
         self.loci = list(loci)
         self.decoders = [LocusDecoder(l.left_flank, l.right_flank, l.repeat_segments, read_length,
                                       scaled_score=l.scaled_score, locus_id=l.id) for l in self.loci]
+        # the models of all loci in ONE native call (profiles, parameter chains, device tables, upload)
+        fast_compile.attach_device_models([d.model for d in self.decoders], self.ctx)
         keywords = [(l.id, sorted(keyword_filter.get_keywords_for_filtering(
             l.left_flank, l.right_flank, l.repeat_segments, l.pattern, keyword_size=keyword_size))) for l in self.loci]
         self.filter = keyword_filter.KeywordFilter(keywords, ctx=self.ctx)

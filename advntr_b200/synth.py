@@ -101,6 +101,40 @@ def config2_locus(locus_id, read_length=150):
     return Locus(locus_id, left, right, segments, read_length=read_length, flank=150)
 
 
+def config5_locus(locus_id, read_length=150):
+    """BASELINE config 5 (the 158,522-locus genic set, README.md:31-35): the config-2 generator with
+    repeat units up to 100 bp and VNTRs up to 1 kb in the reference."""
+    rng = random.Random(1000003 * locus_id + 29)
+    R = rng.randint(6, 100)
+    total = rng.randint(2 * R, max(2 * R, 1000))
+    ncopies = max(2, total // R)
+    ru = rand_dna(rng, R)
+    segments = [substitute(rng, ru, 0.02) for _ in range(ncopies)]
+    left = rand_dna(rng, 500)
+    right = rand_dna(rng, 500)
+    return Locus(locus_id, left, right, segments, read_length=read_length, flank=150)
+
+
+def locus_cost_estimate(locus_id, generator="config2", read_length=150, coverage=30, decoys=50, flank=150):
+    """(reads, DP cells) of a synthetic locus from the FIRST draws of its generator only -- repeat-unit
+    length and copy number -- without making its sequences, reads or model: the reads
+    config2_read_codes will make times the state count m = 3 L_l + 3 L_r + C (3 R + 3) + 18 (SURVEY.md
+    section 8).  Cheap enough for every rank to balance all loci of a run by itself."""
+    if generator == "config5":
+        rng = random.Random(1000003 * locus_id + 29)
+        R = rng.randint(6, 100)
+        ncopies = max(2, rng.randint(2 * R, max(2 * R, 1000)) // R)
+    else:
+        rng = random.Random(1000003 * locus_id + 17)
+        R = rng.randint(6, 70)
+        ncopies = max(2, 139 // R)
+    L = read_length
+    n_reads = max(1, int(round((R * ncopies + L) * coverage / float(L)))) + 2 * decoys
+    C = read_matcher.copies_for_read_length(L, R)
+    m = 6 * flank + C * (3 * R + 3) + 18
+    return n_reads, n_reads * L * m
+
+
 def config2_reads(locus, coverage=30, decoys=50, seed=None):
     """Mapped reads overlapping the VNTR at `coverage`x (decoded on one strand) and decoy
     unmapped reads (decoded on both strands, vntr_finder.py:235-254)."""

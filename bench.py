@@ -2,18 +2,25 @@
 """Benchmark of the hot path: batched Viterbi decoding of Illumina reads against per-locus
 VNTR read-matcher HMMs (BASELINE.json: "Viterbi GCUPS & reads/s (150bp Illumina) ...").
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (config 2)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU engine
+    python bench.py --workload config5 --total-loci 158522   # the genic-set sweep, sharded by locus
+    python bench.py --workload config3 | frameshift          # PacBio-like long reads | --frameshift mode
 
-Workload (``config.workload``): BASELINE config 2 -- synthetic loci shaped like the recommended
-hg19 Illumina set (RU 6..70 bp, 150 bp flanks in the model), per locus the 30x mapped reads that
-overlap the VNTR plus 50 decoy unmapped reads on both strands, 150 bp reads.  One *step* = one
-pass of the hot path over every read of every locus of the rank: 2-bit packing, banded Viterbi
-fill, device backtrack to full state paths.  Weak scaling: every rank decodes its own
-``--loci`` loci (a disjoint slice of the locus id space), no collective on the data path.
+Default workload (``config.workload``): BASELINE config 2 -- synthetic loci shaped like the
+recommended hg19 Illumina set (RU 6..70 bp, 150 bp flanks in the model), per locus the 30x mapped
+reads that overlap the VNTR plus 50 decoy unmapped reads on both strands, 150 bp reads.  One *step* =
+one pass of the hot path over every read of every locus of the rank: 2-bit packing, banded Viterbi
+fill, device backtrack to full state paths.  Weak scaling: every rank decodes its own ``--loci`` loci
+(a disjoint slice of the locus id space), no collective on the data path.
 
-  value   reads/s over all ranks with inputs resident in HBM (CUDA events, max over ranks)
-  e2e     the same through the host-buffer C-ABI call: pinned host reads in, logp + paths out
+  value     reads/s over all ranks with inputs resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the host-buffer C-ABI call: pinned host reads in, logp + paths out
+  pipeline  locus descriptions + reads in -> per-read summaries out: native model compilation
+            (advhmm_models_create_for_loci) INSIDE the timed region, cold (shape cache empty) and
+            warm (shapes cached), next to the decode-only figure
+  strong    the SAME --loci loci split over the ranks by sharding.lpt_assign, results gathered on
+            rank 0 inside the timed region (reported at every N, N = 1 included)
   roofline / cpu_baseline: see DESIGN.md section "Measurement"
 """
 from __future__ import annotations
@@ -41,14 +48,22 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "frameshift", "config5"])
     ap.add_argument("--loci", type=int, default=6719, help="loci per GPU (config 2: 6,719)")
+    ap.add_argument("--total-loci", type=int, default=158522, help="config5: loci of the whole run, sharded over the ranks")
+    ap.add_argument("--chunk-loci", type=int, default=8192, help="config5: loci compiled + decoded per device call")
     ap.add_argument("--coverage", type=int, default=30)
     ap.add_argument("--decoys", type=int, default=50)
     ap.add_argument("--cpu-sample-loci", type=int, default=0, help="loci in the CPU sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--verify-loci", type=int, default=48,
                     help="re-score the state paths of the first N loci on the host (0: skip)")
+    ap.add_argument("--oracle-loci", type=int, default=8,
+                    help="decode the first N loci with the CPU oracle as well and compare (0: skip)")
+    ap.add_argument("--long-reads", type=int, default=592, help="config3: reads per step")
     return ap.parse_args()
 
 
@@ -64,30 +79,69 @@ def locus_ids(rank, n_loci):
     return range(rank * n_loci + 1, (rank + 1) * n_loci + 1)
 
 
-def build_workload(rank, n_loci, coverage, decoys):
-    """Models (host tables) + reads of this rank's loci."""
-    from advntr_b200 import fast_compile, synth
-    baked, flats, lens, goff, cells, relax = [], [], [], [0], 0, 0
-    n_states = []
-    for lid in locus_ids(rank, n_loci):
-        loc = synth.config2_locus(lid, READ_LEN)
-        model = fast_compile.build_vntr_matcher_hmm(loc.left, loc.right, loc.segments, loc.copies,
-                                                    flank_size=loc.flank, error_rate=loc.error_rate)
+def _synth_chunk(job):
+    """(left, right, segments, copies, flat read codes, read lengths) of a slice of loci."""
+    ids, coverage, decoys, generator = job
+    from advntr_b200 import synth
+    make = synth.config5_locus if generator == "config5" else synth.config2_locus
+    out = []
+    for lid in ids:
+        loc = make(lid, READ_LEN)
         flat, ln = synth.config2_read_codes(loc, coverage, decoys)
-        baked.append(model.baked)
-        flats.append(flat)
-        lens.append(ln)
-        goff.append(goff[-1] + len(ln))
-        m = model.baked["n_states"]
-        n_states.append(m)
-        cells += int(ln.sum()) * m
-        relax += int(ln.sum()) * len(model.baked["in_src"])      # SURVEY 8d: edge relaxations = sum n * E
-    lens = np.concatenate(lens)
+        out.append((loc.left[-loc.flank:], loc.right[:loc.flank], loc.segments, loc.copies, loc.error_rate, flat, ln))
+    return out
+
+
+def build_workload(ids, coverage, decoys, generator="config2", procs=1):
+    """Locus descriptions (the columns advhmm_models_create_for_loci takes) + reads of `ids`."""
+    from advntr_b200 import engine
+    ids = list(ids)
+    if procs > 1 and len(ids) >= 512:
+        import multiprocessing as mp
+        step = max(64, (len(ids) + 4 * procs - 1) // (4 * procs))
+        jobs = [(ids[i:i + step], coverage, decoys, generator) for i in range(0, len(ids), step)]
+        with mp.get_context("fork").Pool(procs) as pool:
+            parts = pool.map(_synth_chunk, jobs)
+        rows = [r for p in parts for r in p]
+    else:
+        rows = _synth_chunk((ids, coverage, decoys, generator))
+    cols = engine.LociColumns.from_lists([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows],
+                                         [r[3] for r in rows], [r[4] for r in rows])
+    lens = np.concatenate([r[6] for r in rows]) if rows else np.zeros(0, dtype=np.int64)
     off = np.zeros(len(lens) + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
-    return {"baked": baked, "seqs": np.concatenate(flats), "seq_off": off,
-            "group_off": np.asarray(goff, dtype=np.int64), "cells": cells, "relaxations": relax, "n_reads": len(lens),
-            "n_states": np.asarray(n_states), "edges": [len(b["in_src"]) for b in baked]}
+    goff = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum([len(r[6]) for r in rows], out=goff[1:])
+    seqs = np.concatenate([r[5] for r in rows] + [np.zeros(16, dtype=np.uint8)])
+    return {"ids": ids, "cols": cols, "seqs": seqs, "seq_off": off, "group_off": goff, "n_reads": len(lens)}
+
+
+def model_stats(models, wl):
+    """cells, edge relaxations and fp64 pipe operations of one pass, from the
+    models' own dimensions; the emitting / silent edge split is taken once per shape."""
+    by_shape = {}
+    lens = np.diff(wl["seq_off"])
+    bases = np.add.reduceat(lens, wl["group_off"][:-1]) if len(lens) else np.zeros(0)
+    bases = np.where(np.diff(wl["group_off"]) > 0, bases, 0)
+    cells = relax = ops = 0.0
+    n_states, edges = [], []
+    for dm, nb in zip(models, bases):
+        d = dm.dims()
+        key = tuple(d.shape)
+        st = by_shape.get(key)
+        if st is None:
+            t = dm.tables()
+            deg = np.diff(t["in_off"])
+            st = by_shape[key] = (int(deg[:t["silent_start"]].sum()), int(deg[t["silent_start"]:].sum()))
+        e_emit, e_sil = st
+        n_states.append(d.n_states)
+        edges.append(int(d.n_edges))
+        cells += float(nb) * d.n_states
+        relax += float(nb) * d.n_edges
+        # 2 adds per edge into an emitting state, 1 per edge into a silent state, 1 compare per edge
+        ops += float(nb) * (2 * e_emit + e_sil + e_emit + e_sil)
+    return {"cells": cells, "relaxations": relax, "fp64_ops": ops, "n_states": np.asarray(n_states),
+            "edges": np.asarray(edges)}
 
 
 # ------------------------------------------------------------------------------- clock sampling
@@ -183,6 +237,10 @@ def cpu_reference_pass(n_sample_loci, coverage, decoys, procs):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refenv
     kind = "reference" if refenv.have_reference_engine() else "port"
+    if kind == "reference":
+        # loaded in the parent as well, so that the process that reports the number has the compiled
+        # reference engine (oracle/_ref/pomegranate/*.so) mapped; the workers inherit it by fork
+        refenv.reference_pomegranate()
     ids = list(range(1, n_sample_loci + 1))
     slices = [ids[i::procs] for i in range(procs) if ids[i::procs]]
     ctx = mp.get_context("fork")
@@ -216,13 +274,15 @@ def run_reference_arm(args):
             times.append(last)
     reads_s = sum(t["reads"] for t in times) / sum(t["seconds"] for t in times)
     gcups = sum(t["cells"] for t in times) / sum(t["seconds"] for t in times) / 1e9
-    sample = "%d config-2 loci (%d reads) per step, %d processes" % (n_loci, last["reads"], last["procs"])
+    sample = "the first %d of the %d config-2 loci (%d reads) per step, %d processes" % (
+        n_loci, args.loci, last["reads"], last["procs"])
     line = {"impl": "reference", "metric": "viterbi_reads_per_s", "value": reads_s, "unit": "reads/s",
             "gcups": gcups, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean([t["seconds"] for t in times])),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": workload_config(args, n_loci),
+            "config": workload_config(args, args.loci),
+            "cpu_sample_loci": n_loci,
             "cpu_baseline": {"value": reads_s, "unit": "reads/s", "cores": last["procs"], "kind": last["kind"],
                              "sample": sample},
             "e2e": {"value": reads_s, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -237,40 +297,145 @@ def workload_config(args, n_loci):
             "l2": "inputs+traceback workspace exceed L2 (no explicit flush needed)"}
 
 
+# ------------------------------------------------------------------------------------ helpers
+class Dist(object):
+    """torch.distributed plumbing of one rank (NCCL for timing barriers / the final gather only)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback of the hot path")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            # NCCL prints its version banner to stdout; the contract is ONE JSON line on stdout
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="max"):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def gather_list(self, value):
+        """One float per rank -> list on every rank."""
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device="cuda")
+        t[self.rank] = value
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def make_context(D):
+    """A dedicated (non-default) torch stream: the library launches on it, and the torch events that
+    time the regions are recorded on the very same stream."""
+    from advntr_b200 import engine
+    stream = D.torch.cuda.Stream(device=D.local)
+    D.torch.cuda.set_stream(stream)
+    ctx = engine.Context(device=D.local, stream=stream.cuda_stream)
+    assert stream.cuda_stream != 0 and ctx.stream == stream.cuda_stream
+    return ctx, stream
+
+
+def create_models(ctx, cols, lo=0, hi=None):
+    """Raw advhmm_models_create_for_loci -> ctypes array of handles (no Python object per model)."""
+    from advntr_b200 import engine
+    hi = cols.n if hi is None else hi
+    handles = (C.c_void_p * max(hi - lo, 1))()
+    d = cols.desc(lo, hi)
+    engine._check(engine.load_library().advhmm_models_create_for_loci(ctx._h, C.byref(d), 0, handles))
+    return handles
+
+
+def destroy_models(handles, n):
+    from advntr_b200 import engine
+    lib = engine.load_library()
+    for i in range(n):
+        lib.advhmm_model_destroy(handles[i])
+
+
+def self_check(args, ctx, models, wl, d_logp, d_plen, d_poff, d_path, n_paths):
+    """Outside every timed region.  (1) The state paths of the first loci, re-scored with the models'
+    own tables, give the returned log-probabilities bit for bit (a valid path with that score).
+    (2) The first loci are ALSO decoded by the CPU oracle (oracle/hmm_oracle.c): scores and whole
+    paths must be equal -- the returned path is the reference's optimal path, ties included."""
+    from advntr_b200 import path_utils
+    goff, off = wl["group_off"], wl["seq_off"]
+    nv = min(max(args.verify_loci, args.oracle_loci), len(models))
+    if nv <= 0:
+        return None
+    r_hi = int(goff[nv])
+    h_lp = d_logp[:r_hi].cpu().numpy()
+    h_pl = d_plen[:r_hi].cpu().numpy()
+    h_po = d_poff[:r_hi].cpu().numpy()
+    h_pa = d_path[:n_paths].cpu().numpy()
+    out = {}
+    ok = True
+    n_rescored = min(args.verify_loci, nv)
+    tables = {}
+    for g in range(nv):
+        tables[g] = models[g].tables()
+    for g in range(n_rescored):
+        a, b = int(goff[g]), int(goff[g + 1])
+        codes = [wl["seqs"][off[r]:off[r + 1]] for r in range(a, b)]
+        paths = [h_pa[h_po[r]:h_po[r] + h_pl[r]] for r in range(a, b)]
+        sc = path_utils.rescore_paths(tables[g], codes, paths)
+        ok = ok and bool(np.array_equal(sc.view(np.int64), h_lp[a:b].view(np.int64)))
+    out.update({"loci": n_rescored, "reads": int(goff[n_rescored]), "paths_rescored_bit_exact": ok})
+    if not ok:
+        raise SystemExit("self-check failed: re-scored paths do not reproduce the log-probabilities")
+    n_or = min(args.oracle_loci, nv)
+    if n_or > 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        same = True
+        for g in range(n_or):
+            a, b = int(goff[g]), int(goff[g + 1])
+            codes = [wl["seqs"][off[r]:off[r + 1]] for r in range(a, b)]
+            lp, paths = oracle.OracleModel(tables[g]).viterbi(codes)
+            same = same and bool(np.array_equal(lp.view(np.int64), h_lp[a:b].view(np.int64)))
+            for r, p in zip(range(a, b), paths):
+                same = same and bool(np.array_equal(p, h_pa[h_po[r]:h_po[r] + h_pl[r]]))
+        out.update({"oracle_loci": n_or, "oracle_reads": int(goff[n_or]), "equal_to_cpu_oracle": same})
+        if not same:
+            raise SystemExit("self-check failed: device paths differ from the CPU oracle's")
+    return out
+
+
 # ------------------------------------------------------------------------------------ our arm
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
     from advntr_b200 import engine
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback of the hot path")
-    torch.cuda.set_device(local)
-    if world > 1:
-        # NCCL prints its version banner to stdout; the contract is ONE JSON line on stdout
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    D = Dist()
+    torch = D.torch
+    rank, world, local = D.rank, D.world, D.local
+    barrier = D.barrier
+    procs_for_synth = max(1, host_cores() // max(world, 1))
 
     t_build = time.time()
-    wl = build_workload(rank, args.loci, args.coverage, args.decoys)
-    # a dedicated (non-default) torch stream: the library launches on it, and the torch events that
-    # time the region are recorded on the very same stream
-    stream = torch.cuda.Stream(device=local)
-    torch.cuda.set_stream(stream)
-    ctx = engine.Context(device=local, stream=stream.cuda_stream)
-    assert stream.cuda_stream != 0 and ctx.stream == stream.cuda_stream
-    models = [engine.DeviceModel(ctx, b) for b in wl["baked"]]
-    t_build = time.time() - t_build
+    wl = build_workload(locus_ids(rank, args.loci), args.coverage, args.decoys, "config2", procs_for_synth)
+    t_synth = time.time() - t_build
+    ctx, stream = make_context(D)
     lib = engine.load_library()
+    t0 = time.time()
+    models = ctx.compile_loci(wl["cols"])                 # native: profiles, chains, device tables, upload
+    t_compile = time.time() - t0
+    stats = model_stats(models, wl)
+    t_build = time.time() - t_build
     handles = (C.c_void_p * len(models))(*[m._h for m in models])
     R = wl["n_reads"]
     goff, off = wl["group_off"], wl["seq_off"]
@@ -285,8 +450,8 @@ def run_ours(args):
     d_path = torch.empty(path_cap, dtype=torch.int32, device="cuda")
     d_total = torch.zeros(1, dtype=torch.int64, device="cuda")
 
-    def step_device():
-        rc = lib.advhmm_viterbi_multi(ctx._h, handles, len(models), goff.ctypes.data, d_seqs.data_ptr(),
+    def step_device(hs=handles, n_models=len(models)):
+        rc = lib.advhmm_viterbi_multi(ctx._h, hs, n_models, goff.ctypes.data, d_seqs.data_ptr(),
                                       off.ctypes.data, R, flags_dev, d_logp.data_ptr(), d_plen.data_ptr(),
                                       d_poff.data_ptr(), d_path.data_ptr(), path_cap, d_total.data_ptr())
         engine._check(rc)
@@ -312,28 +477,10 @@ def run_ours(args):
     n_paths = int(d_total.item())
     if n_paths > path_cap or int((d_plen < 0).sum().item()) != 0:
         raise SystemExit("path buffer too small or impossible reads in the synthetic workload")
+    if ctx.bad_symbol() != -1:
+        raise SystemExit("synthetic reads hold a code outside the alphabet")
 
-    # ---- self-check (outside every timed region): the state paths of the first loci, re-scored with
-    #      the models' own tables, must give the returned log-probabilities bit for bit -------------
-    verified = None
-    if rank == 0 and args.verify_loci > 0:
-        from advntr_b200 import path_utils
-        nv = min(args.verify_loci, len(models))
-        r_hi = int(goff[nv])
-        h_lp = d_logp[:r_hi].cpu().numpy()
-        h_pl = d_plen[:r_hi].cpu().numpy()
-        h_po = d_poff[:r_hi].cpu().numpy()
-        h_pa = d_path[:n_paths].cpu().numpy()
-        ok = True
-        for g in range(nv):
-            a, b = int(goff[g]), int(goff[g + 1])
-            codes = [wl["seqs"][off[r]:off[r + 1]] for r in range(a, b)]
-            paths = [h_pa[h_po[r]:h_po[r] + h_pl[r]] for r in range(a, b)]
-            sc = path_utils.rescore_paths(wl["baked"][g], codes, paths)
-            ok = ok and bool(np.array_equal(sc.view(np.int64), h_lp[a:b].view(np.int64)))
-        verified = {"loci": nv, "reads": r_hi, "paths_rescored_bit_exact": ok}
-        if not ok:
-            raise SystemExit("self-check failed: re-scored paths do not reproduce the log-probabilities")
+    verified = self_check(args, ctx, models, wl, d_logp, d_plen, d_poff, d_path, n_paths) if rank == 0 else None
 
     # ---- value: inputs resident in HBM, CUDA events on the launching stream ---------------------
     ctx.profile(True)
@@ -368,18 +515,20 @@ def run_ours(args):
         # the host-buffer call returns what the device-resident call computed, bit for bit
         assert torch.equal(h_logp.view(torch.int64), d_logp.cpu().view(torch.int64))
         assert torch.equal(h_plen, d_plen.cpu())
-    # ---- extra (reported, not the headline): on-device reducers instead of paths; fp32 mode ----
-    extra = {}
-    if not args.no_e2e:
-        summ = np.zeros(R, dtype=engine.SUMMARY_DTYPE)
-        h_summ = torch.from_numpy(summ.view(np.int32).reshape(R, 8)).pin_memory()
 
-        def step_summary():
-            rc = lib.advhmm_viterbi_multi_summary(ctx._h, handles, len(models), goff.ctypes.data, h_seqs.data_ptr(),
-                                                  off.ctypes.data, R, engine.WANT_SUMMARY, h_logp.data_ptr(),
-                                                  h_plen.data_ptr(), h_poff.data_ptr(), None, 0, None,
-                                                  h_summ.data_ptr())
-            engine._check(rc)
+    # ---- pipeline: locus descriptions + reads in -> summaries out, model compilation on the clock --
+    extra, pipeline = {}, None
+    summ = np.zeros(R, dtype=engine.SUMMARY_DTYPE)
+    h_summ = torch.from_numpy(summ.view(np.int32).reshape(R, 8)).pin_memory()
+
+    def step_summary(hs=handles):
+        rc = lib.advhmm_viterbi_multi_summary(ctx._h, hs, len(models), goff.ctypes.data, h_seqs.data_ptr(),
+                                              off.ctypes.data, R, engine.WANT_SUMMARY, h_logp.data_ptr(),
+                                              h_plen.data_ptr(), h_poff.data_ptr(), None, 0, None,
+                                              h_summ.data_ptr())
+        engine._check(rc)
+
+    if not args.no_e2e:
         step_summary()
         torch.cuda.synchronize()
         ts = time.perf_counter()
@@ -387,83 +536,387 @@ def run_ours(args):
             step_summary()
         torch.cuda.synchronize()
         extra["e2e_summary_ms"] = (time.perf_counter() - ts) * 1e3 / args.steps
+    if not args.no_pipeline:
+        runner = ShardRunner(D, ctx, stream, wl)
+        n_chunks = 4
+        chunk = (len(models) + n_chunks - 1) // n_chunks
 
-        def step_fp32():
-            rc = lib.advhmm_viterbi_multi(ctx._h, handles, len(models), goff.ctypes.data, d_seqs.data_ptr(),
-                                          off.ctypes.data, R, flags_dev | engine.FP32, d_logp.data_ptr(),
+        def pipeline_pass(cold, chunked=True):
+            if cold:
+                lib.advhmm_shape_cache_clear()
+            torch.cuda.synchronize()
+            t_a = time.perf_counter()
+            _, comp_ms = runner.one_pass(True, chunk if chunked else len(models))
+            return (time.perf_counter() - t_a) * 1e3, comp_ms
+
+        pipeline_pass(True)                             # warm-up of the route itself (staging buffers, memory pool)
+        cold = [pipeline_pass(True) for _ in range(args.steps)]
+        warm = [pipeline_pass(False) for _ in range(args.steps)]
+        serial = [pipeline_pass(True, chunked=False) for _ in range(args.steps)]
+        if not args.no_e2e:
+            got = runner.h_all.numpy()[:R]
+            assert np.array_equal(got[:, 0], h_logp.numpy().view(np.int64)), "pipeline scores differ from the resident-model route"
+            assert np.array_equal(np.ascontiguousarray(got[:, 1:]).view(np.int32).reshape(R, 8), h_summ.numpy()), \
+                "pipeline summaries differ from the resident-model route"
+        pipeline = {"cold_ms": float(np.mean([c[0] for c in cold])), "cold_compile_ms": float(np.mean([c[1] for c in cold])),
+                    "warm_ms": float(np.mean([c[0] for c in warm])), "warm_compile_ms": float(np.mean([c[1] for c in warm])),
+                    "serial_ms": float(np.mean([c[0] for c in serial])), "serial_compile_ms": float(np.mean([c[1] for c in serial])),
+                    "chunks": n_chunks}
+        del runner
+
+    # ---- extra (reported, not the headline): fp32 mode; the pageable drop-in route ----------------
+    if not args.no_e2e:
+        n32 = min(len(models), 1500)                   # the fp32 twin tables are built on first use: a bounded share
+        r32 = int(goff[n32])
+        goff32 = np.ascontiguousarray(goff[:n32 + 1])
+
+        def step_fp32_part():
+            rc = lib.advhmm_viterbi_multi(ctx._h, handles, n32, goff32.ctypes.data, d_seqs.data_ptr(),
+                                          off.ctypes.data, r32, flags_dev | engine.FP32, d_logp.data_ptr(),
                                           d_plen.data_ptr(), d_poff.data_ptr(), d_path.data_ptr(), path_cap,
                                           d_total.data_ptr())
             engine._check(rc)
-        step_fp32()
+        ru64 = None
+        if rank == 0:
+            ru64 = h_summ.numpy()[:r32, 0].copy() if not args.no_e2e else None
+        step_fp32_part()
         torch.cuda.synchronize()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
         for _ in range(args.steps):
-            step_fp32()
+            step_fp32_part()
         f1.record(stream)
         torch.cuda.synchronize()
         extra["fp32_ms"] = f0.elapsed_time(f1) / args.steps
+        extra["fp32_reads"] = r32
+        # RU-count concordance of the fp32 mode against fp64 on the same reads (north_star: "reported")
+        d_summ32 = torch.zeros((r32, 8), dtype=torch.int32, device="cuda")
+        rc = lib.advhmm_viterbi_multi_summary(ctx._h, handles, n32, goff32.ctypes.data, d_seqs.data_ptr(),
+                                              off.ctypes.data, r32, engine.DEVICE_BUFFERS | engine.FP32 | engine.WANT_SUMMARY,
+                                              d_logp.data_ptr(), d_plen.data_ptr(), d_poff.data_ptr(), None, 0, None,
+                                              d_summ32.data_ptr())
+        engine._check(rc)
+        torch.cuda.synchronize()
+        if ru64 is not None:
+            ru32 = d_summ32[:, 0].cpu().numpy()
+            extra["fp32_ru_concordance"] = float((ru32 == ru64).mean())
+        # pageable drop-in route: model.viterbi_batch(list of str) -> (logp, paths) per locus, Python objects
+        if rank == 0:
+            from advntr_b200 import fast_compile
+            alphabet = np.array(list("ACGT"))
+            n_py = min(64, len(models))
+            reads = []
+            for g in range(n_py):
+                a, b = int(goff[g]), int(goff[g + 1])
+                reads.append(["".join(alphabet[wl["seqs"][off[r]:off[r + 1]]]) for r in range(a, b)])
+            py_models = [fast_compile.CompiledHMM(None, models[g]) for g in range(n_py)]
+            for m in py_models[:2]:
+                m.viterbi_batch(reads[0][:4])
+            tp = time.perf_counter()
+            n_done = 0
+            for m, rs in zip(py_models, reads):
+                res = m.viterbi_batch(rs)
+                vp = [res.path(i) for i in range(len(rs))]
+                n_done += len(rs)
+            extra["pageable_reads_per_s"] = n_done / (time.perf_counter() - tp)
+            extra["pageable_loci"] = n_py
+            for m in py_models:
+                m._engine = None                       # the handles belong to `models`
     sampler.stop()
 
+    # ---- strong scaling: the SAME loci split over the ranks, results gathered on rank 0 ------------
+    strong = None
+    if not args.no_strong:
+        # rank 0's own workload IS loci 1..n: its full decode (summary leg above) checks the gathered table
+        check = (h_logp.numpy().copy(), h_summ.numpy().copy()) if (rank == 0 and not args.no_e2e) else None
+        strong = strong_scaling_leg(args, D, ctx, stream, "config2", args.loci, args.steps,
+                                    resident=(wl, handles) if world == 1 else None, check=check)
+
     # ---- max over ranks -------------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_ms or 0.0, float(R), float(wl["cells"]), fill_ms, float(wl["relaxations"])],
-                     dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    else:
-        tmax = tsum = t
-    ms_all, e2e_all = float(tmax[0]), float(tmax[1])
-    reads_all, cells_all = float(tsum[2]), float(tsum[3])
+    ms_all, e2e_all = D.reduce([ms, e2e_ms or 0.0], "max")
+    reads_all, cells_all, relax_all = D.reduce([float(R), stats["cells"], stats["relaxations"]], "sum")
+    pipe_all = D.reduce([pipeline["cold_ms"], pipeline["warm_ms"], pipeline["serial_ms"]], "max") if pipeline else None
+    loci_all = D.reduce([float(len(models))], "sum")[0]
 
     if rank == 0:
         K = args.steps
         value = reads_all * K / (ms_all * 1e-3)
         gcups = cells_all * K / (ms_all * 1e-3) / 1e9
         line = {"metric": "viterbi_reads_per_s", "value": value, "unit": "reads/s", "gcups": gcups,
-                "edge_relaxations_per_s": float(tsum[5]) * K / (ms_all * 1e-3),
+                "edge_relaxations_per_s": relax_all * K / (ms_all * 1e-3),
                 "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_all / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": workload_config(args, args.loci),
                 "reads_per_step": reads_all, "gpu_launches": int(launches), "clocks": clocks,
-                "setup_s": round(t_build, 1)}
+                "setup_s": round(t_build, 1),
+                "setup": {"synthetic_inputs_s": round(t_synth, 2), "model_compile_s": round(t_compile, 3),
+                          "loci_per_s_compile": len(models) / t_compile}}
         if e2e_ms is not None:
             h2d = int(off[-1])
             d2h = R * (8 + 4 + 8) + n_paths * 4
             line["e2e"] = {"value": reads_all * K / (e2e_all * 1e-3), "unit": "reads/s",
                            "gcups": cells_all * K / (e2e_all * 1e-3) / 1e9,
                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_all / K}
+        if pipeline:
+            cold_ms, warm_ms, serial_ms = pipe_all
+            line["pipeline"] = {
+                "what": "per rank: locus descriptions (flank codes, aligned repeat segments) + pinned host reads in -> "
+                        "H2D -> per chunk of loci advhmm_models_create_for_loci (profiles, parameter chains, device "
+                        "tables on all host threads, upload on a second stream) while the device decodes the previous "
+                        "chunk with the on-device path reducers -> logp + 32 B summary per read on the host; wall clock",
+                "chunks": pipeline["chunks"],
+                "compile_only": {"loci_per_s": len(models) / (pipeline["serial_compile_ms"] * 1e-3),
+                                 "ms": pipeline["serial_compile_ms"],
+                                 "note": "rank 0, cold: all loci of the rank in ONE advhmm_models_create_for_loci call, "
+                                         "shape structures rebuilt, tables uploaded"},
+                "cold_unchunked": {"loci_per_s": loci_all / (serial_ms * 1e-3), "ms_per_step": serial_ms,
+                                   "note": "compile everything, then decode everything (no overlap)"},
+                "cold": {"loci_per_s": loci_all / (cold_ms * 1e-3), "reads_per_s": reads_all / (cold_ms * 1e-3),
+                         "ms_per_step": cold_ms, "compile_ms": pipeline["cold_compile_ms"],
+                         "note": "shape cache cleared before every step: structures of all shapes rebuilt"},
+                "warm": {"loci_per_s": loci_all / (warm_ms * 1e-3), "reads_per_s": reads_all / (warm_ms * 1e-3),
+                         "ms_per_step": warm_ms, "compile_ms": pipeline["warm_compile_ms"],
+                         "note": "shapes cached (a second sample of the same panel); models still compiled per step"},
+                "host_threads": host_cores()}
         if extra:
-            line["extras"] = {
-                "e2e_summary_only": {"value": R * world / (extra["e2e_summary_ms"] * 1e-3), "unit": "reads/s",
-                                     "note": "host buffers, on-device path reducers (32 B/read) instead of "
-                                             "full state paths; rank-0 time x n_gpus",
-                                     "d2h_bytes_per_step": R * (8 + 4 + 32)},
-                "fp32_mode": {"value": R * world / (extra["fp32_ms"] * 1e-3), "unit": "reads/s",
-                              "note": "optional ADVHMM_FP32 mode, device-resident, full paths; tolerance "
-                                      "and RU-count concordance in tests/test_gpu_parity.py::test_fp32_mode"}}
+            ex = {}
+            if "e2e_summary_ms" in extra:
+                ex["e2e_summary_only"] = {"value": R * world / (extra["e2e_summary_ms"] * 1e-3), "unit": "reads/s",
+                                          "note": "models resident, host buffers, on-device path reducers (32 B/read) "
+                                                  "instead of full state paths; rank-0 time x n_gpus",
+                                          "d2h_bytes_per_step": R * (8 + 4 + 32)}
+            if "fp32_ms" in extra:
+                ex["fp32_mode"] = {"value": extra["fp32_reads"] * world / (extra["fp32_ms"] * 1e-3), "unit": "reads/s",
+                                   "reads": extra["fp32_reads"],
+                                   "ru_concordance": extra.get("fp32_ru_concordance"),
+                                   "note": "optional ADVHMM_FP32 mode, device-resident, full paths; tolerance "
+                                           "|dlogp| <= 2e-5 |logp| + 2e-5 (tests/test_gpu_parity.py::test_fp32_mode); "
+                                           "ru_concordance = share of reads whose repeat count equals the fp64 one"}
+            if "pageable_reads_per_s" in extra:
+                ex["pageable_python_route"] = {"value": extra["pageable_reads_per_s"], "unit": "reads/s",
+                                               "loci": extra["pageable_loci"],
+                                               "note": "model.viterbi_batch(list of str) per locus: encode, pageable "
+                                                       "staging, full paths as numpy views (one process, rank 0)"}
+            line["extras"] = ex
+        if strong:
+            line["strong"] = strong
         if verified:
             line["verified"] = verified
-        line["roofline"] = roofline(ctx, wl, fill_ms, fill_n, bt_ms, bt_n, ms, K)
+        line["roofline"] = roofline(ctx, wl, stats, fill_ms, fill_n, bt_ms, bt_n, ms, K)
         if world == 1 and not args.no_cpu_baseline:
             procs = host_cores()
-            cb = cpu_reference_pass(args.cpu_sample_loci or auto_sample_loci(procs), args.coverage, args.decoys, procs)
+            n_cpu = args.cpu_sample_loci or auto_sample_loci(procs)
+            cb = cpu_reference_pass(n_cpu, args.coverage, args.decoys, procs)
             line["cpu_baseline"] = {"value": cb["reads_per_s"], "unit": "reads/s", "gcups": cb["gcups"],
                                     "cores": cb["procs"], "kind": cb["kind"],
                                     "sample": "%d reads of the first %d config-2 loci, %.1f s" %
-                                              (cb["reads"], cb["reads"] // 155 or 1, cb["seconds"])}
+                                              (cb["reads"], n_cpu, cb["seconds"])}
         print(json.dumps(line))
     for m in models:
         m.close()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
-def roofline(ctx, wl, fill_ms, fill_n, bt_ms, bt_n, total_ms, steps):
-    """Dominant kernel = banded_fill_kernel.  HBM view per the contract (algorithmic bytes per
-    SURVEY.md section 8d: 1 traceback byte per DP cell + packed read + outputs) and, because the
-    kernel is bound by the fp64 add/compare pipe rather than by HBM, the fp64 view as well."""
+# ------------------------------------------------------------------ sharded / pipelined passes
+def lpt_shares(n_loci, world, generator, coverage, decoys):
+    """Owner rank of every locus 1..n_loci: sharding.lpt_assign on the estimated DP cells."""
+    from advntr_b200 import sharding, synth
+    est = [synth.locus_cost_estimate(i, generator, READ_LEN, coverage, decoys) for i in range(1, n_loci + 1)]
+    owner, load = sharding.lpt_assign([e[1] for e in est], world)
+    return np.asarray(owner), load, np.asarray([e[0] for e in est], dtype=np.int64)
+
+
+class ShardRunner(object):
+    """One rank's share of a run, host buffers in -> per-read results out:
+
+      pinned host reads --H2D--> [ per chunk of loci: models (resident, or compiled here by
+      advhmm_models_create_for_loci while the previous chunk is being decoded) -> decode with the on-device
+      path reducers ] -> logp + 32-byte summary per read, one 40-byte row each
+      -> (world > 1, gather) ONE NCCL all_gather over NVLink of the device-resident rows -> D2H on rank 0
+         (otherwise) D2H on this rank.
+
+    No other collective touches the data path.  Timed per pass on the device (CUDA events around the
+    rank's own work) and by wall clock around everything."""
+
+    def __init__(self, D, ctx, stream, wl, rows_max=None, handles=None):
+        from advntr_b200 import engine
+        torch = D.torch
+        self.D, self.ctx, self.stream, self.wl = D, ctx, stream, wl
+        self.lib = engine.load_library()
+        self.engine = engine
+        self.R = R = wl["n_reads"]
+        self.n_loci = len(wl["group_off"]) - 1
+        self.rows_max = rows_max or R
+        self.handles = handles                                     # resident models (ctypes array) or None
+        self.h_seqs = torch.from_numpy(wl["seqs"]).pin_memory()
+        self.d_seqs = torch.empty(len(wl["seqs"]), dtype=torch.uint8, device="cuda")
+        self.d_res = torch.zeros((self.rows_max, 5), dtype=torch.int64, device="cuda")
+        self.d_logp = torch.empty(max(R, 1), dtype=torch.float64, device="cuda")
+        self.d_summ = torch.empty((max(R, 1), 8), dtype=torch.int32, device="cuda")
+        self.d_plen = torch.empty(max(R, 1), dtype=torch.int32, device="cuda")
+        self.d_poff = torch.empty(max(R, 1), dtype=torch.int64, device="cuda")
+        self.d_all = self.h_all = None
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def prepare_gather(self):
+        torch, D = self.D.torch, self.D
+        self.d_all = torch.empty((D.world * self.rows_max, 5), dtype=torch.int64, device="cuda") if D.world > 1 else self.d_res
+        n = D.world * self.rows_max if D.rank == 0 else self.rows_max
+        self.h_all = torch.empty((n, 5), dtype=torch.int64).pin_memory()
+
+    def one_pass(self, compile_in_region=False, chunk_loci=0, gather=False):
+        """-> (device ms of this rank's own work, host ms spent inside model compilation)."""
+        torch, engine, lib, ctx = self.D.torch, self.engine, self.lib, self.ctx
+        wl, R, n_loci = self.wl, self.R, self.n_loci
+        goff, off = wl["group_off"], wl["seq_off"]
+        flags = engine.DEVICE_BUFFERS | engine.WANT_SUMMARY
+        chunk = chunk_loci if (compile_in_region and chunk_loci > 0) else n_loci
+        compile_ms, prev = 0.0, None
+        self.e0.record(self.stream)
+        self.d_seqs.copy_(self.h_seqs, non_blocking=True)
+        for lo in range(0, n_loci, max(chunk, 1)):
+            hi = min(n_loci, lo + chunk)
+            if compile_in_region:
+                tc = time.perf_counter()
+                hs = create_models(ctx, wl["cols"], lo, hi)         # the device keeps decoding the previous chunk
+                compile_ms += (time.perf_counter() - tc) * 1e3
+            else:
+                hs = (C.c_void_p * (hi - lo)).from_address(C.addressof(self.handles) + lo * C.sizeof(C.c_void_p))
+            r0, r1 = int(goff[lo]), int(goff[hi])
+            g = np.ascontiguousarray(goff[lo:hi + 1] - goff[lo])
+            o = np.ascontiguousarray(off[r0:r1 + 1])
+            rc = lib.advhmm_viterbi_multi_summary(
+                ctx._h, hs, hi - lo, g.ctypes.data, self.d_seqs.data_ptr(), o.ctypes.data, r1 - r0, flags,
+                self.d_logp[r0:].data_ptr(), self.d_plen[r0:].data_ptr(), self.d_poff[r0:].data_ptr(), None, 0, None,
+                self.d_summ[r0:].data_ptr())
+            engine._check(rc)
+            if compile_in_region:
+                if prev is not None:
+                    destroy_models(*prev)                          # freed in stream order: no wait for the device
+                prev = (hs, hi - lo)
+        if R:
+            self.d_res[:R, 0] = self.d_logp[:R].view(torch.int64)
+            self.d_res[:R, 1:] = self.d_summ[:R].view(torch.int64).reshape(R, 4)
+        self.e1.record(self.stream)
+        if gather and self.D.world > 1:
+            self.D.dist.all_gather_into_tensor(self.d_all, self.d_res)
+            if self.D.rank == 0:
+                self.h_all.copy_(self.d_all, non_blocking=True)
+        else:
+            if self.h_all is None:
+                self.prepare_gather()
+            self.h_all[:self.rows_max].copy_(self.d_res, non_blocking=True)
+        torch.cuda.synchronize()
+        if prev is not None:
+            destroy_models(*prev)
+        return self.e0.elapsed_time(self.e1), compile_ms
+
+
+def strong_scaling_leg(args, D, ctx, stream, generator, n_loci, steps, resident=None, compile_in_region=False,
+                       chunk_loci=0, check=None):
+    """Loci 1..n_loci split over the ranks by longest-processing-time-first on the estimated DP cells
+    (sharding.lpt_assign); every rank runs its share through ShardRunner; the per-read results of all
+    ranks are gathered on rank 0 inside the timed region.  ``compile_in_region``: model compilation is
+    timed as well, chunk by chunk, overlapped with the decoding of the previous chunk (config 5)."""
+    rank, world = D.rank, D.world
+    owner, load, reads_per_locus = lpt_shares(n_loci, world, generator, args.coverage, args.decoys)
+    mine = np.nonzero(owner == rank)[0] + 1                       # locus ids of this rank, ascending
+    t0 = time.time()
+    handles, own_models = None, False
+    if resident is not None and world == 1 and generator == "config2":
+        wl, handles = resident                                     # the weak workload of rank 0 IS loci 1..n
+    else:
+        wl = build_workload(mine, args.coverage, args.decoys, generator, max(1, host_cores() // world))
+    t_synth = time.time() - t0
+    assert wl["n_reads"] == int(reads_per_locus[mine - 1].sum()), "cost estimate and generator disagree on the read count"
+    counts = [int(reads_per_locus[owner == r].sum()) for r in range(world)]
+    R_max = max(counts)
+    if handles is None and not compile_in_region:
+        handles, own_models = create_models(ctx, wl["cols"]), True
+    runner = ShardRunner(D, ctx, stream, wl, rows_max=R_max, handles=handles)
+    runner.prepare_gather()
+    runner.one_pass(compile_in_region, chunk_loci, gather=True)   # warm-up
+    D.barrier()
+    busy, comp = [], []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        b, c = runner.one_pass(compile_in_region, chunk_loci, gather=True)
+        busy.append(b); comp.append(c)
+    D.barrier()
+    wall_ms = D.reduce([(time.perf_counter() - t0) * 1e3 / steps], "max")[0]
+    busy_all = D.gather_list(float(np.mean(busy)))
+    comp_all = D.gather_list(float(np.mean(comp)))
+    if own_models:
+        destroy_models(handles, len(mine))
+    total_reads = int(reads_per_locus.sum())
+    out = None
+    if rank == 0:
+        res = runner.h_all.numpy()
+        ok = sum(counts) == total_reads
+        if check is not None:
+            # rows of rank r = its loci in ascending id, reads in generator order; rank 0 decoded ALL loci
+            # by itself before (reads in locus order): the gathered table must hold exactly those rows
+            want_lp, want_summ = check
+            first = np.zeros(n_loci + 1, dtype=np.int64)
+            np.cumsum(reads_per_locus, out=first[1:])
+            for r in range(world):
+                ids_r = np.nonzero(owner == r)[0]
+                idx = np.concatenate([np.arange(first[i], first[i + 1]) for i in ids_r]) if len(ids_r) else np.zeros(0, dtype=np.int64)
+                rows = res[r * R_max:r * R_max + len(idx)]
+                ok = ok and bool(np.array_equal(rows[:, 0], want_lp.view(np.int64)[idx]))
+                ok = ok and bool(np.array_equal(np.ascontiguousarray(rows[:, 1:]).view(np.int32).reshape(-1, 8), want_summ[idx]))
+            if not ok:
+                raise SystemExit("strong-scaling leg: the gathered results differ from rank 0's own decode of all loci")
+        out = {"what": "loci 1..%d split by sharding.lpt_assign over %d rank(s); per rank: pinned reads H2D + decode "
+                       "with on-device path reducers%s; results of all ranks gathered on rank 0 by one NCCL all_gather "
+                       "(40 B/read) + one D2H copy, inside the timed region"
+                       % (n_loci, world, " + model compilation chunk by chunk, overlapped with the previous chunk's decode"
+                          if compile_in_region else ""),
+               "scaling": "strong", "loci_total": n_loci, "reads_total": total_reads,
+               "value": total_reads / (wall_ms * 1e-3), "unit": "reads/s", "ms_per_step": wall_ms,
+               "loci_per_s": n_loci / (wall_ms * 1e-3),
+               "rank_busy_ms": [round(b, 3) for b in busy_all],
+               "rank_busy_spread": (max(busy_all) - min(busy_all)) / max(busy_all) if max(busy_all) > 0 else 0.0,
+               "rank_reads": counts, "estimated_load_spread": (max(load) - min(load)) / max(load),
+               "gathered_equals_single_rank_decode": ok if check is not None else None,
+               "synthetic_inputs_s": round(t_synth, 1)}
+        if compile_in_region:
+            out["rank_compile_ms"] = [round(c, 2) for c in comp_all]
+    return out
+
+
+def run_config5(args):
+    """BASELINE config 5: the genic-set sweep.  --total-loci loci (config-5 generator) x 30x reads,
+    sharded by locus over the ranks (LPT), compiled and decoded chunk by chunk, results gathered on rank 0."""
+    D = Dist()
+    ctx, stream = make_context(D)
+    sampler = ClockSampler(D.local)
+    t0 = time.time()
+    strong = strong_scaling_leg(args, D, ctx, stream, "config5", args.total_loci, args.steps,
+                                compile_in_region=True, chunk_loci=args.chunk_loci)
+    t1 = time.time()
+    clocks = sampler.window(t0, t1)
+    sampler.stop()
+    if D.rank == 0:
+        line = {"metric": "viterbi_reads_per_s", "value": strong["value"], "unit": "reads/s",
+                "n_gpus": D.world, "steps": args.steps, "warmup": 1, "ms_per_step": strong["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "config5: %d synthetic genic-like loci (RU 6-100 bp, VNTR up to 1 kb) x 30x reads "
+                                       "+ 50 decoys x 2 strands, sharded by locus (LPT) over the ranks" % args.total_loci,
+                           "total_loci": args.total_loci, "chunk_loci": args.chunk_loci, "read_length": READ_LEN,
+                           "model_compilation": "inside the timed region", "want_path": False},
+                "gpu_launches": int(ctx.launch_count), "clocks": clocks, "strong": strong}
+        print(json.dumps(line))
+    ctx.close()
+    D.close()
+
+
+def roofline(ctx, wl, stats, fill_ms, fill_n, bt_ms, bt_n, total_ms, steps):
+    """Dominant kernel = banded_fill_kernel.  Its binding resource is the SM's fp64 add / compare issue
+    rate (SURVEY.md section 8d: max-plus DP, no FMA, no tensor cores), so that is the top-level bound;
+    the HBM view the bench contract names (algorithmic bytes: 1 traceback byte per DP cell + packed
+    read + outputs) sits beside it as hbm_* scalars."""
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak, which = 6650.0, "fallback"
     if os.path.exists(peaks_path):
@@ -472,46 +925,53 @@ def roofline(ctx, wl, fill_ms, fill_n, bt_ms, bt_n, total_ms, steps):
         except Exception:
             pass
     lens = np.diff(wl["seq_off"])
-    m_per_read = np.repeat(wl["n_states"], np.diff(wl["group_off"]))
+    m_per_read = np.repeat(stats["n_states"], np.diff(wl["group_off"]))
     # traceback 1 B per (position, state) + 2-bit packed read + logp, per read
     bytes_per_step = float((lens * m_per_read).sum()) + float(((lens + 3) // 4).sum()) + len(lens) * 8.0
-    # fp64 pipe operations per read: 2 adds per edge into an emitting state, 1 per edge into a
-    # silent state, 1 compare per edge; emitting share from the models
-    ops = 0.0
-    for b, r0, r1 in zip(wl["baked"], wl["group_off"][:-1], wl["group_off"][1:]):
-        deg = np.diff(b["in_off"])
-        e_emit = int(deg[:b["silent_start"]].sum())
-        e_sil = int(deg[b["silent_start"]:].sum())
-        ops += float(lens[r0:r1].sum()) * (2 * e_emit + e_sil + e_emit + e_sil)
+    ops = stats["fp64_ops"]
     fill_s = fill_ms * 1e-3
-    achieved = bytes_per_step * steps / fill_s / 1e9 if fill_s > 0 else None
+    hbm_achieved = bytes_per_step * steps / fill_s / 1e9 if fill_s > 0 else None
     fp64_peak = ctx.fp64_add_peak()
-    # measured DRAM bytes per read of this kernel from the committed ncu --set full capture
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_fill_traffic.json")
-    if os.path.exists(tpath) and fill_n:
-        try:
-            traffic = json.load(open(tpath))["dram_bytes_per_read"] * len(lens) * steps / fill_n
-        except Exception:
-            traffic = None
-    out = {"kernel": "banded_fill_kernel", "bound": "hbm",
-           "achieved": achieved, "peak": hbm_peak,
-           "peak_source": which, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
-           "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_step * steps / max(fill_n, 1),
-           "launches": int(fill_n), "avg_launch_ms": fill_ms / max(fill_n, 1),
-           "share_of_step": fill_ms / total_ms if total_ms else None,
-           "backtrack_share_of_step": bt_ms / total_ms if total_ms else None,
-           "fp64": {"achieved_gops": ops * steps / fill_s / 1e9 if fill_s > 0 else None,
-                    "peak_gops": fp64_peak, "peak_source": "measured (DADD microbenchmark, this run)",
-                    "frac": (ops * steps / fill_s / 1e9) / fp64_peak if fill_s > 0 and fp64_peak else None,
-                    "note": "the kernel's binding resource: fp64 add + compare issue, no FMA/tensor work"}}
-    return out
+    fp64_achieved = ops * steps / fill_s / 1e9 if fill_s > 0 else None
+    # DRAM bytes per read of this kernel from the committed ncu --set full capture (not measurable in-run)
+    traffic, traffic_src = None, None
+    for name in ("r2_fill_traffic.json", "r1_fill_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath) and fill_n:
+            try:
+                traffic = json.load(open(tpath))["dram_bytes_per_read"] * len(lens) * steps / fill_n
+                traffic_src = "profiles/%s: dram bytes per read of an ncu --set full capture x reads per launch " \
+                              "(extrapolated, not measured in this run)" % name
+                break
+            except Exception:
+                traffic = None
+    return {"kernel": "banded_fill_kernel", "bound": "fp64_issue",
+            "achieved": fp64_achieved, "peak": fp64_peak, "unit": "Gop/s",
+            "frac": fp64_achieved / fp64_peak if fp64_achieved and fp64_peak else None,
+            "peak_source": "measured in this run (DADD microbenchmark, advhmm_fp64_add_peak)",
+            "note": "algorithmic fp64 adds + compares (n * (2 E_emit + E_silent) + n * E, SURVEY 8d) per second over the "
+                    "measured fp64 add issue peak: no FMA / tensor work exists in a max-plus DP with exact tie-breaking",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "hbm_achieved_gbs": hbm_achieved, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": which,
+            "hbm_frac": hbm_achieved / hbm_peak if hbm_achieved else None,
+            "algorithmic_bytes_per_launch": bytes_per_step * steps / max(fill_n, 1),
+            "launches": int(fill_n), "avg_launch_ms": fill_ms / max(fill_n, 1),
+            "share_of_step": fill_ms / total_ms if total_ms else None,
+            "backtrack_share_of_step": bt_ms / total_ms if total_ms else None}
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "config5":
+        run_config5(args)
+    elif args.workload == "config3":
+        import bench_workloads
+        bench_workloads.run_config3(args)
+    elif args.workload == "frameshift":
+        import bench_workloads
+        bench_workloads.run_frameshift(args)
     else:
         run_ours(args)
 

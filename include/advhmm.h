@@ -117,6 +117,66 @@ int  advhmm_model_create(advhmm_context* ctx, const advhmm_model_desc* desc, adv
 void advhmm_model_destroy(advhmm_model* model);
 int  advhmm_model_info_get(const advhmm_model* model, advhmm_model_info* out);
 
+/* ---- models of many loci in one call ------------------------------------------------------
+ * Replaces, for a batch of loci, what the reference does per locus before it can decode a read:
+ * VNTRFinder.get_vntr_matcher_hmm -> build_vntr_matcher_hmm -> hmm_utils.get_read_matcher_model
+ * (vntr_finder.py:108-138, hmm_utils.py:289-595, profile_hmm.py:13-161: three sub-models, eight
+ * bake() calls and two dense matrix round trips in Python) plus the tail of bake().  The library
+ * evaluates the repeat-unit profile of every locus, takes the structure of its shape (flank
+ * lengths, match columns, copies) from a per-process cache (built once by the same sequence of
+ * graph operations as the reference), evaluates the parameters through the reference's chain of
+ * log / exp calls and writes the device tables of all loci with all host threads; one upload.
+ * Tables are bit-identical to a model of the reference's builders handed to advhmm_model_create
+ * (tests/test_native_compile.py) PROVIDED the vector exp the reference uses is set: the reference
+ * applies numpy.exp (hmm.pyx:514), whose SIMD kernels differ from libm's exp in the last bit of
+ * ~3 % of the values; advhmm_set_vexp(NULL) = libm (the Python binding installs numpy.exp).
+ *
+ * Columns of advhmm_loci (locus i):
+ *   left / right     flank bases that enter the model, codes 0..3: left[left_off[i] .. left_off[i+1])
+ *                    = the last flank_size bases before the repeats, right = the first ones after
+ *                    (vntr_finder.py:111-112, :131)
+ *   segments         the aligned repeat segments, n_segments[i] rows of equal width over "ACGT-",
+ *                    row-major from segments[seg_off[i]] (equal-length segments are their own
+ *                    alignment; profile_hmm.py:165-171 runs MUSCLE otherwise -- pass its output)
+ *   copies           unrolled copies of the repeat unit (vntr_finder.py:98-99)
+ *   error_rate       settings.MAX_ERROR_RATE (0.05 Illumina, 0.3 PacBio / nanopore)
+ * out[n_loci] receives the handles (destroy each with advhmm_model_destroy).  n_threads <= 0: all
+ * cores of the calling process.  State classes for the on-device path reducers are set. */
+typedef struct advhmm_loci {
+    int32_t        n_loci;
+    const uint8_t* left;        const int64_t* left_off;    /* [n_loci + 1] */
+    const uint8_t* right;       const int64_t* right_off;   /* [n_loci + 1] */
+    const char*    segments;    const int64_t* seg_off;     /* [n_loci + 1] */
+    const int32_t* n_segments;  /* [n_loci] */
+    const int32_t* copies;      /* [n_loci] */
+    const double*  error_rate;  /* [n_loci] */
+} advhmm_loci;
+
+typedef void (*advhmm_vexp_fn)(const double* in, double* out, int64_t n, void* user);
+int advhmm_set_vexp(advhmm_vexp_fn fn, void* user);
+int advhmm_models_create_for_loci(advhmm_context* ctx, const advhmm_loci* loci, int32_t n_threads, advhmm_model** out);
+/* Forget the cached shape structures (cold-start measurements). */
+void advhmm_shape_cache_clear(void);
+
+/* The baked arrays of a model made by advhmm_models_create_for_loci, in the layout of
+ * advhmm_model_desc (what pomegranate's bake() would hold for it), and its state names ('\n' after
+ * each, names_bytes in all): the Python wrapper builds its State list from them, the tests compare
+ * them with the reference's builders.  Any output pointer may be NULL. */
+typedef struct advhmm_model_dims {
+    int32_t n_states, silent_start, start_index, end_index, finite, n_symbols;
+    int64_t n_edges, names_bytes;
+    int32_t shape[4];        /* left flank, right flank, match columns, copies */
+} advhmm_model_dims;
+int advhmm_model_dims_get(const advhmm_model* model, advhmm_model_dims* out);
+int advhmm_model_tables_get(const advhmm_model* model, int32_t* in_off, int32_t* in_src, double* in_logp, double* emis,
+                            char* names);
+/* What the banded kernels read for this model, as host copies (tests: a locus model and a
+ * descriptor-made model of the same tables must agree byte for byte).  image == NULL: only
+ * *image_bytes is set.  tb1[4 * silent_start], tb0[n_states], classes[n_states], fin_w as many as the
+ * model has final-state edges (<= n_edges). */
+int advhmm_model_banded_tables_get(advhmm_model* model, unsigned char* image, int64_t image_cap, int32_t* tb1, int32_t* tb0,
+                                   double* fin_w, uint8_t* classes, double* logp_empty, int64_t* image_bytes);
+
 /* ---- decoding, host buffers -------------------------------------------------------------
  * Replaces HiddenMarkovModel.viterbi / _viterbi (hmm.pyx:1911-2136) for a batch of reads
  * of ONE model.  seqs holds the reads back to back, read r = seqs[seq_off[r] .. seq_off[r+1]).

@@ -58,3 +58,24 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert open(os.path.join(str(tmp_path), "rank%d.ok" % r)).read() == "1"
+
+
+def test_cost_estimate_matches_the_generators_and_balances_config2():
+    """bench.py's strong-scaling legs balance the loci of a run from locus_cost_estimate alone (every
+    rank computes the same assignment without generating anything): it must predict the read count the
+    generator really makes, and LPT on it must split config 2 evenly."""
+    import numpy as np
+    from advntr_b200 import synth
+    for gen, make in (("config2", synth.config2_locus), ("config5", synth.config5_locus)):
+        for lid in (1, 2, 17, 444, 6719, 158522):
+            loc = make(lid)
+            _, lens = synth.config2_read_codes(loc, 30, 50)
+            n, cells = synth.locus_cost_estimate(lid, gen, 150, 30, 50)
+            assert n == len(lens), (gen, lid)
+            m = 3 * 150 + 3 * 150 + loc.copies * (3 * len(loc.pattern) + 3) + 18
+            assert cells == n * 150 * m
+    est = [synth.locus_cost_estimate(i, "config2")[1] for i in range(1, 6720)]
+    for world in (2, 4, 8):
+        owner, load = sharding.lpt_assign(est, world)
+        assert (max(load) - min(load)) / max(load) < 1e-3
+        assert sorted(np.bincount(owner, minlength=world).tolist())[0] > 6719 // world - 60
