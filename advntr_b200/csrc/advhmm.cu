@@ -16,8 +16,9 @@
 //                            shared memory with one TMA bulk copy per CTA; 6-bit traceback per
 //                            (position, column) packed into one word per lane and step.
 //   banded_fill_f32_kernel   the same schedule in float (optional ADVHMM_FP32 mode)
-//   banded_long_kernel       long reads / models larger than shared memory: 256-position
-//                            stripes, carry through HBM, tables via the read-only path
+//   banded_long_kernel       long reads / models larger than shared memory: 160-position
+//                            stripes, carry through HBM, the model image streamed through a
+//                            per-warp ring in shared memory by TMA bulk copies
 //   banded_backtrack_kernel  device backtrack to the state path + on-device path reducers
 //   generic_fill_kernel<FWD> any baked model: row-synchronous CSR kernel, silent states by level;
 //                            FWD = log_probability (sum-product with the reference's pair_lse)
@@ -260,8 +261,9 @@ int ensure_full_model(advhmm_model* mod)
     return ADVHMM_OK;
 }
 
-int ensure_shape_on_device(advhmm_context* ctx, const rm::ShapeStructure* sh, DevShape** out)
+int ensure_shape_on_device(advhmm_context* ctx, const std::shared_ptr<const rm::ShapeStructure>& shp, DevShape** out)
 {
+    const rm::ShapeStructure* sh = shp.get();
     auto it = ctx->shape_dev.find(sh);
     if (it != ctx->shape_dev.end()) { *out = it->second.get(); return ADVHMM_OK; }
     const BandedTables& b = sh->cm.b;
@@ -271,6 +273,7 @@ int ensure_shape_on_device(advhmm_context* ctx, const rm::ShapeStructure* sh, De
     const size_t o_st = bb.add(st), o_acc = bb.add(b.acc_src_col), o_fs = bb.add(b.fin_state);
     const size_t o_fo = bb.add(b.fin_off), o_fsrc = bb.add(b.fin_src);
     std::unique_ptr<DevShape> ds(new DevShape);
+    ds->shape = shp;            // (a structure dropped from the cache must not give its address to another shape)
     CU_TRY(ds->blob.ensure(bb.bytes.size() + 256));
     unsigned char* base = ds->blob.as<unsigned char>();
     CU_TRY(cudaMemcpyAsync(base, bb.bytes.data(), bb.bytes.size(), cudaMemcpyHostToDevice, ctx->upload_stream));
@@ -423,7 +426,7 @@ int create_models_for_loci(advhmm_context* ctx, const advhmm_loci* L, int n_thre
             if (!mods[i]->lean) { off[i + 1] = off[i]; continue; }
             lay[i] = rm::lean_layout(*mods[i]->locus.shape, sizeof(DevBanded));
             off[i + 1] = off[i] + lay[i].bytes;
-            if (int rc = ensure_shape_on_device(ctx, mods[i]->locus.shape.get(), &dshape[i])) return rc;
+            if (int rc = ensure_shape_on_device(ctx, mods[i]->locus.shape, &dshape[i])) return rc;
         }
         auto arena = std::make_shared<DeviceArena>();
         arena->device = ctx->device;
@@ -834,7 +837,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     const size_t nw_short = rpl > 5 ? 2 : 1;
     const size_t s_per_item = n_short ? 32 * Ps * nw_short * 4 + 3 * Ps * 8 + (size_t)32 * rpl * 2 + 32 * 4 : 0;
     const size_t stripes_max = n_long ? ((size_t)std::max(fam_long.max_len, 1) + 32 * kLongRPL - 1) / (32 * kLongRPL) : 0;
-    const size_t l_tbw_words = stripes_max * 32 * Pl * 2;
+    const size_t l_tbw_words = stripes_max * 32 * Pl;
     const size_t l_acc = stripes_max * 32 * kLongRPL;
     const size_t l_per_item = n_long ? l_tbw_words * 4 + 6 * Pl * 8 + l_acc * 2 + 32 * 4 : 0;
     const size_t gm = (size_t)pl.max_m_generic;
@@ -938,9 +941,10 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         la.vfin = reinterpret_cast<double*>(w + lo_vfin); la.vfin_stride = 3 * Pl;
         la.carry = reinterpret_cast<double*>(w + lo_carry); la.carry_stride = 3 * Pl;
         la.ftb = reinterpret_cast<int32_t*>(w + lo_ftb);
+        if (int rc = allow_max_dynamic_smem(ctx, banded_long_kernel)) return rc;
         {
             ProfScope prof(ctx, 0);
-            banded_long_kernel<<<tile1 - tile0, kLongWarps * 32, 0, ctx->stream>>>(la);
+            banded_long_kernel<<<tile1 - tile0, kLongWarps * 32, kLongWarps * sizeof(LongRing), ctx->stream>>>(la);
         }
         CU_TRY(cudaGetLastError());
         ctx->launches++;

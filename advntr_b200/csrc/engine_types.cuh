@@ -154,6 +154,7 @@ struct DeviceArena {
 
 // structural device tables of a shape, shared by every locus model of that shape on a context
 struct DevShape {
+    std::shared_ptr<const rm::ShapeStructure> shape;   // kept alive: the map below is keyed by its address
     DevBuf blob;
     const int32_t* st = nullptr;
     const int32_t* acc_src_col = nullptr;

@@ -658,13 +658,21 @@ banded_fill_f32_kernel(const BandedArgs a)
 // =============================================================================================
 // banded fill kernel for long reads / large models (PacBio-like, BASELINE config 3)
 //
-// Same recurrence, tables and traceback encoding as banded_fill_kernel, but
-//   * a read is cut into stripes of 32*RPL positions that one warp sweeps one after the other;
+// Same recurrence, tables, rows per lane (5) and traceback encoding as banded_fill_kernel<5, 8>, but
+//   * a read is cut into stripes of 32 * 5 = 160 positions that one warp sweeps one after the other;
 //     the last position of a stripe is carried to the next stripe through a per-read buffer in
-//     global memory (3 doubles per column, updated in place: writes trail reads by >= 32 columns)
-//     that lane 0 consumes through a double-buffered 32-column ring in shared memory;
-//   * the model tables are read from global memory through the read-only path (the image of a
-//     100-copy model is > 1 MB); the warps of an SM walk the columns together, so L1 serves them.
+//     global memory (3 doubles per column, updated in place: writes trail reads by >= 16 columns)
+//     that lanes 0..15 stage 16 columns ahead in shared memory;
+//   * the model image (1.3 MB for the 100-copy model) does not fit in shared memory, and it does not
+//     have to: at step t the 32 lanes of a warp touch columns t-31 .. t only.  Every warp keeps a
+//     RING of 64 columns (+ 16 mirrored, see below) of the image in shared memory -- weights 80 B and
+//     emissions 4 x 16 B per column -- that lane 0 refills 16 columns at a time with TMA bulk copies
+//     (cp.async.bulk + one mbarrier per 16-column slot), one block ahead of the lane-0 front.  The
+//     column loop is the short-read kernel's: LDS.128 from the ring instead of global loads.
+//   * ring addressing without a wrap test per access: the steps run in blocks of 16; within a block a
+//     lane walks 16 consecutive ring slots from ((16 b - lane) & 63), and the first 16 slots are
+//     mirrored behind the 64th (the copy of every fourth column block is issued twice), so the walk
+//     never wraps.
 // =============================================================================================
 struct LongArgs {
     const Tile* tiles;
@@ -674,7 +682,7 @@ struct LongArgs {
     const int64_t* pk_off;
     const int32_t* rlen;
     double* logp;
-    uint32_t* tbw;              // per slot: stripes_max * 32 * Pmax * 2 words
+    uint32_t* tbw;              // per slot: stripes_max * 32 * Pmax words
     size_t tbw_stride;
     uint16_t* acc_tb;           // per slot: stripes_max * 32 * RPL entries
     size_t acc_stride;
@@ -685,8 +693,17 @@ struct LongArgs {
     int32_t* ftb;               // per slot 32
 };
 
-constexpr int kLongRPL = 8;
-constexpr int kLongWarps = 4;
+constexpr int kLongRPL = 5;
+constexpr int kLongWarps = 8;
+constexpr int kRingBlk = 16;                       // columns per TMA refill
+constexpr int kRingCols = 64 + kRingBlk;           // 4 slots + the mirror of slot 0
+
+struct __align__(128) LongRing {                   // per warp
+    double w[kRingCols * 10];                      // w10[slot][10]
+    double e[4][kRingCols * 2];                    // e2[sym][slot][2]
+    double carry[2][3][kRingBlk];                  // carried row of the previous stripe, double-buffered
+    uint64_t bar[4];
+};
 
 __device__ __forceinline__ double2 ldg128(const unsigned char* p)
 {
@@ -698,8 +715,8 @@ __device__ __forceinline__ double2 ldg128(const unsigned char* p)
 __global__ void __launch_bounds__(kLongWarps * 32, 2)
 banded_long_kernel(const LongArgs a)
 {
-    constexpr int RPL = kLongRPL, NW = 2, H = 32 * RPL;
-    __shared__ double s_ring[kLongWarps][2][3][32];
+    constexpr int RPL = kLongRPL, H = 32 * RPL, B = kRingBlk;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_fval[kLongWarps][32];
 
     const Tile tile = a.tiles[blockIdx.x];
@@ -715,6 +732,7 @@ banded_long_kernel(const LongArgs a)
         if (lane == 0) a.logp[q] = M->logp_empty;
         return;
     }
+    LongRing& ring = reinterpret_cast<LongRing*>(smem_raw)[warp];
     const unsigned char* __restrict__ img = M->image;
     const unsigned char* __restrict__ img_e = img + (size_t)kImgE * P;
     const unsigned char* __restrict__ img_v1 = img + (size_t)kImgV1 * P;
@@ -723,6 +741,35 @@ banded_long_kernel(const LongArgs a)
     double* __restrict__ carry = a.carry + slot * a.carry_stride;
     const int n_stripes = (n + H - 1) / H;
     const int last_word = (n + 15) / 16;
+    const int n_cblocks = P / B;                                   // P is a multiple of 16
+    const uint32_t w_ring = smem_u32(ring.w), e_ring = smem_u32(ring.e);
+
+    if (lane == 0)
+        for (int k = 0; k < 4; ++k) mbar_init(&ring.bar[k], 1);
+    __syncwarp();
+    uint32_t phase = 0;                                            // bit k: parity the next wait on slot k expects
+    auto wait_block = [&](int j) {
+        const int sl = j & 3;
+        mbar_wait(&ring.bar[sl], (phase >> sl) & 1u);
+        phase ^= 1u << sl;
+    };
+
+    // lane 0: queue the copies of column block j of the image into ring slot j & 3
+    auto issue_block = [&](int j) {
+        const int sl = j & 3;
+        const uint32_t bytes = (uint32_t)(B * 80 + 4 * B * 16) * (sl == 0 ? 2u : 1u);
+        mbar_expect_tx(&ring.bar[sl], bytes);
+        tma_bulk_g2s(&ring.w[(size_t)sl * B * 10], img + (size_t)j * B * 80, B * 80, &ring.bar[sl]);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            tma_bulk_g2s(&ring.e[x][(size_t)sl * B * 2], img_e + (size_t)x * 16 * P + (size_t)j * B * 16, B * 16, &ring.bar[sl]);
+        if (sl == 0) {                                              // the mirror behind slot 3
+            tma_bulk_g2s(&ring.w[(size_t)64 * 10], img + (size_t)j * B * 80, B * 80, &ring.bar[sl]);
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                tma_bulk_g2s(&ring.e[x][(size_t)64 * 2], img_e + (size_t)x * 16 * P + (size_t)j * B * 16, B * 16, &ring.bar[sl]);
+        }
+    };
 
     for (int s = 0; s < n_stripes; ++s) {
         const int rows = min(H, n - s * H);
@@ -732,104 +779,132 @@ banded_long_kernel(const LongArgs a)
         uint32_t symbits;
         {
             const int bit = 2 * (s * H + lane * RPL);
-            const int w = bit >> 5;
-            symbits = (w <= last_word) ? (pk[w] >> (bit & 31)) & 0xffffu : 0u;
+            const int w = bit >> 5, sh = bit & 31;
+            const uint32_t lo = (w <= last_word) ? pk[w] : 0u;
+            const uint32_t hi = (w + 1 <= last_word) ? pk[w + 1] : 0u;
+            symbits = __funnelshift_r(lo, hi, sh);
         }
-        size_t eoff[RPL];
+        uint32_t e_sym[RPL];                                        // ring address of e2[sym_j][slot 0]
 #pragma unroll
-        for (int j = 0; j < RPL; ++j) eoff[j] = (size_t)((symbits >> (2 * j)) & 3u) * 16u * P;
+        for (int j = 0; j < RPL; ++j) e_sym[j] = e_ring + ((symbits >> (2 * j)) & 3u) * (uint32_t)(kRingCols * 16);
+        const size_t v1_off = (size_t)(symbits & 3u) * 16u * P;
 
-        uint32_t* __restrict__ tbw = a.tbw + slot * a.tbw_stride + ((size_t)(s * 32 + lane) * P) * NW;
+        uint32_t* __restrict__ tbw = a.tbw + slot * a.tbw_stride + ((size_t)(s * 32 + lane) * P);
         uint16_t* __restrict__ acc_tb = a.acc_tb + slot * a.acc_stride + (size_t)s * H + lane * RPL;
 
         double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
 #pragma unroll
         for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; }
         double bI = kNegInf, bM = kNegInf, bD = kNegInf;
+        const bool first_row = (lane == 0 && s == 0);
+        const bool carried = (lane == 0 && s > 0);
+        const bool carry_out = (lane == 31 && !last_stripe);
 
-        if (s > 0) {                           // ring block 0 = carried values of columns 0..31
-#pragma unroll
-            for (int k = 0; k < 3; ++k) s_ring[warp][0][k][lane] = carry[(size_t)k * P + lane];
-        }
+        // prologue: column block 0 on its way, carried columns 0..15 staged
         __syncwarp();
+        if (lane == 0) issue_block(0);
+        if (s > 0 && lane < B) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ring.carry[0][k][lane] = carry[(size_t)k * P + lane];
+        }
 
         const int steps = NC + nl - 1;
-#pragma unroll 1
-        for (int t = 0; t < steps; ++t) {
-            if (s > 0 && (t & 31) == 0) {      // prefetch the next 32 carried columns
-                const int col = t + 32 + lane;
-                const int buf = ((t >> 5) + 1) & 1;
+        const int n_sblocks = (steps + B - 1) / B;
+        for (int sb = 0; sb < n_sblocks; ++sb) {
+            const int t0 = sb * B;
+            __syncwarp();                                           // every lane is done with the slot refilled next
+            if (sb + 1 < n_cblocks) {
+                if (lane == 0) issue_block(sb + 1);
+                if (s > 0 && lane < B) {
+                    const int col = (sb + 1) * B + lane;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) s_ring[warp][buf][k][lane] = (col < P) ? carry[(size_t)k * P + col] : kNegInf;
-                __syncwarp();
-            }
-            double uI0 = shfl_up_f64(cI[RPL - 1], 1);
-            double uM0 = shfl_up_f64(cM[RPL - 1], 1);
-            double uD0 = shfl_up_f64(cD[RPL - 1], 1);
-            const int c = t - lane;
-            if (c < 0 || c >= NC || lane >= nl) continue;
-            if (lane == 0 && s > 0) {
-                const int buf = (t >> 5) & 1;
-                uI0 = s_ring[warp][buf][0][t & 31];
-                uM0 = s_ring[warp][buf][1][t & 31];
-                uD0 = s_ring[warp][buf][2][t & 31];
-            }
-            const unsigned char* wp = img + (size_t)c * 80u;
-            const double2 w01 = ldg128(wp), w23 = ldg128(wp + 16), w45 = ldg128(wp + 32);
-            const double2 w67 = ldg128(wp + 48), w89 = ldg128(wp + 64);
-            const double wII = w01.x, wIM = w01.y, wID = w23.x, wMI = w23.y, wMM = w45.x, wMD = w45.y;
-            const double wDI = w67.x, wDM = w67.y, wDD = w89.x, aw = w89.y;
-            const size_t cb = (size_t)c * 16u;
-
-            double nM[RPL], nD[RPL], eIr[RPL];
-            uint32_t word[NW] = {0u, 0u};
-            static_for<0, RPL>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                const double2 e = ldg128(img_e + eoff[j] + cb);
-                eIr[j] = e.x;
-                const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-                nM[j] = max3_first<6 * (j % 5) + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
-                nD[j] = max3_first<6 * (j % 5) + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
-            });
-            const bool first_row = (lane == 0 && s == 0);
-            if (first_row) {
-                const double2 f = ldg128(img_v1 + eoff[0] + cb);
-                nM[0] = f.y;
-                eIr[0] = f.x;
-            }
-            if (c == acc_col) {
-#pragma unroll
-                for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
-            }
-            if (aw > kNegInf) {
-#pragma unroll
-                for (int j = 0; j < RPL; ++j) {
-                    const double cand = nD[j] + aw;
-                    if (cand > acc[j]) { acc[j] = cand; acc_tb[j] = (uint16_t)c; }   // stored as it changes (see banded_sweep)
+                    for (int k = 0; k < 3; ++k) ring.carry[(sb + 1) & 1][k][lane] = carry[(size_t)k * P + col];
                 }
             }
-            double uI = uI0, uM = uM0, uD = uD0;
-            static_for<0, RPL>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                double vI = max3_first<6 * (j % 5)>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
-                if (j == 0 && first_row) vI = eIr[0];
-                uI = vI; uM = nM[j]; uD = nD[j];
-                cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
-            });
-            bI = uI0; bM = uM0; bD = uD0;
-            reinterpret_cast<uint2*>(tbw)[c] = make_uint2(word[0], word[1]);
-            if (!last_stripe) {
-                if (lane == 31) {              // full stripe: lane 31 owns its last position
+            if (sb < n_cblocks) wait_block(sb);
+            __syncwarp();
+            // this lane's 16 consecutive ring slots (mirror: no wrap inside the block)
+            const uint32_t slot0 = (uint32_t)(t0 - lane) & 63u;
+            const uint32_t wa0 = w_ring + slot0 * 80u, eb0 = slot0 * 16u;
+            const double* cr = &ring.carry[sb & 1][0][0];
+
+            auto step = [&](const int i, auto guard_c) {
+                constexpr bool GUARD = decltype(guard_c)::value;
+                const int t = t0 + i;
+                double uI0 = shfl_up_f64(cI[RPL - 1], 1);
+                double uM0 = shfl_up_f64(cM[RPL - 1], 1);
+                double uD0 = shfl_up_f64(cD[RPL - 1], 1);
+                const int c = t - lane;
+                if (GUARD && (c < 0 || c >= NC || lane >= nl)) return;
+                if (carried) { uI0 = cr[i]; uM0 = cr[B + i]; uD0 = cr[2 * B + i]; }
+                const uint32_t wa = wa0 + (uint32_t)i * 80u;
+                const double2 w01 = lds128(wa), w23 = lds128(wa + 16), w45 = lds128(wa + 32);
+                const double2 w67 = lds128(wa + 48), w89 = lds128(wa + 64);
+                const double wII = w01.x, wIM = w01.y, wID = w23.x, wMI = w23.y, wMM = w45.x, wMD = w45.y;
+                const double wDI = w67.x, wDM = w67.y, wDD = w89.x, aw = w89.y;
+                const uint32_t cb = eb0 + (uint32_t)i * 16u;
+
+                double nM[RPL], nD[RPL], eIr[RPL];
+                uint32_t word = 0;
+                static_for<0, RPL>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    const double2 e = lds128(e_sym[j] + cb);       // {eI, eM}
+                    eIr[j] = e.x;
+                    const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
+                    nM[j] = max3_first<6 * j + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word);
+                    nD[j] = max3_first<6 * j + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word);
+                });
+                if (first_row) {
+                    const double2 f = ldg128(img_v1 + v1_off + (size_t)c * 16u);
+                    nM[0] = f.y;
+                    eIr[0] = f.x;
+                }
+                if (c == acc_col) {
+#pragma unroll
+                    for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
+                }
+                if (aw > kNegInf) {
+#pragma unroll
+                    for (int j = 0; j < RPL; ++j) {
+                        const double cand = nD[j] + aw;
+                        if (cand > acc[j]) { acc[j] = cand; acc_tb[j] = (uint16_t)c; }   // stored as it changes (see banded_sweep)
+                    }
+                }
+                double uI = uI0, uM = uM0, uD = uD0;
+                static_for<0, RPL>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    double vI = max3_first<6 * j>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word);
+                    if (j == 0 && first_row) vI = eIr[0];
+                    uI = vI; uM = nM[j]; uD = nD[j];
+                    cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
+                });
+                bI = uI0; bM = uM0; bD = uD0;
+                tbw[c] = word;
+                if (carry_out) {                                    // full stripe: lane 31 owns its last position
                     carry[c] = cI[RPL - 1]; carry[(size_t)P + c] = cM[RPL - 1]; carry[(size_t)2 * P + c] = cD[RPL - 1];
                 }
-            } else if (lane == ln) {
-                double fI = cI[0], fM = cM[0], fD = cD[0];
+                if (last_stripe && lane == ln) {
+                    double fI = cI[0], fM = cM[0], fD = cD[0];
 #pragma unroll
-                for (int j = 1; j < RPL; ++j)
-                    if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
-                vfin[c] = fI; vfin[(size_t)P + c] = fM; vfin[(size_t)2 * P + c] = fD;
+                    for (int j = 1; j < RPL; ++j)
+                        if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
+                    vfin[c] = fI; vfin[(size_t)P + c] = fM; vfin[(size_t)2 * P + c] = fD;
+                }
+            };
+            // steady blocks: every lane has a column at every step (lanes beyond the stripe's last row run
+            // along, as in banded_sweep); boundary blocks test per step
+            if (t0 >= 31 && t0 + B <= NC && t0 + B <= steps) {
+#pragma unroll 4
+                for (int i = 0; i < B; ++i) step(i, std::false_type{});
+            } else {
+                const int i_end = min(B, steps - t0);
+#pragma unroll 1
+                for (int i = 0; i < i_end; ++i) step(i, std::true_type{});
             }
         }
+        // a block queued beyond the last one this stripe waited for (the prefetch runs one block ahead of the
+        // steps; cannot happen while steps >= columns, kept for symmetry): drain it, every copy is waited for once
+        if (n_sblocks < n_cblocks) wait_block(n_sblocks);
         __syncwarp();
     }
 

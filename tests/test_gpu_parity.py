@@ -606,3 +606,32 @@ def test_locus_decoder_uses_read_length_flanks(ctx, read_length):
     # and the call site: the flank match-rate / recruitment decisions follow from those paths
     selected = dec.select_reads(reads[:40])
     assert len(selected) >= 30
+
+
+def test_config3_at_its_stated_size(ctx):
+    """BASELINE config 3 as stated: 60 bp repeat unit x 100 unrolled copies, 100 bp flanks, error rate 0.3
+    (18,918 states, 6,412 columns, 1.3 MB of tables: the striped long-read kernel with the per-warp TMA
+    ring), PacBio-like reads of 10-14 kb -- more repeat copies than the model unrolls, CLR-like errors --
+    against the CPU oracle: scores as bit patterns, whole state paths, repeat counts.  (The oracle needs
+    16 bytes per DP cell, 3-4 GB and a few seconds per read: two long reads, plus short and empty ones.)"""
+    from advntr_b200 import fast_compile, path_utils, synth
+    loc = synth.config3_locus()
+    model = fast_compile.get_read_matcher_model(loc.left, loc.right, loc.segments, loc.copies, error_rate=0.3)
+    dm = model._device_model()
+    assert dm.kind == "banded" and dm.info.n_states == 18918 and dm.info.smem_bytes > 227 * 1024
+    rng = random.Random(303)
+    reads = []
+    for copies in (170, 225):                      # ~10.5 kb and ~14 kb
+        reads.append(synth.sequencing_errors(rng, loc.left + loc.pattern * copies + loc.right, 0.02, 0.05, 0.05))
+    reads.append(synth.sequencing_errors(rng, loc.left + loc.pattern * 40 + loc.right, 0.02, 0.05, 0.05))   # spans, 40 copies
+    reads += [reads[0][:161], reads[1][:160], reads[1][5000:5321], ""]
+    assert 10000 <= len(reads[0]) <= 20000 and 10000 <= len(reads[1]) <= 20000
+    codes = [oracle.encode(r) for r in reads]
+    want_lp, want_paths = oracle.OracleModel(model.baked).viterbi(codes)
+    res = model.viterbi_batch(reads)
+    assert same_bits(res.logp, want_lp)
+    assert_paths_equal([res.path(i) for i in range(len(res))], want_paths, "config 3")
+    st = model.states
+    assert path_utils.get_number_of_repeats_in_vpath([(int(k), st[k]) for k in res.path(2)]) == 40
+    summ = model.viterbi_batch(reads, want_path=False, want_summary=True)
+    assert same_bits(summ.logp, want_lp) and summ.summaries["repeats"][2] == 40

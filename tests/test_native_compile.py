@@ -255,3 +255,33 @@ def test_many_batches_and_model_lifetimes():
     for _, dm in keep:
         dm.close()
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_shape_cache_clear_does_not_leave_stale_device_tables():
+    """Regression: the per-context structural tables were keyed by the address of the shape structure;
+    after advhmm_shape_cache_clear() a NEW structure could get the address of a dropped one and inherit
+    its (wrong) device tables."""
+    import oracle
+    ctx = engine.Context(device=0)
+    lib = engine.load_library()
+    rng = random.Random(8)
+    for rep in range(12):
+        ids = [rng.randrange(1, 5000) for _ in range(6)]
+        loci = [synth.config2_locus(i) for i in ids]
+        cols = engine.LociColumns.from_lists([l.left[-150:] for l in loci], [l.right[:150] for l in loci],
+                                             [l.segments for l in loci], [l.copies for l in loci], 0.05)
+        models = ctx.compile_loci(cols)
+        groups = [[oracle.encode(r) for r in synth.config2_reads(l, coverage=2, decoys=1)[0]] for l in loci]
+        res = ctx.viterbi_multi(models, groups, want_summary=True)
+        k = 0
+        for dm, codes in zip(models, groups):
+            lp, paths = oracle.OracleModel(dm.tables()).viterbi(codes)
+            assert same_bits(res.logp[k:k + len(codes)], lp), rep
+            for i, p in enumerate(paths):
+                assert np.array_equal(res.path(k + i), p), rep
+            k += len(codes)
+        for m in models:
+            m.close()
+        lib.advhmm_shape_cache_clear()
+    ctx.close()
