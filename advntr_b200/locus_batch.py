@@ -35,7 +35,11 @@ def reverse_complement(seq):
 class LocusDecoder(object):
     def __init__(self, left_flank, right_flank, repeat_segments, read_length=150, scaled_score=None,
                  error_rate=read_matcher.DEFAULT_MAX_ERROR_RATE, flank_size=None, locus_id=None,
-                 trained_hmms_dir=None):
+                 trained_hmms_dir=None, aligned_segments=None):
+        """``aligned_segments``: a multiple alignment of ``repeat_segments`` (equal-length strings over
+        ``ACGT-``).  The reference gets it from MUSCLE when the segments differ in length
+        (``profile_hmm.py:165-171``); MUSCLE is not part of this package, so a caller with such a locus
+        passes the alignment (equal-length segments are their own alignment)."""
         # get_vntr_matcher_hmm builds the matcher with flanking_region_size = read_length
         # (vntr_finder.py:131-132): a 100 bp or 250 bp library gets 100 / 250-base flank models
         if flank_size is None:
@@ -44,6 +48,11 @@ class LocusDecoder(object):
         self.id = locus_id
         self.left_flank, self.right_flank = left_flank, right_flank
         self.segments = list(repeat_segments)
+        if aligned_segments is not None:
+            aligned_segments = [a.upper() for a in aligned_segments]
+            if sorted(a.replace("-", "") for a in aligned_segments) != sorted(x.upper() for x in self.segments):
+                raise ValueError("aligned_segments is not an alignment of repeat_segments")
+        profile_rows = aligned_segments if aligned_segments is not None else self.segments
         self.pattern = self.segments[0]
         self.read_length = read_length
         self.scaled_score = scaled_score
@@ -59,12 +68,12 @@ class LocusDecoder(object):
             self.model = pomegranate.HiddenMarkovModel.from_json(stored)
             return
         if stored is not None:                       # the graph-level builder: only it can serialise
-            self.model = read_matcher.build_vntr_matcher_hmm(left_flank, right_flank, self.segments, copies,
+            self.model = read_matcher.build_vntr_matcher_hmm(left_flank, right_flank, profile_rows, copies,
                                                              flank_size=flank_size, error_rate=error_rate)
             with open(stored, "w") as outfile:
                 outfile.write(self.model.to_json())
             return
-        self.model = fast_compile.build_vntr_matcher_hmm(left_flank, right_flank, self.segments, copies,
+        self.model = fast_compile.build_vntr_matcher_hmm(left_flank, right_flank, profile_rows, copies,
                                                          flank_size=flank_size, error_rate=error_rate)
 
     # vntr_finder.py:174-177

@@ -32,13 +32,16 @@ class LocusSpec(object):
     """What ``ReferenceVNTR`` holds for one locus (``reference_vntr.py:7-40``)."""
 
     def __init__(self, locus_id, left_flank, right_flank, repeat_segments, scaled_score=None, chromosome=None,
-                 start_point=None):
+                 start_point=None, aligned_segments=None):
         self.id = int(locus_id)
         self.chromosome, self.start_point = chromosome, start_point   # only for genotype_alignment_file
         self.left_flank, self.right_flank = left_flank, right_flank
         self.repeat_segments = list(repeat_segments)
         self.pattern = self.repeat_segments[0]
         self.scaled_score = scaled_score
+        # multiple alignment of the repeat segments when they differ in length (what the reference asks
+        # MUSCLE for, profile_hmm.py:165-171); None: equal-length segments are their own alignment
+        self.aligned_segments = aligned_segments
 
 
 class GenotypingRun(object):
@@ -47,7 +50,8 @@ class GenotypingRun(object):
         self.read_length = read_length
         self.loci = list(loci)
         self.decoders = [LocusDecoder(l.left_flank, l.right_flank, l.repeat_segments, read_length,
-                                      scaled_score=l.scaled_score, locus_id=l.id) for l in self.loci]
+                                      scaled_score=l.scaled_score, locus_id=l.id,
+                                      aligned_segments=getattr(l, "aligned_segments", None)) for l in self.loci]
         # the models of all loci in ONE native call (profiles, parameter chains, device tables, upload)
         fast_compile.attach_device_models([d.model for d in self.decoders], self.ctx)
         keywords = [(l.id, sorted(keyword_filter.get_keywords_for_filtering(

@@ -182,6 +182,50 @@ def test_locus_model_can_become_a_full_model_on_the_host(hctx):
     legacy.close()
 
 
+def test_caller_supplied_alignment_equals_the_reference_tables():
+    """tests/golden/aligned.npz: the reference's own get_read_matcher_model on repeat segments of UNEQUAL
+    length, its MUSCLE wrapper answering with a fixed gapped alignment (make_golden_aligned.py).  The
+    native compiler and the literal builder, given that alignment, must reproduce the reference's tables."""
+    from conftest import Golden
+    g = Golden("aligned")
+    i = g.inputs
+    assert len(set(map(len, i["segments"]))) > 1 and any("-" in a for a in i["alignment"])
+    for build in (fast_compile.get_read_matcher_model, read_matcher.get_read_matcher_model):
+        m = build(i["left"], i["right"], i["alignment"], i["copies"], error_rate=i["error_rate"])
+        b = m.baked
+        assert [s.name for s in m.states] == g.names
+        assert np.array_equal(b["in_off"], g.baked["in_off"]) and np.array_equal(b["in_src"], g.baked["in_src"])
+        assert same_bits(b["in_logp"], g.baked["in_logp"]) and same_bits(b["emis"], g.baked["emis"])
+    with pytest.raises(ValueError, match="unequal length"):
+        fast_compile.get_read_matcher_model(i["left"], i["right"], i["segments"], i["copies"])
+
+
+@pytest.mark.gpu
+def test_locus_with_aligned_segments_end_to_end():
+    """The aligned-segment path through LocusDecoder and GenotypingRun on the device against the
+    reference's decode of the golden reads (scores as bit patterns, paths, repeat counts)."""
+    from conftest import Golden
+    from advntr_b200 import locus_batch, pipeline
+    g = Golden("aligned")
+    i = g.inputs
+    dec = locus_batch.LocusDecoder(i["left"], i["right"], i["segments"], read_length=150, aligned_segments=i["alignment"])
+    res = dec.model.viterbi_batch(g.reads, want_summary=True)
+    assert same_bits(res.logp, g.logp)
+    for k in range(len(g.reads)):
+        assert np.array_equal(res.path(k), g.path(k)), k
+    assert np.array_equal(res.summaries["repeats"], g.ru_count)
+    with pytest.raises(ValueError, match="not an alignment"):
+        locus_batch.LocusDecoder(i["left"], i["right"], i["segments"], aligned_segments=i["alignment"][:-1] + ["ACGT"])
+    reads = [r for r in g.reads if len(r) == 150]
+    run = pipeline.GenotypingRun([pipeline.LocusSpec(7, i["left"], i["right"], i["segments"],
+                                                     aligned_segments=i["alignment"])])
+    got = run.genotype({7: reads})[7]
+    want = dec.genotype(dec.select_reads(reads))
+    for key in ("copy_numbers", "recruited_reads_count", "spanning_reads_count", "flanking_reads_count"):
+        assert got[key] == want[key], key
+    run.close()
+
+
 @pytest.mark.gpu
 def test_locus_models_decode_on_device_like_descriptor_models_and_the_oracle():
     """Device side of the native route: tables written by all host threads into pinned staging, one
