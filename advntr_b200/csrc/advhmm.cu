@@ -785,7 +785,23 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         fam_long.items.swap(items);
         fam_long.model.swap(model);
     }
-    make_tiles(fam_long, kLongWarps, 1);
+    // long reads: `long_wpr` warps of a CTA share one read (its stripes are dealt round-robin).  One warp per
+    // read while the traceback of two CTAs of reads per SM fits in the workspace and the reads are short;
+    // more warps per read when a read has many stripes or few reads fit (a 20 kb read takes ~100 MB).
+    int long_wpr = 1;
+    if (!fam_long.items.empty()) {
+        const size_t stripes = ((size_t)std::max(fam_long.max_len, 1) + 32 * kLongRPL - 1) / (32 * kLongRPL);
+        const size_t per_read = stripes * 32 * (size_t)pl.max_P_long * 4;                    // traceback words
+        while (long_wpr < kLongWarps &&
+               (stripes >= (size_t)16 * long_wpr ||
+                per_read * (2 * kLongWarps / long_wpr) * (size_t)std::max(ctx->sm_count, 1) > ctx->workspace_budget))
+            long_wpr *= 2;
+        if (const char* env = getenv("ADVHMM_LONG_WPR")) {
+            const int v = atoi(env);
+            if (v == 1 || v == 2 || v == 4 || v == 8) long_wpr = v;
+        }
+    }
+    make_tiles(fam_long, kLongWarps / long_wpr, 1);
     make_tiles(fam_generic, gwarps, 2);
     const int n_short = (int)fam_short.items.size(), n_long = (int)fam_long.items.size();
     const int n_generic = (int)fam_generic.items.size();
@@ -855,9 +871,9 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     // i+1 is decoded
     if (ctx->mark_chunks && ctx->host_chunks > 1 && n_short >= ctx->host_chunks * 16384)
         s_chunk = std::min<size_t>(s_chunk, ((size_t)n_short + ctx->host_chunks - 1) / ctx->host_chunks);
-    size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)kLongWarps);
-    {   // whole waves: two CTAs of kLongWarps reads per SM
-        const size_t wave = (size_t)2 * kLongWarps * std::max(ctx->sm_count, 1);
+    size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)(kLongWarps / long_wpr));
+    {   // whole waves: two CTAs of kLongWarps / long_wpr reads per SM
+        const size_t wave = (size_t)2 * (kLongWarps / long_wpr) * std::max(ctx->sm_count, 1);
         if (l_chunk > wave && l_chunk < (size_t)n_long) l_chunk = l_chunk / wave * wave;
     }
     const size_t g_chunk = chunk_of(g_per_item, n_generic, (size_t)gwarps);
@@ -941,6 +957,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         la.vfin = reinterpret_cast<double*>(w + lo_vfin); la.vfin_stride = 3 * Pl;
         la.carry = reinterpret_cast<double*>(w + lo_carry); la.carry_stride = 3 * Pl;
         la.ftb = reinterpret_cast<int32_t*>(w + lo_ftb);
+        la.wpr = long_wpr;
         if (int rc = allow_max_dynamic_smem(ctx, banded_long_kernel)) return rc;
         {
             ProfScope prof(ctx, 0);

@@ -673,6 +673,11 @@ banded_fill_f32_kernel(const BandedArgs a)
 //     lane walks 16 consecutive ring slots from ((16 b - lane) & 63), and the first 16 slots are
 //     mirrored behind the 64th (the copy of every fourth column block is issued twice), so the walk
 //     never wraps.
+//   * a 20 kb read needs ~100 MB of traceback, so few reads can be in flight; the parallelism comes from
+//     INSIDE a read instead: `wpr` warps of a CTA share one read and take its stripes round-robin, each
+//     one trailing the warp that sweeps the stripe above by three 16-column blocks (it needs that
+//     stripe's last row).  The hand-over is the carry buffer; how far a stripe has got is published in
+//     shared memory by the lane that writes the carry (stores, fence, flag) and polled by the consumer.
 // =============================================================================================
 struct LongArgs {
     const Tile* tiles;
@@ -691,6 +696,7 @@ struct LongArgs {
     double* carry;              // per slot 3 * Pmax
     size_t carry_stride;
     int32_t* ftb;               // per slot 32
+    int32_t wpr;                // warps per read: 1, 2, 4 or 8 (the stripes of a read are dealt round-robin)
 };
 
 constexpr int kLongRPL = 5;
@@ -718,20 +724,36 @@ banded_long_kernel(const LongArgs a)
     constexpr int RPL = kLongRPL, H = 32 * RPL, B = kRingBlk;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_fval[kLongWarps][32];
+    __shared__ long long s_prog[kLongWarps];       // (stripe << 32 | carried columns written) of every warp
 
     const Tile tile = a.tiles[blockIdx.x];
     const DevBanded* __restrict__ M = reinterpret_cast<const DevBanded*>(tile.model);
     const int P = M->P, NC = M->NC, acc_col = M->acc_col;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp >= tile.cnt) return;
-    const int item = tile.first + warp;
+    const int wpr = a.wpr;
+    if (threadIdx.x < kLongWarps) s_prog[threadIdx.x] = -1;
+    __syncthreads();
+    const int rd = warp / wpr, sub = warp - rd * wpr;              // read of this CTA, position among its warps
+    if (rd >= tile.cnt) return;
+    const int item = tile.first + rd;
     const int q = a.order[item];
     const size_t slot = (size_t)(item - a.chunk_base);
     const int n = a.rlen[q];
     if (n == 0) {
-        if (lane == 0) a.logp[q] = M->logp_empty;
+        if (lane == 0 && sub == 0) a.logp[q] = M->logp_empty;
         return;
     }
+    volatile long long* prog = s_prog;
+    // the warp that sweeps the stripe above mine, and a wait until it has written `need` carried columns of it
+    const int pw = rd * wpr + (sub + wpr - 1) % wpr;
+    auto wait_carry = [&](int stripe_above, int need) {
+        if (lane == 0) {
+            const long long want = ((long long)stripe_above << 32) | (long long)need;
+            while (prog[pw] < want) __nanosleep(64);
+            __threadfence_block();
+        }
+        __syncwarp();
+    };
     LongRing& ring = reinterpret_cast<LongRing*>(smem_raw)[warp];
     const unsigned char* __restrict__ img = M->image;
     const unsigned char* __restrict__ img_e = img + (size_t)kImgE * P;
@@ -771,7 +793,7 @@ banded_long_kernel(const LongArgs a)
         }
     };
 
-    for (int s = 0; s < n_stripes; ++s) {
+    for (int s = sub; s < n_stripes; s += wpr) {
         const int rows = min(H, n - s * H);
         const int nl = (rows + RPL - 1) / RPL;
         const bool last_stripe = (s == n_stripes - 1);
@@ -803,9 +825,12 @@ banded_long_kernel(const LongArgs a)
         // prologue: column block 0 on its way, carried columns 0..15 staged
         __syncwarp();
         if (lane == 0) issue_block(0);
-        if (s > 0 && lane < B) {
+        if (s > 0) {
+            if (wpr > 1) wait_carry(s - 1, min(B, NC));
+            if (lane < B) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) ring.carry[0][k][lane] = carry[(size_t)k * P + lane];
+                for (int k = 0; k < 3; ++k) ring.carry[0][k][lane] = __ldcg(&carry[(size_t)k * P + lane]);
+            }
         }
 
         const int steps = NC + nl - 1;
@@ -815,10 +840,13 @@ banded_long_kernel(const LongArgs a)
             __syncwarp();                                           // every lane is done with the slot refilled next
             if (sb + 1 < n_cblocks) {
                 if (lane == 0) issue_block(sb + 1);
-                if (s > 0 && lane < B) {
-                    const int col = (sb + 1) * B + lane;
+                if (s > 0) {
+                    if (wpr > 1) wait_carry(s - 1, min((sb + 2) * B, NC));
+                    if (lane < B) {
+                        const int col = (sb + 1) * B + lane;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) ring.carry[(sb + 1) & 1][k][lane] = carry[(size_t)k * P + col];
+                        for (int k = 0; k < 3; ++k) ring.carry[(sb + 1) & 1][k][lane] = __ldcg(&carry[(size_t)k * P + col]);
+                    }
                 }
             }
             if (sb < n_cblocks) wait_block(sb);
@@ -901,6 +929,17 @@ banded_long_kernel(const LongArgs a)
 #pragma unroll 1
                 for (int i = 0; i < i_end; ++i) step(i, std::true_type{});
             }
+            // tell the warp below how many carried columns of this stripe are in memory: after step t lane 31
+            // has written columns 0 .. t - 31.  Published by the lane that wrote them: stores, fence, flag.
+            if (wpr > 1 && carry_out) {
+                const int done = min(max(t0 + B - 31, 0), NC);
+                __threadfence_block();
+                prog[warp] = ((long long)s << 32) | (long long)done;
+            }
+        }
+        if (wpr > 1 && carry_out) {
+            __threadfence_block();
+            prog[warp] = ((long long)s << 32) | (long long)NC;
         }
         // a block queued beyond the last one this stripe waited for (the prefetch runs one block ahead of the
         // steps; cannot happen while steps >= columns, kept for symmetry): drain it, every copy is waited for once
@@ -908,7 +947,8 @@ banded_long_kernel(const LongArgs a)
         __syncwarp();
     }
 
-    // final-only silent states on the last row
+    // final-only silent states on the last row: the warp that swept the last stripe holds it
+    if (sub != (n_stripes - 1) % wpr) return;
     const int NF = M->NF;
     int32_t* __restrict__ ftb = a.ftb + slot * 32;
     for (int f = 0; f < NF; ++f) {

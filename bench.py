@@ -95,7 +95,7 @@ def _synth_chunk(job):
 def build_workload(ids, coverage, decoys, generator="config2", procs=1):
     """Locus descriptions (the columns advhmm_models_create_for_loci takes) + reads of `ids`."""
     from advntr_b200 import engine
-    ids = list(ids)
+    ids = [int(i) for i in ids]
     if procs > 1 and len(ids) >= 512:
         import multiprocessing as mp
         step = max(64, (len(ids) + 4 * procs - 1) // (4 * procs))

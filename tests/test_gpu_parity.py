@@ -635,3 +635,29 @@ def test_config3_at_its_stated_size(ctx):
     assert path_utils.get_number_of_repeats_in_vpath([(int(k), st[k]) for k in res.path(2)]) == 40
     summ = model.viterbi_batch(reads, want_path=False, want_summary=True)
     assert same_bits(summ.logp, want_lp) and summ.summaries["repeats"][2] == 40
+
+
+@pytest.mark.parametrize("wpr", [1, 2, 4, 8])
+def test_long_read_kernel_with_every_warps_per_read_setting(ctx, wpr, monkeypatch):
+    """The striped long-read kernel deals the stripes of a read to 1, 2, 4 or 8 warps that trail each other
+    by three column blocks (carry hand-over through memory + progress flags).  Whatever the split, the
+    result is the oracle's: reads of 1 .. 23 stripes, fewer stripes than warps included."""
+    from advntr_b200 import engine, read_matcher, synth
+    monkeypatch.setenv("ADVHMM_LONG_WPR", str(wpr))
+    rng = random.Random(1000 + wpr)
+    ru = synth.rand_dna(rng, 41)
+    left, right = synth.rand_dna(rng, 100), synth.rand_dna(rng, 100)
+    model = read_matcher.get_read_matcher_model(left, right, [ru], 30, error_rate=0.3)
+    dm = engine.DeviceModel(ctx, model.baked)
+    assert dm.kind == "banded" and dm.info.smem_bytes > 227 * 1024
+    reads = []
+    for copies in (1, 3, 7, 12, 19, 30, 44, 80):
+        reads.append(synth.sequencing_errors(rng, left + ru * copies + right, 0.02, 0.05, 0.05))
+    reads += [reads[3][:159], reads[3][:160], reads[3][:161], reads[5][:321], "", "ACGT"]
+    codes = [oracle.encode(r) for r in reads]
+    lp, paths = oracle.OracleModel(model.baked).viterbi(codes)
+    for _ in range(2):                                   # twice: flags and rings start clean every launch
+        res = dm.viterbi(codes)
+        assert same_bits(res.logp, lp)
+        assert_paths_equal([res.path(i) for i in range(len(res))], paths, "wpr %d" % wpr)
+    dm.close()
