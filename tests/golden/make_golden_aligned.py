@@ -56,7 +56,8 @@ def inputs():
         s = rng.randrange(0, len(locus) - 150)
         reads.append(synth.sequencing_errors(rng, locus[s:s + 158], 0.01, 0.002, 0.002)[:150])
     reads += [synth.revcomp(r) for r in reads[3:11]]
-    return left, right, segments, alignment, 10, 0.05, reads
+    copies = int(round(150.0 / len(segments[0]) + 0.5))          # vntr_finder.py:98-99 for 150 bp reads
+    return left, right, segments, alignment, copies, 0.05, reads
 
 
 def main():
