@@ -352,13 +352,19 @@ def make_context(D):
     return ctx, stream
 
 
+def compile_threads():
+    """Host threads one rank gives to model compilation: its share of the box's cores."""
+    ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    return max(1, host_cores() // max(ranks_here, 1))
+
+
 def create_models(ctx, cols, lo=0, hi=None):
     """Raw advhmm_models_create_for_loci -> ctypes array of handles (no Python object per model)."""
     from advntr_b200 import engine
     hi = cols.n if hi is None else hi
     handles = (C.c_void_p * max(hi - lo, 1))()
     d = cols.desc(lo, hi)
-    engine._check(engine.load_library().advhmm_models_create_for_loci(ctx._h, C.byref(d), 0, handles))
+    engine._check(engine.load_library().advhmm_models_create_for_loci(ctx._h, C.byref(d), compile_threads(), handles))
     return handles
 
 
@@ -432,7 +438,7 @@ def run_ours(args):
     ctx, stream = make_context(D)
     lib = engine.load_library()
     t0 = time.time()
-    models = ctx.compile_loci(wl["cols"])                 # native: profiles, chains, device tables, upload
+    models = ctx.compile_loci(wl["cols"], n_threads=compile_threads())   # native: profiles, chains, device tables, upload
     t_compile = time.time() - t0
     stats = model_stats(models, wl)
     t_build = time.time() - t_build
@@ -677,7 +683,7 @@ def run_ours(args):
                 "warm": {"loci_per_s": loci_all / (warm_ms * 1e-3), "reads_per_s": reads_all / (warm_ms * 1e-3),
                          "ms_per_step": warm_ms, "compile_ms": pipeline["warm_compile_ms"],
                          "note": "shapes cached (a second sample of the same panel); models still compiled per step"},
-                "host_threads": host_cores()}
+                "host_threads": compile_threads()}
         if extra:
             ex = {}
             if "e2e_summary_ms" in extra:
