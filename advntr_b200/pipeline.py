@@ -138,33 +138,49 @@ class GenotypingRun(object):
         models = [d.model._device_model() for d in self.decoders]
         res = self.ctx._run(models, np.asarray(goff, dtype=np.int64), seqs, off, False, False, False, None,
                             want_summary=True)
-        S, logp = res.summaries, res.logp
         lens = (off[1:] - off[:-1]).astype(np.float64)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            right = np.where(S["right_bp"] > 0, S["right_hits"] / S["right_bp"].astype(np.float64), 1.0)
-            left = np.where(S["left_bp"] > 0, S["left_hits"] / S["left_bp"].astype(np.float64), 1.0)
-        rate = np.minimum(right, left)
-        possible = res.path_len >= 0
-        out = {}
-        for dec, (n_mapped, n_unm), a in zip(self.decoders, layout, goff[:-1]):
-            score = dec.min_score_to_select_a_read()
-            idx = np.arange(a, a + n_mapped)
-            if n_unm:                                   # the better strand of every unmapped read
-                f = a + n_mapped + 2 * np.arange(n_unm)
-                best = np.where(logp[f] < logp[f + 1], f + 1, f)
-                best = best[S["repeat_bp"][best] > dec.min_repeat_bp_to_add_read]
-                idx = np.concatenate([idx, best])
-            if score is not None:
-                ok = logp[idx] > score
-            else:
-                ok = (S["n_match"][idx] >= 0.9 * lens[idx]) & (logp[idx] > -lens[idx])
-            sel = idx[ok & (rate[idx] >= 0.9) & possible[idx]]
-            spanning = (rate[sel] >= 0.95) & (S["left_bp"][sel] > 5) & (S["right_bp"][sel] > 5)
-            covered = S["repeats"][sel][spanning].tolist()
-            flanking = [] if accuracy_filter else sorted(S["repeats"][sel][~spanning].tolist())
-            cn, prob = genotype.genotype_from_illumina_counts(covered, flanking, accuracy_filter, is_haploid)
-            kept = genotype._drop_unsupported(covered) if accuracy_filter else covered
-            out[dec.id] = {"copy_numbers": cn, "recruited_reads_count": int(len(sel)),
-                           "spanning_reads_count": len(kept), "flanking_reads_count": len(flanking),
-                           "maximum_likelihood": prob, "covered_repeats": covered, "flanking_repeats": flanking}
-        return out
+        calls = genotypes_from_summaries(res.logp, res.summaries, res.path_len, lens, goff, layout,
+                                         [d.min_score_to_select_a_read() for d in self.decoders],
+                                         accuracy_filter, is_haploid, self.decoders[0].min_repeat_bp_to_add_read
+                                         if self.decoders else 2)
+        return {dec.id: c for dec, c in zip(self.decoders, calls)}
+
+
+def genotypes_from_summaries(logp, S, path_len, lens, goff, layout, scores, accuracy_filter=False, is_haploid=False,
+                             min_repeat_bp=2):
+    """Recruitment (``recruit_read``, ``vntr_finder.py:179-190``), the better strand of every unmapped read
+    (``:235-254``), the spanning test (``:311-322``) and the genotype statistics (``:846-875``) of every locus
+    from the per-read device results: ``logp``, the on-device path summaries ``S`` (``advhmm_read_summary``
+    records), ``path_len`` (< 0: impossible read) and the read lengths.  ``layout[g]`` = (mapped reads,
+    unmapped reads) of locus g, whose reads start at ``goff[g]`` (mapped first, then both strands of every
+    unmapped read); ``scores[g]`` = its minimum Viterbi score or None.  -> one result dict per locus."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        right = np.where(S["right_bp"] > 0, S["right_hits"] / S["right_bp"].astype(np.float64), 1.0)
+        left = np.where(S["left_bp"] > 0, S["left_hits"] / S["left_bp"].astype(np.float64), 1.0)
+    rate = np.minimum(right, left)
+    possible = path_len >= 0
+    # everything that does not depend on the locus, for all reads at once
+    ok_no_score = (S["n_match"] >= 0.9 * lens) & (logp > -lens) & (rate >= 0.9) & possible
+    ok_rate = (rate >= 0.9) & possible
+    spanning_all = (rate >= 0.95) & (S["left_bp"] > 5) & (S["right_bp"] > 5)
+    repeats, repeat_bp = S["repeats"], S["repeat_bp"]
+    out = []
+    for (n_mapped, n_unm), a, score in zip(layout, goff[:-1], scores):
+        a = int(a)
+        idx = np.arange(a, a + n_mapped)
+        if n_unm:                                   # the better strand of every unmapped read
+            f = a + n_mapped + 2 * np.arange(n_unm)
+            best = np.where(logp[f] < logp[f + 1], f + 1, f)
+            best = best[repeat_bp[best] > min_repeat_bp]
+            idx = np.concatenate([idx, best])
+        keep = (logp[idx] > score) & ok_rate[idx] if score is not None else ok_no_score[idx]
+        sel = idx[keep]
+        spanning = spanning_all[sel]
+        covered = repeats[sel][spanning].tolist()
+        flanking = [] if accuracy_filter else sorted(repeats[sel][~spanning].tolist())
+        cn, prob = genotype.genotype_from_illumina_counts(covered, flanking, accuracy_filter, is_haploid)
+        kept = genotype._drop_unsupported(covered) if accuracy_filter else covered
+        out.append({"copy_numbers": cn, "recruited_reads_count": int(len(sel)),
+                    "spanning_reads_count": len(kept), "flanking_reads_count": len(flanking),
+                    "maximum_likelihood": prob, "covered_repeats": covered, "flanking_repeats": flanking})
+    return out

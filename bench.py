@@ -606,6 +606,18 @@ def run_ours(args):
         if ru64 is not None:
             ru32 = d_summ32[:, 0].cpu().numpy()
             extra["fp32_ru_concordance"] = float((ru32 == ru64).mean())
+        # what happens downstream of the summaries: recruitment, strand choice, spanning test, genotype
+        # statistics of every locus (host numpy / Python, one process; not part of any timed figure above)
+        if rank == 0:
+            from advntr_b200 import pipeline as _pl
+            decoys2 = 2 * args.decoys
+            layout = [(int(goff[g + 1] - goff[g]) - decoys2, args.decoys) for g in range(len(models))]
+            Sv = h_summ.numpy().view(engine.SUMMARY_DTYPE).reshape(-1)
+            tg = time.perf_counter()
+            calls = _pl.genotypes_from_summaries(h_logp.numpy(), Sv, h_plen.numpy(), np.diff(off).astype(np.float64),
+                                                 goff, layout, [None] * len(models))
+            extra["genotype_stage_loci_per_s"] = len(models) / (time.perf_counter() - tg)
+            extra["loci_with_a_genotype"] = sum(1 for c in calls if c["copy_numbers"] is not None)
         # pageable drop-in route: model.viterbi_batch(list of str) -> (logp, paths) per locus, Python objects
         if rank == 0:
             from advntr_b200 import fast_compile
@@ -698,6 +710,11 @@ def run_ours(args):
                                    "note": "optional ADVHMM_FP32 mode, device-resident, full paths; tolerance "
                                            "|dlogp| <= 2e-5 |logp| + 2e-5 (tests/test_gpu_parity.py::test_fp32_mode); "
                                            "ru_concordance = share of reads whose repeat count equals the fp64 one"}
+            if "genotype_stage_loci_per_s" in extra:
+                ex["genotype_stage"] = {"value": extra["genotype_stage_loci_per_s"], "unit": "loci/s",
+                                        "loci_with_a_genotype": extra["loci_with_a_genotype"],
+                                        "note": "pipeline.genotypes_from_summaries on the summaries of all loci: recruitment, "
+                                                "strand choice, spanning test, genotype likelihoods (host numpy / Python, one process)"}
             if "pageable_reads_per_s" in extra:
                 ex["pageable_python_route"] = {"value": extra["pageable_reads_per_s"], "unit": "reads/s",
                                                "loci": extra["pageable_loci"],
@@ -778,11 +795,18 @@ class ShardRunner(object):
         goff, off = wl["group_off"], wl["seq_off"]
         flags = engine.DEVICE_BUFFERS | engine.WANT_SUMMARY
         chunk = chunk_loci if (compile_in_region and chunk_loci > 0) else n_loci
+        # chunk boundaries: the first chunks are small (1/8, 1/4, 1/2 of a chunk), because nothing runs on
+        # the device while the first one is compiled
+        bounds, lo = [0], 0
+        ramp = [8, 4, 2] if (compile_in_region and 0 < chunk < n_loci) else []
+        while lo < n_loci:
+            size = max(chunk // ramp.pop(0), 64) if ramp else max(chunk, 1)
+            lo = min(n_loci, lo + size)
+            bounds.append(lo)
         compile_ms, prev = 0.0, None
         self.e0.record(self.stream)
         self.d_seqs.copy_(self.h_seqs, non_blocking=True)
-        for lo in range(0, n_loci, max(chunk, 1)):
-            hi = min(n_loci, lo + chunk)
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
             if compile_in_region:
                 tc = time.perf_counter()
                 hs = create_models(ctx, wl["cols"], lo, hi)         # the device keeps decoding the previous chunk
