@@ -760,6 +760,10 @@ struct LongArgs {
     int32_t wpr;                // warps per read: 1, 2, 4 or 8 (the stripes of a read are dealt round-robin)
 };
 
+#ifndef ADV_LONG_UNROLL
+#define ADV_LONG_UNROLL 4      // unroll factor of the steady 16-step blocks of banded_long_kernel
+#endif
+constexpr int kLongUnroll = ADV_LONG_UNROLL;
 constexpr int kLongRPL = 5;
 constexpr int kLongWarps = 8;
 constexpr int kRingBlk = 16;                       // columns per TMA refill
@@ -854,10 +858,12 @@ banded_long_kernel(const LongArgs a)
         }
     };
 
-    for (int s = sub; s < n_stripes; s += wpr) {
+    // One stripe.  FIRST / LAST are compile-time: the middle stripes of a read -- all but two of ~100 -- carry
+    // neither the first-row override nor the last-row stores through their column loop.
+    auto sweep_stripe = [&](const int s, auto first_c, auto last_c) {
+        constexpr bool FIRST = decltype(first_c)::value, LAST = decltype(last_c)::value;
         const int rows = min(H, n - s * H);
         const int nl = (rows + RPL - 1) / RPL;
-        const bool last_stripe = (s == n_stripes - 1);
         const int ln = (rows - 1) / RPL, jn = (rows - 1) % RPL;
         uint32_t symbits;
         {
@@ -867,26 +873,34 @@ banded_long_kernel(const LongArgs a)
             const uint32_t hi = (w + 1 <= last_word) ? pk[w + 1] : 0u;
             symbits = __funnelshift_r(lo, hi, sh);
         }
-        uint32_t e_sym[RPL];                                        // ring address of e2[sym_j][slot 0]
+        // ring address of e2[sym_j][slot of my column at the start of the current block]; moved on by 16 slots
+        // (mod 64) from block to block
+        uint32_t e_blk[RPL];
+        const uint32_t slot_init = (uint32_t)(0 - lane) & 63u;
 #pragma unroll
-        for (int j = 0; j < RPL; ++j) e_sym[j] = e_ring + ((symbits >> (2 * j)) & 3u) * (uint32_t)(kRingCols * 16);
+        for (int j = 0; j < RPL; ++j)
+            e_blk[j] = e_ring + ((symbits >> (2 * j)) & 3u) * (uint32_t)(kRingCols * 16) + slot_init * 16u;
+        uint32_t w_blk = w_ring + slot_init * 80u;
+        uint32_t slot0 = slot_init;
         const size_t v1_off = (size_t)(symbits & 3u) * 16u * P;
 
-        uint32_t* __restrict__ tbw = a.tbw + slot * a.tbw_stride + ((size_t)(s * 32 + lane) * P);
+        uint32_t* tbw_t = a.tbw + slot * a.tbw_stride + ((size_t)(s * 32 + lane) * P) - lane;   // index with the step t
         uint16_t* __restrict__ acc_tb = a.acc_tb + slot * a.acc_stride + (size_t)s * H + lane * RPL;
+        double* carry_t = carry - 31;                               // lane 31 writes column t - 31: index with t
+        asm volatile("" : "+l"(tbw_t), "+l"(carry_t));
 
         double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
 #pragma unroll
         for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; }
         double bI = kNegInf, bM = kNegInf, bD = kNegInf;
-        const bool first_row = (lane == 0 && s == 0);
-        const bool carried = (lane == 0 && s > 0);
-        const bool carry_out = (lane == 31 && !last_stripe);
+        const bool first_row = FIRST && lane == 0;
+        const bool carried = !FIRST && lane == 0;
+        const bool carry_out = !LAST && lane == 31;
 
         // prologue: column block 0 on its way, carried columns 0..15 staged
         __syncwarp();
         if (lane == 0) issue_block(0);
-        if (s > 0) {
+        if (!FIRST) {
             if (wpr > 1) wait_carry(s - 1, min(B, NC));
             if (lane < B) {
 #pragma unroll
@@ -901,7 +915,7 @@ banded_long_kernel(const LongArgs a)
             __syncwarp();                                           // every lane is done with the slot refilled next
             if (sb + 1 < n_cblocks) {
                 if (lane == 0) issue_block(sb + 1);
-                if (s > 0) {
+                if (!FIRST) {
                     if (wpr > 1) wait_carry(s - 1, min((sb + 2) * B, NC));
                     if (lane < B) {
                         const int col = (sb + 1) * B + lane;
@@ -912,9 +926,6 @@ banded_long_kernel(const LongArgs a)
             }
             if (sb < n_cblocks) wait_block(sb);
             __syncwarp();
-            // this lane's 16 consecutive ring slots (mirror: no wrap inside the block)
-            const uint32_t slot0 = (uint32_t)(t0 - lane) & 63u;
-            const uint32_t wa0 = w_ring + slot0 * 80u, eb0 = slot0 * 16u;
             const double* cr = &ring.carry[sb & 1][0][0];
 
             auto step = [&](const int i, auto guard_c) {
@@ -925,25 +936,25 @@ banded_long_kernel(const LongArgs a)
                 double uD0 = shfl_up_f64(cD[RPL - 1], 1);
                 const int c = t - lane;
                 if (GUARD && (c < 0 || c >= NC || lane >= nl)) return;
-                if (carried) { uI0 = cr[i]; uM0 = cr[B + i]; uD0 = cr[2 * B + i]; }
-                const uint32_t wa = wa0 + (uint32_t)i * 80u;
+                if (!FIRST && carried) { uI0 = cr[i]; uM0 = cr[B + i]; uD0 = cr[2 * B + i]; }
+                // this lane's 16 consecutive ring slots of the block (mirror: no wrap inside the block)
+                const uint32_t wa = w_blk + (uint32_t)i * 80u;
                 const double2 w01 = lds128(wa), w23 = lds128(wa + 16), w45 = lds128(wa + 32);
                 const double2 w67 = lds128(wa + 48), w89 = lds128(wa + 64);
                 const double wII = w01.x, wIM = w01.y, wID = w23.x, wMI = w23.y, wMM = w45.x, wMD = w45.y;
                 const double wDI = w67.x, wDM = w67.y, wDD = w89.x, aw = w89.y;
-                const uint32_t cb = eb0 + (uint32_t)i * 16u;
 
                 double nM[RPL], nD[RPL], eIr[RPL];
                 uint32_t word = 0;
                 static_for<0, RPL>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    const double2 e = lds128(e_sym[j] + cb);       // {eI, eM}
+                    const double2 e = lds128(e_blk[j] + (uint32_t)i * 16u);       // {eI, eM}
                     eIr[j] = e.x;
                     const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
                     nM[j] = max3_first<6 * j + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word);
                     nD[j] = max3_first<6 * j + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word);
                 });
-                if (first_row) {
+                if (FIRST && first_row) {
                     const double2 f = ldg128(img_v1 + v1_off + (size_t)c * 16u);
                     nM[0] = f.y;
                     eIr[0] = f.x;
@@ -963,16 +974,16 @@ banded_long_kernel(const LongArgs a)
                 static_for<0, RPL>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     double vI = max3_first<6 * j>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word);
-                    if (j == 0 && first_row) vI = eIr[0];
+                    if (FIRST && j == 0 && first_row) vI = eIr[0];
                     uI = vI; uM = nM[j]; uD = nD[j];
                     cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
                 });
                 bI = uI0; bM = uM0; bD = uD0;
-                tbw[c] = word;
-                if (carry_out) {                                    // full stripe: lane 31 owns its last position
-                    carry[c] = cI[RPL - 1]; carry[(size_t)P + c] = cM[RPL - 1]; carry[(size_t)2 * P + c] = cD[RPL - 1];
+                tbw_t[t] = word;
+                if (!LAST && carry_out) {                           // full stripe: lane 31 owns its last position
+                    carry_t[t] = cI[RPL - 1]; carry_t[(size_t)P + t] = cM[RPL - 1]; carry_t[(size_t)2 * P + t] = cD[RPL - 1];
                 }
-                if (last_stripe && lane == ln) {
+                if (LAST && lane == ln) {
                     double fI = cI[0], fM = cM[0], fD = cD[0];
 #pragma unroll
                     for (int j = 1; j < RPL; ++j)
@@ -983,22 +994,32 @@ banded_long_kernel(const LongArgs a)
             // steady blocks: every lane has a column at every step (lanes beyond the stripe's last row run
             // along, as in banded_sweep); boundary blocks test per step
             if (t0 >= 31 && t0 + B <= NC && t0 + B <= steps) {
-#pragma unroll 4
+#pragma unroll (kLongUnroll)
                 for (int i = 0; i < B; ++i) step(i, std::false_type{});
             } else {
                 const int i_end = min(B, steps - t0);
 #pragma unroll 1
                 for (int i = 0; i < i_end; ++i) step(i, std::true_type{});
             }
+            // the next block starts 16 ring slots further on (mod 64)
+            {
+                const bool wrap = slot0 + B >= 64u;
+                const uint32_t dw = wrap ? (uint32_t)(B * 80) - 64u * 80u : (uint32_t)(B * 80);
+                const uint32_t de = wrap ? (uint32_t)(B * 16) - 64u * 16u : (uint32_t)(B * 16);
+                slot0 = (slot0 + B) & 63u;
+                w_blk += dw;
+#pragma unroll
+                for (int j = 0; j < RPL; ++j) e_blk[j] += de;
+            }
             // tell the warp below how many carried columns of this stripe are in memory: after step t lane 31
             // has written columns 0 .. t - 31.  Published by the lane that wrote them: stores, fence, flag.
-            if (wpr > 1 && carry_out) {
+            if (!LAST && wpr > 1 && carry_out) {
                 const int done = min(max(t0 + B - 31, 0), NC);
                 __threadfence_block();
                 prog[warp] = ((long long)s << 32) | (long long)done;
             }
         }
-        if (wpr > 1 && carry_out) {
+        if (!LAST && wpr > 1 && carry_out) {
             __threadfence_block();
             prog[warp] = ((long long)s << 32) | (long long)NC;
         }
@@ -1006,6 +1027,13 @@ banded_long_kernel(const LongArgs a)
         // steps; cannot happen while steps >= columns, kept for symmetry): drain it, every copy is waited for once
         if (n_sblocks < n_cblocks) wait_block(n_sblocks);
         __syncwarp();
+    };
+    for (int s = sub; s < n_stripes; s += wpr) {
+        const bool first = (s == 0), last = (s == n_stripes - 1);
+        if (first && last) sweep_stripe(s, std::true_type{}, std::true_type{});
+        else if (first) sweep_stripe(s, std::true_type{}, std::false_type{});
+        else if (last) sweep_stripe(s, std::false_type{}, std::true_type{});
+        else sweep_stripe(s, std::false_type{}, std::false_type{});
     }
 
     // final-only silent states on the last row: the warp that swept the last stripe holds it

@@ -24,12 +24,18 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <cstring>
+#include <exception>
 #include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
 #include <tuple>
+
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 #include "model_compile.hpp"
 

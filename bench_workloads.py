@@ -301,7 +301,7 @@ def run_frameshift(args):
         py_calls.append(dec.frameshift_candidate(selected)[0])
     py_s = time.perf_counter() - tp
     # the same host logic on CPU-oracle paths, first loci (outside every timed region)
-    n_or = min(args.oracle_loci if args.oracle_loci > 0 else 0, len(loci))
+    n_or = min(3 * args.oracle_loci if args.oracle_loci > 0 else 0, len(loci))     # ~0.5 s of CPU oracle per locus
     oracle_same = None
     if n_or and D.rank == 0:
         oracle = _oracle()
