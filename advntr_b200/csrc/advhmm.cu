@@ -792,9 +792,12 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     if (!fam_long.items.empty()) {
         const size_t stripes = ((size_t)std::max(fam_long.max_len, 1) + 32 * kLongRPL - 1) / (32 * kLongRPL);
         const size_t per_read = stripes * 32 * (size_t)pl.max_P_long * 4;                    // traceback words
+        const size_t sms = (size_t)std::max(ctx->sm_count, 1);
+        // (a) two CTAs of reads per SM must fit in the workspace; (b) few reads (a PacBio locus has tens of
+        // spanning reads): more warps per read fill the warp slots the missing reads leave empty
         while (long_wpr < kLongWarps &&
-               (stripes >= (size_t)16 * long_wpr ||
-                per_read * (2 * kLongWarps / long_wpr) * (size_t)std::max(ctx->sm_count, 1) > ctx->workspace_budget))
+               (per_read * (2 * kLongWarps / long_wpr) * sms > ctx->workspace_budget ||
+                (fam_long.items.size() * (size_t)long_wpr < 2 * kLongWarps * sms && stripes >= (size_t)4 * long_wpr)))
             long_wpr *= 2;
         if (const char* env = getenv("ADVHMM_LONG_WPR")) {
             const int v = atoi(env);
@@ -855,7 +858,9 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     const size_t stripes_max = n_long ? ((size_t)std::max(fam_long.max_len, 1) + 32 * kLongRPL - 1) / (32 * kLongRPL) : 0;
     const size_t l_tbw_words = stripes_max * 32 * Pl;
     const size_t l_acc = stripes_max * 32 * kLongRPL;
-    const size_t l_per_item = n_long ? l_tbw_words * 4 + 6 * Pl * 8 + l_acc * 2 + 32 * 4 : 0;
+    // (+ one path-sized scratch region per read: the backtrack of a long read walks once, not twice)
+    const size_t l_scratch = (want_path && n_long) ? ((size_t)fam_long.max_len + 3 * Pl + 64) : 0;
+    const size_t l_per_item = n_long ? l_tbw_words * 4 + 6 * Pl * 8 + l_acc * 2 + 32 * 4 + l_scratch * 4 : 0;
     const size_t gm = (size_t)pl.max_m_generic;
     const size_t g_tb_per = (want_walk && n_generic) ? (size_t)std::max(fam_generic.max_len, 1) * gm * sizeof(uint16_t) : 0;
     const size_t g_rows_per = (n_generic && !rows_in_smem) ? 2 * gm * sizeof(double) : 0;
@@ -884,7 +889,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     // long layout
     const size_t lo_tbw = 0, lo_vfin = al(l_chunk * l_tbw_words * 4), lo_carry = lo_vfin + al(l_chunk * 3 * Pl * 8);
     const size_t lo_acc = lo_carry + al(l_chunk * 3 * Pl * 8), lo_ftb = lo_acc + al(l_chunk * l_acc * 2);
-    const size_t l_bytes = lo_ftb + al(l_chunk * 32 * 4);
+    const size_t lo_scratch = lo_ftb + al(l_chunk * 32 * 4);
+    const size_t l_bytes = lo_scratch + al(l_chunk * l_scratch * 4);
     // generic layout
     const size_t go_tb = 0, go_rows = al(g_chunk * g_tb_per);
     const size_t g_bytes = go_rows + al(g_chunk * g_rows_per);
@@ -904,8 +910,10 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         return hi;
     };
     auto launch_backtrack = [&](int lo, int items, int bt_rpl, const uint32_t* tbw, size_t tbw_stride,
-                                const uint16_t* acc, size_t acc_stride, const int32_t* ftb) -> int {
+                                const uint16_t* acc, size_t acc_stride, const int32_t* ftb,
+                                int32_t* scratch = nullptr, int64_t scratch_stride = 0) -> int {
         BandedBtArgs ba{};
+        ba.scratch = scratch; ba.scratch_stride = scratch_stride;
         ba.tiles = d_tiles; ba.order = d_order; ba.chunk_base = lo; ba.n_items = items; ba.rpl = bt_rpl;
         ba.fp32 = fp32 ? 1 : 0;
         ba.pk = d_pk; ba.pk_off = d_pk_off; ba.rlen = d_rlen; ba.logp = out.logp;
@@ -966,7 +974,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         CU_TRY(cudaGetLastError());
         ctx->launches++;
         if (want_walk) {
-            int rc = launch_backtrack(lo, hi - lo, kLongRPL, la.tbw, la.tbw_stride, la.acc_tb, la.acc_stride, la.ftb);
+            int rc = launch_backtrack(lo, hi - lo, kLongRPL, la.tbw, la.tbw_stride, la.acc_tb, la.acc_stride, la.ftb,
+                                      l_scratch ? reinterpret_cast<int32_t*>(w + lo_scratch) : nullptr, (int64_t)l_scratch);
             if (rc) return rc;
             if (want_path && (rc = mark_chunk(ctx, out.cursor))) return rc;
         }

@@ -761,7 +761,7 @@ struct LongArgs {
 };
 
 #ifndef ADV_LONG_UNROLL
-#define ADV_LONG_UNROLL 4      // unroll factor of the steady 16-step blocks of banded_long_kernel
+#define ADV_LONG_UNROLL 2      // unroll factor of the steady 16-step blocks of banded_long_kernel (4: -4 %, the loop outgrows the instruction cache)
 #endif
 constexpr int kLongUnroll = ADV_LONG_UNROLL;
 constexpr int kLongRPL = 5;
@@ -1133,6 +1133,10 @@ struct BandedBtArgs {
     int64_t path_cap;
     unsigned long long* cursor; // total path entries
     advhmm_read_summary* summaries;   // NULL or [n_out]
+    // long reads: the walk is a serial pointer chase of n + columns steps; instead of walking twice (count,
+    // then write) the states of the first walk are kept here, per work item, and copied out
+    int32_t* scratch;           // NULL or n_items * scratch_stride entries
+    int64_t scratch_stride;
 };
 
 template <typename Emit>
@@ -1198,7 +1202,19 @@ __global__ void __launch_bounds__(128) banded_backtrack_kernel(const BandedBtArg
         M = reinterpret_cast<const DevBanded*>(a.tiles[a.item_tile[item]].model);
         n = a.rlen[q];
         possible = a.logp[q] > kNegInf;
-        if (possible) {
+        if (possible && a.scratch && a.path) {
+            // one walk: states land at the END of this item's scratch region, in path order
+            if (n > 0) sym0 = packed_sym(a.pk + a.pk_off[q], 0);
+            int32_t* __restrict__ sc = a.scratch + (size_t)i * a.scratch_stride;
+            const int64_t cap = a.scratch_stride;
+            if (a.summaries) {
+                PathReducer red(M->classes, a.pk + a.pk_off[q], n);
+                banded_walk(M, a, slot, n, sym0, [&](int s) { if (len < cap) sc[cap - 1 - len] = s; ++len; red.visit(s); });
+                red.store(a.summaries + q);
+            } else {
+                banded_walk(M, a, slot, n, sym0, [&](int s) { if (len < cap) sc[cap - 1 - len] = s; ++len; });
+            }
+        } else if (possible) {
             if (n > 0) sym0 = packed_sym(a.pk + a.pk_off[q], 0);
             if (a.summaries) {
                 // the walk starts at the model's end state and finishes at its start state; like
@@ -1238,6 +1254,12 @@ __global__ void __launch_bounds__(128) banded_backtrack_kernel(const BandedBtArg
     if (off + len > a.path_cap) { a.path_len[q] = -2; return; }   // caller buffer too small
     a.path_len[q] = len;
     int32_t* out = a.path + off;
+    if (a.scratch && len <= a.scratch_stride) {
+        const int32_t* __restrict__ sc = a.scratch + (size_t)i * a.scratch_stride + (a.scratch_stride - len);
+#pragma unroll 4
+        for (int k = 0; k < len; ++k) out[k] = sc[k];
+        return;
+    }
     int w = len;
     banded_walk(M, a, slot, n, sym0, [&](int s) { out[--w] = s; });
 }
