@@ -522,8 +522,8 @@ template <typename T> size_t vec_bytes(const std::vector<T>& v) { return v.size(
 
 // event pair bracketing one kernel launch when profiling is on (kind: 0 banded fill, 1 backtrack)
 struct ProfScope {
-    advhmm_context* ctx; int kind; cudaEvent_t stop = nullptr;
-    ProfScope(advhmm_context* c, int k) : ctx(c), kind(k)
+    advhmm_context* ctx; int kind; cudaEvent_t stop = nullptr; cudaStream_t stream;
+    ProfScope(advhmm_context* c, int k, cudaStream_t st = nullptr) : ctx(c), kind(k), stream(st ? st : c->stream)
     {
         if (!ctx->profile) return;
         auto& ev = ctx->prof_events[kind];
@@ -533,10 +533,10 @@ struct ProfScope {
             ev.emplace_back(a, b);
         }
         auto& pr = ev[ctx->prof_used[kind]++];
-        cudaEventRecord(pr.first, ctx->stream);
+        cudaEventRecord(pr.first, stream);
         stop = pr.second;
     }
-    ~ProfScope() { if (stop) cudaEventRecord(stop, ctx->stream); }
+    ~ProfScope() { if (stop) cudaEventRecord(stop, stream); }
 };
 
 // Dynamic shared memory above 48 KB needs an opt-in that is a property of the KERNEL (per device),
@@ -639,8 +639,9 @@ constexpr size_t kMaxChunkMarks = 4096;
 
 // after a backtrack launch: snapshot the path cursor and record an event, so that the host-buffer
 // front end can start copying this chunk's paths while the next chunk runs
-int mark_chunk(advhmm_context* ctx, const unsigned long long* d_cursor)
+int mark_chunk(advhmm_context* ctx, const unsigned long long* d_cursor, cudaStream_t stream = nullptr)
 {
+    if (!stream) stream = ctx->stream;
     if (!ctx->mark_chunks || ctx->n_marks >= kMaxChunkMarks) return ADVHMM_OK;
     const size_t i = ctx->n_marks;
     if (i == ctx->chunk_events.size()) {
@@ -649,8 +650,8 @@ int mark_chunk(advhmm_context* ctx, const unsigned long long* d_cursor)
         ctx->chunk_events.push_back(ev);
     }
     CU_TRY(cudaMemcpyAsync(static_cast<unsigned long long*>(ctx->h_cursors.p) + i, d_cursor, sizeof(unsigned long long),
-                           cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaEventRecord(ctx->chunk_events[i], ctx->stream));
+                           cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaEventRecord(ctx->chunk_events[i], stream));
     ctx->n_marks = i + 1;
     return ADVHMM_OK;
 }
@@ -793,10 +794,15 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         const size_t stripes = ((size_t)std::max(fam_long.max_len, 1) + 32 * kLongRPL - 1) / (32 * kLongRPL);
         const size_t per_read = stripes * 32 * (size_t)pl.max_P_long * 4;                    // traceback words
         const size_t sms = (size_t)std::max(ctx->sm_count, 1);
-        // (a) two CTAs of reads per SM must fit in the workspace; (b) few reads (a PacBio locus has tens of
-        // spanning reads): more warps per read fill the warp slots the missing reads leave empty
+        // (a) two CTAs of reads per SM must fit in the workspace -- with room to spare: a launch of several
+        // waves of CTAs (reads are ordered longest-first) back-fills the SMs whose reads finish early, a
+        // launch of one wave lasts as long as its longest read (measured on 10-20 kb reads, 1,184 per step:
+        // 8 warps per read 1,107 GCUPS, 4: 1,039, 2: 662; profiles/r2_long_kernel.md), hence also (b): reads
+        // of many stripes always get more warps; (c) few reads (a PacBio locus has tens of spanning reads):
+        // more warps per read fill the warp slots the missing reads leave empty
         while (long_wpr < kLongWarps &&
                (per_read * (2 * kLongWarps / long_wpr) * sms > ctx->workspace_budget ||
+                stripes >= (size_t)16 * long_wpr ||
                 (fam_long.items.size() * (size_t)long_wpr < 2 * kLongWarps * sms && stripes >= (size_t)4 * long_wpr)))
             long_wpr *= 2;
         if (const char* env = getenv("ADVHMM_LONG_WPR")) {
@@ -877,6 +883,11 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     if (ctx->mark_chunks && ctx->host_chunks > 1 && n_short >= ctx->host_chunks * 16384)
         s_chunk = std::min<size_t>(s_chunk, ((size_t)n_short + ctx->host_chunks - 1) / ctx->host_chunks);
     size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)(kLongWarps / long_wpr));
+    // Long reads that do not fit in one chunk: the workspace is cut in two halves, the backtrack of chunk k
+    // (a serial pointer chase per read, ~10 % of the fill time) runs on a second stream while chunk k+1 is
+    // filled into the other half.
+    const bool l_double = want_walk && l_chunk < (size_t)n_long && ctx->device >= 0;
+    if (l_double) l_chunk = std::max<size_t>(chunk_of(2 * l_per_item, n_long, (size_t)(kLongWarps / long_wpr)), 1);
     {   // whole waves: two CTAs of kLongWarps / long_wpr reads per SM
         const size_t wave = (size_t)2 * (kLongWarps / long_wpr) * std::max(ctx->sm_count, 1);
         if (l_chunk > wave && l_chunk < (size_t)n_long) l_chunk = l_chunk / wave * wave;
@@ -890,7 +901,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     const size_t lo_tbw = 0, lo_vfin = al(l_chunk * l_tbw_words * 4), lo_carry = lo_vfin + al(l_chunk * 3 * Pl * 8);
     const size_t lo_acc = lo_carry + al(l_chunk * 3 * Pl * 8), lo_ftb = lo_acc + al(l_chunk * l_acc * 2);
     const size_t lo_scratch = lo_ftb + al(l_chunk * 32 * 4);
-    const size_t l_bytes = lo_scratch + al(l_chunk * l_scratch * 4);
+    const size_t l_half = lo_scratch + al(l_chunk * l_scratch * 4);
+    const size_t l_bytes = l_double ? 2 * l_half : l_half;
     // generic layout
     const size_t go_tb = 0, go_rows = al(g_chunk * g_tb_per);
     const size_t g_bytes = go_rows + al(g_chunk * g_rows_per);
@@ -911,7 +923,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     };
     auto launch_backtrack = [&](int lo, int items, int bt_rpl, const uint32_t* tbw, size_t tbw_stride,
                                 const uint16_t* acc, size_t acc_stride, const int32_t* ftb,
-                                int32_t* scratch = nullptr, int64_t scratch_stride = 0) -> int {
+                                int32_t* scratch = nullptr, int64_t scratch_stride = 0, cudaStream_t bt_stream = nullptr) -> int {
+        if (!bt_stream) bt_stream = ctx->stream;
         BandedBtArgs ba{};
         ba.scratch = scratch; ba.scratch_stride = scratch_stride;
         ba.tiles = d_tiles; ba.order = d_order; ba.chunk_base = lo; ba.n_items = items; ba.rpl = bt_rpl;
@@ -922,8 +935,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         ba.path_len = out.path_len; ba.path_off = out.path_off; ba.path = want_path ? out.path : nullptr;
         ba.path_cap = out.path_cap; ba.cursor = out.cursor; ba.summaries = out.summaries;
         {
-            ProfScope prof(ctx, 1);
-            banded_backtrack_kernel<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ba);
+            ProfScope prof(ctx, 1, bt_stream);
+            banded_backtrack_kernel<<<(items + 127) / 128, 128, 0, bt_stream>>>(ba);
         }
         CU_TRY(cudaGetLastError());
         ctx->launches++;
@@ -954,17 +967,28 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     }
 
     // ---- long banded reads / models too large for shared memory ------------------------------
-    for (int lo = fam_long.first_item, end = lo + n_long; lo < end;) {
+    if (l_double && !ctx->bt_stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&ctx->bt_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CU_TRY(cudaEventCreateWithFlags(&ctx->fill_done[k], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ctx->bt_done[k], cudaEventDisableTiming));
+        }
+    }
+    int l_index = 0;
+    for (int lo = fam_long.first_item, end = lo + n_long; lo < end; ++l_index) {
         const int hi = next_chunk(lo, end, l_chunk);
         const int tile0 = pl.item_tile[lo], tile1 = pl.item_tile[hi - 1] + 1;
+        const int half = l_double ? (l_index & 1) : 0;
+        unsigned char* wl = w + (size_t)half * l_half;
+        if (l_double && l_index >= 2) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->bt_done[half], 0));   // its backtrack is done
         LongArgs la{};
         la.tiles = d_tiles + tile0; la.order = d_order; la.chunk_base = lo;
         la.pk = d_pk; la.pk_off = d_pk_off; la.rlen = d_rlen; la.logp = out.logp;
-        la.tbw = reinterpret_cast<uint32_t*>(w + lo_tbw); la.tbw_stride = l_tbw_words;
-        la.acc_tb = reinterpret_cast<uint16_t*>(w + lo_acc); la.acc_stride = l_acc;
-        la.vfin = reinterpret_cast<double*>(w + lo_vfin); la.vfin_stride = 3 * Pl;
-        la.carry = reinterpret_cast<double*>(w + lo_carry); la.carry_stride = 3 * Pl;
-        la.ftb = reinterpret_cast<int32_t*>(w + lo_ftb);
+        la.tbw = reinterpret_cast<uint32_t*>(wl + lo_tbw); la.tbw_stride = l_tbw_words;
+        la.acc_tb = reinterpret_cast<uint16_t*>(wl + lo_acc); la.acc_stride = l_acc;
+        la.vfin = reinterpret_cast<double*>(wl + lo_vfin); la.vfin_stride = 3 * Pl;
+        la.carry = reinterpret_cast<double*>(wl + lo_carry); la.carry_stride = 3 * Pl;
+        la.ftb = reinterpret_cast<int32_t*>(wl + lo_ftb);
         la.wpr = long_wpr;
         if (int rc = allow_max_dynamic_smem(ctx, banded_long_kernel)) return rc;
         {
@@ -974,12 +998,24 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         CU_TRY(cudaGetLastError());
         ctx->launches++;
         if (want_walk) {
+            cudaStream_t bts = l_double ? ctx->bt_stream : ctx->stream;
+            if (l_double) {
+                CU_TRY(cudaEventRecord(ctx->fill_done[half], ctx->stream));
+                CU_TRY(cudaStreamWaitEvent(bts, ctx->fill_done[half], 0));
+            }
             int rc = launch_backtrack(lo, hi - lo, kLongRPL, la.tbw, la.tbw_stride, la.acc_tb, la.acc_stride, la.ftb,
-                                      l_scratch ? reinterpret_cast<int32_t*>(w + lo_scratch) : nullptr, (int64_t)l_scratch);
+                                      l_scratch ? reinterpret_cast<int32_t*>(wl + lo_scratch) : nullptr, (int64_t)l_scratch, bts);
             if (rc) return rc;
-            if (want_path && (rc = mark_chunk(ctx, out.cursor))) return rc;
+            if (want_path && (rc = mark_chunk(ctx, out.cursor, bts))) return rc;
+            if (l_double) CU_TRY(cudaEventRecord(ctx->bt_done[half], bts));
         }
         lo = hi;
+    }
+    if (l_double && l_index > 0) {
+        // whatever follows on the context's stream (the generic family in the same workspace, result copies)
+        // comes after the last backtracks
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->bt_done[0], 0));
+        if (l_index > 1) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->bt_done[1], 0));
     }
 
     // ---- everything else: generic kernel ------------------------------------------------------
@@ -1462,9 +1498,10 @@ int advhmm_context_create(int device, void* stream, advhmm_context** out)
         else { CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->owns_stream = true; }
         size_t free_b = 0, total_b = 0;
         CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-        // traceback workspace: long reads need ~40 MB each to keep every SM busy, so by default
-        // half of the free device memory (capped at 96 GB) may be used; ADVHMM_WORKSPACE_MB overrides
-        ctx->workspace_budget = std::min<size_t>((size_t)96 << 30, free_b / 2);
+        // traceback workspace: a 20 kb read needs ~100 MB and two double-buffered chunks of two waves of
+        // reads keep every SM busy, so by default three quarters of the free device memory (capped at
+        // 140 GB) MAY be used (only what a batch needs is allocated); ADVHMM_WORKSPACE_MB overrides
+        ctx->workspace_budget = std::min<size_t>((size_t)140 << 30, free_b / 4 * 3);
         const char* env = getenv("ADVHMM_WORKSPACE_MB");
         if (env && atoll(env) > 0) ctx->workspace_budget = (size_t)atoll(env) << 20;
         env = getenv("ADVHMM_SHORT_MAX_LEN");
@@ -1488,6 +1525,11 @@ void advhmm_context_destroy(advhmm_context* ctx)
         }
         for (auto& kv : ctx->shape_dev) kv.second->blob.release();
         ctx->alive->store(false);
+        if (ctx->bt_stream) {
+            cudaStreamSynchronize(ctx->bt_stream);
+            cudaStreamDestroy(ctx->bt_stream);
+            for (int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->fill_done[k]); cudaEventDestroy(ctx->bt_done[k]); }
+        }
         if (ctx->upload_stream) { cudaStreamSynchronize(ctx->upload_stream); cudaStreamDestroy(ctx->upload_stream); }
         if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
         for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);

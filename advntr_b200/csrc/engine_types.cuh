@@ -192,6 +192,8 @@ struct advhmm_context {
     std::map<const rm::ShapeStructure*, std::unique_ptr<DevShape>> shape_dev;
     PinnedBuf h_stage[2];
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    cudaStream_t bt_stream = nullptr;        // long reads: backtrack of chunk k next to the fill of chunk k+1
+    cudaEvent_t fill_done[2] = {nullptr, nullptr}, bt_done[2] = {nullptr, nullptr};
     cudaStream_t upload_stream = nullptr;    // model tables travel here, next to the decoding of the previous batch
     cudaEvent_t upload_done = nullptr;
     std::shared_ptr<std::atomic<bool>> alive = std::make_shared<std::atomic<bool>>(true);

@@ -661,3 +661,31 @@ def test_long_read_kernel_with_every_warps_per_read_setting(ctx, wpr, monkeypatc
         assert same_bits(res.logp, lp)
         assert_paths_equal([res.path(i) for i in range(len(res))], paths, "wpr %d" % wpr)
     dm.close()
+
+
+def test_long_reads_in_several_chunks_backtrack_overlaps_the_next_fill(monkeypatch):
+    """A workspace too small for all long reads of a batch: the long-read family runs in chunks, two
+    workspace halves, the backtrack of chunk k on a second stream next to the fill of chunk k+1.  Same
+    scores and paths as the oracle, through both front ends (host buffers with chunk-wise path copies)."""
+    from advntr_b200 import engine, read_matcher, synth
+    monkeypatch.setenv("ADVHMM_WORKSPACE_MB", "24")
+    c2 = engine.Context(device=0)
+    rng = random.Random(77)
+    ru = synth.rand_dna(rng, 41)
+    left, right = synth.rand_dna(rng, 100), synth.rand_dna(rng, 100)
+    model = read_matcher.get_read_matcher_model(left, right, [ru], 30, error_rate=0.3)
+    dm = engine.DeviceModel(c2, model.baked)
+    reads = [synth.sequencing_errors(rng, left + ru * rng.randint(5, 60) + right, 0.02, 0.05, 0.05) for _ in range(21)]
+    reads += [reads[0][:100], ""]                       # a short-kernel read and an empty one in the same call
+    codes = [oracle.encode(r) for r in reads]
+    lp, paths = oracle.OracleModel(model.baked).viterbi(codes)
+    launches0 = c2.launch_count
+    for _ in range(2):
+        res = dm.viterbi(codes, want_summary=True)
+        assert same_bits(res.logp, lp)
+        assert_paths_equal([res.path(i) for i in range(len(res))], paths, "chunked long reads")
+    assert c2.launch_count - launches0 >= 2 * (1 + 2 * 3), "expected the long reads to be split into several chunks"
+    only = dm.viterbi(codes, want_path=False)
+    assert same_bits(only.logp, lp)
+    dm.close()
+    c2.close()
