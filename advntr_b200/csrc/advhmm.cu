@@ -801,7 +801,7 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         // of many stripes always get more warps; (c) few reads (a PacBio locus has tens of spanning reads):
         // more warps per read fill the warp slots the missing reads leave empty
         while (long_wpr < kLongWarps &&
-               (per_read * (2 * kLongWarps / long_wpr) * sms > ctx->workspace_budget ||
+               (per_read * (2 * kLongWarps / long_wpr) * sms > ctx->workspace_budget_long ||
                 stripes >= (size_t)16 * long_wpr ||
                 (fam_long.items.size() * (size_t)long_wpr < 2 * kLongWarps * sms && stripes >= (size_t)4 * long_wpr)))
             long_wpr *= 2;
@@ -871,9 +871,9 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     const size_t g_tb_per = (want_walk && n_generic) ? (size_t)std::max(fam_generic.max_len, 1) * gm * sizeof(uint16_t) : 0;
     const size_t g_rows_per = (n_generic && !rows_in_smem) ? 2 * gm * sizeof(double) : 0;
     const size_t g_per_item = n_generic ? g_tb_per + g_rows_per + 8 : 0;
-    auto chunk_of = [&](size_t per_item, int n_items, size_t floor_items) {
+    auto chunk_of = [&](size_t per_item, int n_items, size_t floor_items, size_t budget = 0) {
         if (!n_items) return (size_t)0;
-        size_t c = std::max<size_t>(ctx->workspace_budget / per_item, floor_items);
+        size_t c = std::max<size_t>((budget ? budget : ctx->workspace_budget) / per_item, floor_items);
         return std::min<size_t>(c, (size_t)n_items);
     };
     size_t s_chunk = chunk_of(s_per_item, n_short, (size_t)kBandedWarpsMax * ctx->sm_count);
@@ -882,12 +882,12 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
     // i+1 is decoded
     if (ctx->mark_chunks && ctx->host_chunks > 1 && n_short >= ctx->host_chunks * 16384)
         s_chunk = std::min<size_t>(s_chunk, ((size_t)n_short + ctx->host_chunks - 1) / ctx->host_chunks);
-    size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)(kLongWarps / long_wpr));
+    size_t l_chunk = chunk_of(l_per_item, n_long, (size_t)(kLongWarps / long_wpr), ctx->workspace_budget_long);
     // Long reads that do not fit in one chunk: the workspace is cut in two halves, the backtrack of chunk k
     // (a serial pointer chase per read, ~10 % of the fill time) runs on a second stream while chunk k+1 is
     // filled into the other half.
     const bool l_double = want_walk && l_chunk < (size_t)n_long && ctx->device >= 0;
-    if (l_double) l_chunk = std::max<size_t>(chunk_of(2 * l_per_item, n_long, (size_t)(kLongWarps / long_wpr)), 1);
+    if (l_double) l_chunk = std::max<size_t>(chunk_of(2 * l_per_item, n_long, (size_t)(kLongWarps / long_wpr), ctx->workspace_budget_long), 1);
     {   // whole waves: two CTAs of kLongWarps / long_wpr reads per SM
         const size_t wave = (size_t)2 * (kLongWarps / long_wpr) * std::max(ctx->sm_count, 1);
         if (l_chunk > wave && l_chunk < (size_t)n_long) l_chunk = l_chunk / wave * wave;
@@ -1498,12 +1498,14 @@ int advhmm_context_create(int device, void* stream, advhmm_context** out)
         else { CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->owns_stream = true; }
         size_t free_b = 0, total_b = 0;
         CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-        // traceback workspace: a 20 kb read needs ~100 MB and two double-buffered chunks of two waves of
-        // reads keep every SM busy, so by default three quarters of the free device memory (capped at
-        // 140 GB) MAY be used (only what a batch needs is allocated); ADVHMM_WORKSPACE_MB overrides
-        ctx->workspace_budget = std::min<size_t>((size_t)140 << 30, free_b / 4 * 3);
+        // traceback workspace (only what a batch needs is allocated): short reads take up to half of the free
+        // device memory (capped at 96 GB); long reads -- ~100 MB per 20 kb read, and a launch of several waves
+        // of CTAs back-fills the SMs whose reads finish early -- up to three quarters (capped at 140 GB);
+        // ADVHMM_WORKSPACE_MB overrides both
+        ctx->workspace_budget = std::min<size_t>((size_t)96 << 30, free_b / 2);
+        ctx->workspace_budget_long = std::min<size_t>((size_t)140 << 30, free_b / 4 * 3);
         const char* env = getenv("ADVHMM_WORKSPACE_MB");
-        if (env && atoll(env) > 0) ctx->workspace_budget = (size_t)atoll(env) << 20;
+        if (env && atoll(env) > 0) ctx->workspace_budget = ctx->workspace_budget_long = (size_t)atoll(env) << 20;
         env = getenv("ADVHMM_SHORT_MAX_LEN");
         if (env && atoi(env) > 0) ctx->short_max_len = std::min(atoi(env), 32 * kMaxRPL);
     }

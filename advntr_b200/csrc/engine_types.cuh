@@ -170,7 +170,8 @@ struct advhmm_context {
     int sm_count = 0;
     size_t smem_optin = 0;
     int64_t launches = 0;
-    size_t workspace_budget = 0;
+    size_t workspace_budget = 0;       // traceback workspace a batch may take (short-read / generic families)
+    size_t workspace_budget_long = 0;  // ... the long-read family: ~100 MB per 20 kb read, see advhmm_context_create
     DevBuf d_seqs, d_seq_off, d_pk, d_meta, d_work, d_out, d_paths, d_flags;
     DevBuf d_badflag;            // device-buffer calls: first read with a code outside the alphabet
     PinnedBuf h_meta, h_out;
