@@ -357,7 +357,7 @@ int create_models_for_loci(advhmm_context* ctx, const advhmm_loci* L, int n_thre
     std::vector<std::vector<int32_t>> slot_item((size_t)N);
     std::atomic<int> bad{-1};
     rm::parallel_for((size_t)N, nt, [&](size_t i, int) {
-        const rm::ShapeStructure& sh = *shapes[prep[i].key];
+        const rm::ShapeStructure& sh = *shapes.find(prep[i].key)->second;
         const double to_end = 0.7 / (sh.key.C * sh.key.R);
         const double total = 1 + to_end;
         auto& its = items[i];
@@ -392,7 +392,7 @@ int create_models_for_loci(advhmm_context* ctx, const advhmm_loci* L, int n_thre
         std::unique_ptr<advhmm_model> mod(new advhmm_model);
         mod->ctx = ctx;
         mod->lean = true;
-        mod->locus.shape = shapes[prep[i].key];
+        mod->locus.shape = shapes.find(prep[i].key)->second;
         mod->locus.slot_log.resize(slot_item[i].size());
         for (size_t s = 0; s < slot_item[i].size(); ++s) mod->locus.slot_log[s] = chain.items[first[i] + slot_item[i][s]].out;
         mod->locus.emis_tab = std::move(prep[i].emis_tab);

@@ -805,8 +805,22 @@ class ShardRunner(object):
             bounds.append(lo)
         compile_ms, prev = 0.0, None
         self.e0.record(self.stream)
-        self.d_seqs.copy_(self.h_seqs, non_blocking=True)
-        for lo, hi in zip(bounds[:-1], bounds[1:]):
+        # reads: the first chunk's on the compute stream, every later chunk's on a side stream while the chunk
+        # before it is decoded
+        def upload(lo, hi, st):
+            a, b = int(off[int(goff[lo])]), int(off[int(goff[hi])])
+            if hi == n_loci:
+                b = len(self.h_seqs)
+            with torch.cuda.stream(st):
+                self.d_seqs[a:b].copy_(self.h_seqs[a:b], non_blocking=True)
+        if not hasattr(self, "side"):
+            self.side = torch.cuda.Stream(device=self.D.local)
+            self.up_done = [torch.cuda.Event() for _ in range(2)]
+        self.side.wait_stream(self.stream)                          # (the previous pass is done with d_seqs)
+        upload(bounds[0], bounds[1], self.stream)
+        for ci, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+            if ci > 0:
+                self.stream.wait_event(self.up_done[ci & 1])
             if compile_in_region:
                 tc = time.perf_counter()
                 hs = create_models(ctx, wl["cols"], lo, hi)         # the device keeps decoding the previous chunk
@@ -821,6 +835,9 @@ class ShardRunner(object):
                 self.d_logp[r0:].data_ptr(), self.d_plen[r0:].data_ptr(), self.d_poff[r0:].data_ptr(), None, 0, None,
                 self.d_summ[r0:].data_ptr())
             engine._check(rc)
+            if ci + 2 < len(bounds):                               # the next chunk's reads travel during this decode
+                upload(bounds[ci + 1], bounds[ci + 2], self.side)
+                self.up_done[(ci + 1) & 1].record(self.side)
             if compile_in_region:
                 if prev is not None:
                     destroy_models(*prev)                          # freed in stream order: no wait for the device
