@@ -738,7 +738,7 @@ banded_fill_f32_kernel(const BandedArgs a)
 //     INSIDE a read instead: `wpr` warps of a CTA share one read and take its stripes round-robin, each
 //     one trailing the warp that sweeps the stripe above by three 16-column blocks (it needs that
 //     stripe's last row).  The hand-over is the carry buffer; how far a stripe has got is published in
-//     shared memory by the lane that writes the carry (stores, fence, flag) and polled by the consumer.
+//     shared memory by the lane that writes the carry (st.release) and polled by the consumer (ld.acquire).
 // =============================================================================================
 struct LongArgs {
     const Tile* tiles;
@@ -808,14 +808,22 @@ banded_long_kernel(const LongArgs a)
         if (lane == 0 && sub == 0) a.logp[q] = M->logp_empty;
         return;
     }
-    volatile long long* prog = s_prog;
+    // progress flags: release store by the lane that wrote the carried values, acquire load by the consumer
+    auto publish = [&](long long v) {
+        asm volatile("st.release.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_prog[warp])), "l"(v) : "memory");
+    };
     // the warp that sweeps the stripe above mine, and a wait until it has written `need` carried columns of it
     const int pw = rd * wpr + (sub + wpr - 1) % wpr;
     auto wait_carry = [&](int stripe_above, int need) {
         if (lane == 0) {
             const long long want = ((long long)stripe_above << 32) | (long long)need;
-            while (prog[pw] < want) __nanosleep(64);
-            __threadfence_block();
+            const uint32_t addr = smem_u32(&s_prog[pw]);
+            long long have;
+            for (;;) {
+                asm volatile("ld.acquire.cta.shared::cta.b64 %0, [%1];" : "=l"(have) : "r"(addr) : "memory");
+                if (have >= want) break;
+                __nanosleep(64);
+            }
         }
         __syncwarp();
     };
@@ -916,6 +924,8 @@ banded_long_kernel(const LongArgs a)
             if (sb + 1 < n_cblocks) {
                 if (lane == 0) issue_block(sb + 1);
                 if (!FIRST) {
+                    // (keeping the three loaded values in registers across the 16 steps to hide the L2 round trip
+                    // measured 6 % SLOWER: the kernel sits at its 128-register cap)
                     if (wpr > 1) wait_carry(s - 1, min((sb + 2) * B, NC));
                     if (lane < B) {
                         const int col = (sb + 1) * B + lane;
@@ -1012,17 +1022,13 @@ banded_long_kernel(const LongArgs a)
                 for (int j = 0; j < RPL; ++j) e_blk[j] += de;
             }
             // tell the warp below how many carried columns of this stripe are in memory: after step t lane 31
-            // has written columns 0 .. t - 31.  Published by the lane that wrote them: stores, fence, flag.
+            // has written columns 0 .. t - 31.  Published by the lane that wrote them (release).
             if (!LAST && wpr > 1 && carry_out) {
                 const int done = min(max(t0 + B - 31, 0), NC);
-                __threadfence_block();
-                prog[warp] = ((long long)s << 32) | (long long)done;
+                publish(((long long)s << 32) | (long long)done);
             }
         }
-        if (!LAST && wpr > 1 && carry_out) {
-            __threadfence_block();
-            prog[warp] = ((long long)s << 32) | (long long)NC;
-        }
+        if (!LAST && wpr > 1 && carry_out) publish(((long long)s << 32) | (long long)NC);
         // a block queued beyond the last one this stripe waited for (the prefetch runs one block ahead of the
         // steps; cannot happen while steps >= columns, kept for symmetry): drain it, every copy is waited for once
         if (n_sblocks < n_cblocks) wait_block(n_sblocks);
