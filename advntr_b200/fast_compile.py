@@ -131,6 +131,11 @@ def get_read_matcher_model(left, right, segments, copies, error_rate=read_matche
     """Drop-in for ``read_matcher.get_read_matcher_model`` (no ``vpaths``): same tables, compiled natively.
     ``segments``: equal-length repeat segments, or an alignment of them (strings over ``ACGT-``)."""
     model = CompiledHMM(_spec(left, right, segments, copies, error_rate))
+    if error_rate > 0 and len(left) > 0 and len(right) > 0 and copies >= 1:
+        # every transition probability of the builders is positive then (pseudocounts), the structure is the
+        # shape's: nothing is compiled until the tables or a decode are asked for -- or until compile_many /
+        # attach_device_models compiles the models of many loci in one native call
+        return model
     try:
         model._any_model()
     except engine.EngineError as e:
