@@ -689,3 +689,52 @@ def test_long_reads_in_several_chunks_backtrack_overlaps_the_next_fill(monkeypat
     assert same_bits(only.logp, lp)
     dm.close()
     c2.close()
+
+
+@pytest.mark.parametrize("seed", [11, 22])
+def test_random_shapes_native_models_and_long_reads_vs_oracle(ctx, seed, monkeypatch):
+    """Differential test of this round's two new pieces together: models made by the NATIVE compiler
+    (advhmm_models_create_for_loci; random shapes incl. gapped alignments) and reads of 321..2,600 bases
+    (the striped long-read kernel; a random warps-per-read setting per model) against the C restatement of
+    the reference running on the LITERAL builder's tables."""
+    from advntr_b200 import engine, read_matcher, synth
+    rng = random.Random(seed)
+    specs = []
+    for _ in range(6):
+        R = rng.choice((2, 3, 5, 8, 13, 21, 34, 55))
+        copies = rng.randint(1, 10 if R < 30 else 4)
+        Ll, Lr = rng.choice((1, 2, 7, 30, 100, 150)), rng.choice((1, 3, 12, 60, 150))
+        eps = rng.choice((0.05, 0.3))
+        ru = synth.rand_dna(rng, R)
+        rows = [synth.substitute(rng, ru, rng.choice((0.0, 0.05, 0.3))) for _ in range(rng.randint(1, 6))]
+        if rng.random() < 0.5:                               # gapped alignment: one extra column, gaps sprinkled
+            rows = [r[:R // 2] + (rng.choice("ACGT") if rng.random() < 0.3 else "-") + r[R // 2:] for r in rows]
+            rows = ["".join("-" if (c != "-" and rng.random() < 0.08) else c for c in r) for r in rows]
+            rows = [r if r.strip("-") else "A" + r[1:] for r in rows]
+        left, right = synth.rand_dna(rng, Ll), synth.rand_dna(rng, Lr)
+        try:
+            read_matcher.repeat_profile(rows, eps)
+        except Exception:
+            rows = [r.replace("-", "A") for r in rows]
+        specs.append((left, right, rows, copies, eps))
+    cols = engine.LociColumns.from_lists(*[list(x) for x in zip(*specs)])
+    models = ctx.compile_loci(cols)
+    for (left, right, rows, copies, eps), dm in zip(specs, models):
+        lit = read_matcher.get_read_matcher_model(left, right, rows, copies, error_rate=eps)
+        t = dm.tables()
+        assert same_bits(t["in_logp"], lit.baked["in_logp"]) and same_bits(t["emis"], lit.baked["emis"])
+        assert np.array_equal(t["in_src"], lit.baked["in_src"])
+        locus = left + "".join(r.replace("-", "") for r in rows) * 4 + right
+        reads = ["", "G"]
+        for n in (150, 321, 400, 640, 801, 1281, rng.randint(1500, 2600)):
+            s0 = rng.randrange(0, len(locus))
+            r = synth.sequencing_errors(rng, (locus * (n // len(locus) + 2))[s0:s0 + n + 40], 0.02, 0.03, 0.03)[:n]
+            reads.append(synth.revcomp(r) if rng.random() < 0.3 else r)
+        reads.append(synth.rand_dna(rng, 700))
+        codes = [oracle.encode(r) for r in reads]
+        want_lp, want_paths = oracle.OracleModel(lit.baked).viterbi(codes)
+        monkeypatch.setenv("ADVHMM_LONG_WPR", str(rng.choice((1, 2, 4, 8))))
+        res = dm.viterbi(codes, want_summary=True)
+        assert same_bits(res.logp, want_lp), (seed, len(left), len(right), copies, eps)
+        assert_paths_equal([res.path(i) for i in range(len(res))], want_paths, "native + long reads")
+        dm.close()

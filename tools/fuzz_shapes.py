@@ -16,7 +16,15 @@ first = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 ctx = engine.Context(device=0)
 t0 = time.time()
+class _Env(object):                      # stands in for pytest's monkeypatch
+    def setenv(self, k, v):
+        os.environ[k] = v
+
+
 for seed in range(first, first + n):
     T.test_random_loci_random_reads_vs_oracle(ctx, seed)
-print("seeds %d..%d: %d model shapes, %d reads, every routing bit-exact against the oracle (%.0f s)" % (
-    first, first + n - 1, 8 * n, 8 * 40 * n, time.time() - t0))
+    T.test_random_shapes_native_models_and_long_reads_vs_oracle(ctx, seed, _Env())
+os.environ.pop("ADVHMM_LONG_WPR", None)
+print("seeds %d..%d: %d model shapes (%d of them through the native compiler, with reads of up to 2,600 bases on the "
+      "long-read kernel), %d reads, every routing bit-exact against the oracle (%.0f s)" % (
+          first, first + n - 1, 14 * n, 6 * n, (8 * 40 + 6 * 10) * n, time.time() - t0))
