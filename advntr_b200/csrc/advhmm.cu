@@ -736,9 +736,8 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
             }
         }
     }
-    if (fp32 && (!fam_long.items.empty() || !fam_generic.items.empty()))
-        return set_error(ADVHMM_EUNSUPPORTED, "fp32 mode is implemented for the short-read banded kernel only "
-                                              "(profile-shaped model, reads <= %d bases)", 32 * kMaxRPL);
+    if (fp32 && !fam_generic.items.empty())
+        return set_error(ADVHMM_EUNSUPPORTED, "fp32 mode is implemented for the banded kernels (profile-shaped models) only");
 
     // generic launch geometry: as many warps per CTA as DP rows fit in shared memory
     int gwarps = kGenericWarpsMax, rows_in_smem = 1;
@@ -990,10 +989,14 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         la.carry = reinterpret_cast<double*>(wl + lo_carry); la.carry_stride = 3 * Pl;
         la.ftb = reinterpret_cast<int32_t*>(wl + lo_ftb);
         la.wpr = long_wpr;
-        if (int rc = allow_max_dynamic_smem(ctx, banded_long_kernel)) return rc;
-        {
+        if (fp32) {
+            if (int rc = allow_max_dynamic_smem(ctx, banded_long_kernel<float>)) return rc;
             ProfScope prof(ctx, 0);
-            banded_long_kernel<<<tile1 - tile0, kLongWarps * 32, kLongWarps * sizeof(LongRing), ctx->stream>>>(la);
+            banded_long_kernel<float><<<tile1 - tile0, kLongWarps * 32, kLongWarps * sizeof(LongRing<float>), ctx->stream>>>(la);
+        } else {
+            if (int rc = allow_max_dynamic_smem(ctx, banded_long_kernel<double>)) return rc;
+            ProfScope prof(ctx, 0);
+            banded_long_kernel<double><<<tile1 - tile0, kLongWarps * 32, kLongWarps * sizeof(LongRing<double>), ctx->stream>>>(la);
         }
         CU_TRY(cudaGetLastError());
         ctx->launches++;

@@ -769,26 +769,79 @@ constexpr int kLongWarps = 8;
 constexpr int kRingBlk = 16;                       // columns per TMA refill
 constexpr int kRingCols = 64 + kRingBlk;           // 4 slots + the mirror of slot 0
 
+// The kernel is written once for both arithmetic types: double (the bit-exact default) and float (the optional
+// ADVHMM_FP32 mode, float image of 112 bytes per column, see banded_fill_f32_kernel).
+template <typename T> struct LongT;
+template <> struct LongT<double> {
+    static constexpr int WB = 80, EB = 16;         // ring bytes per column: ten weights; {eI, eM} of one symbol
+    static constexpr int kE = kImgE, kV1 = kImgV1; // byte offsets (per column) of the image sections
+    static __device__ __forceinline__ const unsigned char* image(const DevBanded* M) { return M->image; }
+    static __device__ __forceinline__ double empty(const DevBanded* M) { return M->logp_empty; }
+    static __device__ __forceinline__ const double* fin_w(const DevBanded* M) { return M->fin_w; }
+};
+template <> struct LongT<float> {
+    static constexpr int WB = 48, EB = 8;
+    static constexpr int kE = kImgFE, kV1 = kImgFV1;
+    static __device__ __forceinline__ const unsigned char* image(const DevBanded* M) { return M->image_f; }
+    static __device__ __forceinline__ float empty(const DevBanded* M) { return M->logp_empty_f; }
+    static __device__ __forceinline__ const float* fin_w(const DevBanded* M) { return M->fin_w_f; }
+};
+
+template <typename T>
 struct __align__(128) LongRing {                   // per warp
-    double w[kRingCols * 10];                      // w10[slot][10]
-    double e[4][kRingCols * 2];                    // e2[sym][slot][2]
-    double carry[2][3][kRingBlk];                  // carried row of the previous stripe, double-buffered
+    unsigned char w[kRingCols * LongT<T>::WB];     // w[slot][10 (+2 pad for float)]
+    unsigned char e[4][kRingCols * LongT<T>::EB];  // e2[sym][slot][2]
+    T carry[2][3][kRingBlk];                       // carried row of the previous stripe, double-buffered
     uint64_t bar[4];
 };
 
-__device__ __forceinline__ double2 ldg128(const unsigned char* p)
+__device__ __forceinline__ void ldg_pair(const unsigned char* p, double& x, double& y)
 {
-    double2 v;
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
+}
+__device__ __forceinline__ void ldg_pair(const unsigned char* p, float& x, float& y)
+{
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p));
+}
+__device__ __forceinline__ void lds_pair(uint32_t addr, double& x, double& y) { const double2 v = lds128(addr); x = v.x; y = v.y; }
+__device__ __forceinline__ void lds_pair(uint32_t addr, float& x, float& y) { const float2 v = lds64f(addr); x = v.x; y = v.y; }
+// the ten weights of a column: wII wIM wID | wMI wMM wMD | wDI wDM wDD | accw
+__device__ __forceinline__ void lds_weights(uint32_t wa, double (&w)[10])
+{
+    const double2 a = lds128(wa), b = lds128(wa + 16), c = lds128(wa + 32), d = lds128(wa + 48), e = lds128(wa + 64);
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y; w[6] = d.x; w[7] = d.y; w[8] = e.x; w[9] = e.y;
+}
+__device__ __forceinline__ void lds_weights(uint32_t wa, float (&w)[10])
+{
+    const float4 a = lds128f(wa), b = lds128f(wa + 16), c = lds128f(wa + 32);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; w[8] = c.x; w[9] = c.y;
+}
+template <int SH> __device__ __forceinline__ double max3_t(double a0, double a1, double a2, uint32_t& bits) { return max3_first<SH>(a0, a1, a2, bits); }
+template <int SH> __device__ __forceinline__ float max3_t(float a0, float a1, float a2, uint32_t& bits) { return max3_first_f32<SH>(a0, a1, a2, bits); }
+__device__ __forceinline__ double shfl_up_t(double v) { return shfl_up_f64(v, 1); }
+__device__ __forceinline__ float shfl_up_t(float v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double ldcg_t(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ float ldcg_t(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ void warp_argmax_first_t(double& v, int& idx) { warp_argmax_first(v, idx); }
+__device__ __forceinline__ void warp_argmax_first_t(float& v, int& idx)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kLongWarps * 32, 2)
 banded_long_kernel(const LongArgs a)
 {
-    constexpr int RPL = kLongRPL, H = 32 * RPL, B = kRingBlk;
+    using LT = LongT<T>;
+    constexpr int RPL = kLongRPL, H = 32 * RPL, B = kRingBlk, WB = LT::WB, EB = LT::EB;
+    const T kNI = (T)kNegInf;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double s_fval[kLongWarps][32];
+    __shared__ T s_fval[kLongWarps][32];
     __shared__ long long s_prog[kLongWarps];       // (stripe << 32 | carried columns written) of every warp
 
     const Tile tile = a.tiles[blockIdx.x];
@@ -805,7 +858,7 @@ banded_long_kernel(const LongArgs a)
     const size_t slot = (size_t)(item - a.chunk_base);
     const int n = a.rlen[q];
     if (n == 0) {
-        if (lane == 0 && sub == 0) a.logp[q] = M->logp_empty;
+        if (lane == 0 && sub == 0) a.logp[q] = (double)LT::empty(M);
         return;
     }
     // progress flags: release store by the lane that wrote the carried values, acquire load by the consumer
@@ -827,13 +880,13 @@ banded_long_kernel(const LongArgs a)
         }
         __syncwarp();
     };
-    LongRing& ring = reinterpret_cast<LongRing*>(smem_raw)[warp];
-    const unsigned char* __restrict__ img = M->image;
-    const unsigned char* __restrict__ img_e = img + (size_t)kImgE * P;
-    const unsigned char* __restrict__ img_v1 = img + (size_t)kImgV1 * P;
+    LongRing<T>& ring = reinterpret_cast<LongRing<T>*>(smem_raw)[warp];
+    const unsigned char* __restrict__ img = LT::image(M);
+    const unsigned char* __restrict__ img_e = img + (size_t)LT::kE * P;
+    const unsigned char* __restrict__ img_v1 = img + (size_t)LT::kV1 * P;
     const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
-    double* __restrict__ vfin = a.vfin + slot * a.vfin_stride;
-    double* __restrict__ carry = a.carry + slot * a.carry_stride;
+    T* __restrict__ vfin = reinterpret_cast<T*>(a.vfin + slot * a.vfin_stride);        // (the float build uses half of it)
+    T* __restrict__ carry = reinterpret_cast<T*>(a.carry + slot * a.carry_stride);
     const int n_stripes = (n + H - 1) / H;
     const int last_word = (n + 15) / 16;
     const int n_cblocks = P / B;                                   // P is a multiple of 16
@@ -852,17 +905,17 @@ banded_long_kernel(const LongArgs a)
     // lane 0: queue the copies of column block j of the image into ring slot j & 3
     auto issue_block = [&](int j) {
         const int sl = j & 3;
-        const uint32_t bytes = (uint32_t)(B * 80 + 4 * B * 16) * (sl == 0 ? 2u : 1u);
+        const uint32_t bytes = (uint32_t)(B * WB + 4 * B * EB) * (sl == 0 ? 2u : 1u);
         mbar_expect_tx(&ring.bar[sl], bytes);
-        tma_bulk_g2s(&ring.w[(size_t)sl * B * 10], img + (size_t)j * B * 80, B * 80, &ring.bar[sl]);
+        tma_bulk_g2s(&ring.w[(size_t)sl * B * WB], img + (size_t)j * B * WB, B * WB, &ring.bar[sl]);
 #pragma unroll
         for (int x = 0; x < 4; ++x)
-            tma_bulk_g2s(&ring.e[x][(size_t)sl * B * 2], img_e + (size_t)x * 16 * P + (size_t)j * B * 16, B * 16, &ring.bar[sl]);
+            tma_bulk_g2s(&ring.e[x][(size_t)sl * B * EB], img_e + (size_t)x * EB * P + (size_t)j * B * EB, B * EB, &ring.bar[sl]);
         if (sl == 0) {                                              // the mirror behind slot 3
-            tma_bulk_g2s(&ring.w[(size_t)64 * 10], img + (size_t)j * B * 80, B * 80, &ring.bar[sl]);
+            tma_bulk_g2s(&ring.w[(size_t)64 * WB], img + (size_t)j * B * WB, B * WB, &ring.bar[sl]);
 #pragma unroll
             for (int x = 0; x < 4; ++x)
-                tma_bulk_g2s(&ring.e[x][(size_t)64 * 2], img_e + (size_t)x * 16 * P + (size_t)j * B * 16, B * 16, &ring.bar[sl]);
+                tma_bulk_g2s(&ring.e[x][(size_t)64 * EB], img_e + (size_t)x * EB * P + (size_t)j * B * EB, B * EB, &ring.bar[sl]);
         }
     };
 
@@ -887,20 +940,20 @@ banded_long_kernel(const LongArgs a)
         const uint32_t slot_init = (uint32_t)(0 - lane) & 63u;
 #pragma unroll
         for (int j = 0; j < RPL; ++j)
-            e_blk[j] = e_ring + ((symbits >> (2 * j)) & 3u) * (uint32_t)(kRingCols * 16) + slot_init * 16u;
-        uint32_t w_blk = w_ring + slot_init * 80u;
+            e_blk[j] = e_ring + ((symbits >> (2 * j)) & 3u) * (uint32_t)(kRingCols * EB) + slot_init * (uint32_t)EB;
+        uint32_t w_blk = w_ring + slot_init * (uint32_t)WB;
         uint32_t slot0 = slot_init;
-        const size_t v1_off = (size_t)(symbits & 3u) * 16u * P;
+        const size_t v1_off = (size_t)(symbits & 3u) * (size_t)EB * P;
 
         uint32_t* tbw_t = a.tbw + slot * a.tbw_stride + ((size_t)(s * 32 + lane) * P) - lane;   // index with the step t
         uint16_t* __restrict__ acc_tb = a.acc_tb + slot * a.acc_stride + (size_t)s * H + lane * RPL;
-        double* carry_t = carry - 31;                               // lane 31 writes column t - 31: index with t
+        T* carry_t = carry - 31;                                    // lane 31 writes column t - 31: index with t
         asm volatile("" : "+l"(tbw_t), "+l"(carry_t));
 
-        double cI[RPL], cM[RPL], cD[RPL], acc[RPL];
+        T cI[RPL], cM[RPL], cD[RPL], acc[RPL];
 #pragma unroll
-        for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; }
-        double bI = kNegInf, bM = kNegInf, bD = kNegInf;
+        for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNI; }
+        T bI = kNI, bM = kNI, bD = kNI;
         const bool first_row = FIRST && lane == 0;
         const bool carried = !FIRST && lane == 0;
         const bool carry_out = !LAST && lane == 31;
@@ -912,7 +965,7 @@ banded_long_kernel(const LongArgs a)
             if (wpr > 1) wait_carry(s - 1, min(B, NC));
             if (lane < B) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) ring.carry[0][k][lane] = __ldcg(&carry[(size_t)k * P + lane]);
+                for (int k = 0; k < 3; ++k) ring.carry[0][k][lane] = ldcg_t(&carry[(size_t)k * P + lane]);
             }
         }
 
@@ -930,60 +983,61 @@ banded_long_kernel(const LongArgs a)
                     if (lane < B) {
                         const int col = (sb + 1) * B + lane;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) ring.carry[(sb + 1) & 1][k][lane] = __ldcg(&carry[(size_t)k * P + col]);
+                        for (int k = 0; k < 3; ++k) ring.carry[(sb + 1) & 1][k][lane] = ldcg_t(&carry[(size_t)k * P + col]);
                     }
                 }
             }
             if (sb < n_cblocks) wait_block(sb);
             __syncwarp();
-            const double* cr = &ring.carry[sb & 1][0][0];
+            const T* cr = &ring.carry[sb & 1][0][0];
 
             auto step = [&](const int i, auto guard_c) {
                 constexpr bool GUARD = decltype(guard_c)::value;
                 const int t = t0 + i;
-                double uI0 = shfl_up_f64(cI[RPL - 1], 1);
-                double uM0 = shfl_up_f64(cM[RPL - 1], 1);
-                double uD0 = shfl_up_f64(cD[RPL - 1], 1);
+                T uI0 = shfl_up_t(cI[RPL - 1]);
+                T uM0 = shfl_up_t(cM[RPL - 1]);
+                T uD0 = shfl_up_t(cD[RPL - 1]);
                 const int c = t - lane;
                 if (GUARD && (c < 0 || c >= NC || lane >= nl)) return;
                 if (!FIRST && carried) { uI0 = cr[i]; uM0 = cr[B + i]; uD0 = cr[2 * B + i]; }
                 // this lane's 16 consecutive ring slots of the block (mirror: no wrap inside the block)
-                const uint32_t wa = w_blk + (uint32_t)i * 80u;
-                const double2 w01 = lds128(wa), w23 = lds128(wa + 16), w45 = lds128(wa + 32);
-                const double2 w67 = lds128(wa + 48), w89 = lds128(wa + 64);
-                const double wII = w01.x, wIM = w01.y, wID = w23.x, wMI = w23.y, wMM = w45.x, wMD = w45.y;
-                const double wDI = w67.x, wDM = w67.y, wDD = w89.x, aw = w89.y;
+                T wv[10];
+                lds_weights(w_blk + (uint32_t)i * (uint32_t)WB, wv);
+                const T wII = wv[0], wIM = wv[1], wID = wv[2], wMI = wv[3], wMM = wv[4], wMD = wv[5];
+                const T wDI = wv[6], wDM = wv[7], wDD = wv[8], aw = wv[9];
 
-                double nM[RPL], nD[RPL], eIr[RPL];
+                T nM[RPL], nD[RPL], eIr[RPL];
                 uint32_t word = 0;
                 static_for<0, RPL>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    const double2 e = lds128(e_blk[j] + (uint32_t)i * 16u);       // {eI, eM}
-                    eIr[j] = e.x;
-                    const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-                    nM[j] = max3_first<6 * j + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word);
-                    nD[j] = max3_first<6 * j + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word);
+                    T eI, eM;
+                    lds_pair(e_blk[j] + (uint32_t)i * (uint32_t)EB, eI, eM);
+                    eIr[j] = eI;
+                    const T oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
+                    nM[j] = max3_t<6 * j + 2>((oI + wMI) + eM, (oM + wMM) + eM, (oD + wMD) + eM, word);
+                    nD[j] = max3_t<6 * j + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word);
                 });
                 if (FIRST && first_row) {
-                    const double2 f = ldg128(img_v1 + v1_off + (size_t)c * 16u);
-                    nM[0] = f.y;
-                    eIr[0] = f.x;
+                    T fI, fM;
+                    ldg_pair(img_v1 + v1_off + (size_t)c * (size_t)EB, fI, fM);
+                    nM[0] = fM;
+                    eIr[0] = fI;
                 }
                 if (c == acc_col) {
 #pragma unroll
                     for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
                 }
-                if (aw > kNegInf) {
+                if (aw > kNI) {
 #pragma unroll
                     for (int j = 0; j < RPL; ++j) {
-                        const double cand = nD[j] + aw;
+                        const T cand = nD[j] + aw;
                         if (cand > acc[j]) { acc[j] = cand; acc_tb[j] = (uint16_t)c; }   // stored as it changes (see banded_sweep)
                     }
                 }
-                double uI = uI0, uM = uM0, uD = uD0;
+                T uI = uI0, uM = uM0, uD = uD0;
                 static_for<0, RPL>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    double vI = max3_first<6 * j>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word);
+                    T vI = max3_t<6 * j>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word);
                     if (FIRST && j == 0 && first_row) vI = eIr[0];
                     uI = vI; uM = nM[j]; uD = nD[j];
                     cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
@@ -994,7 +1048,7 @@ banded_long_kernel(const LongArgs a)
                     carry_t[t] = cI[RPL - 1]; carry_t[(size_t)P + t] = cM[RPL - 1]; carry_t[(size_t)2 * P + t] = cD[RPL - 1];
                 }
                 if (LAST && lane == ln) {
-                    double fI = cI[0], fM = cM[0], fD = cD[0];
+                    T fI = cI[0], fM = cM[0], fD = cD[0];
 #pragma unroll
                     for (int j = 1; j < RPL; ++j)
                         if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
@@ -1014,8 +1068,8 @@ banded_long_kernel(const LongArgs a)
             // the next block starts 16 ring slots further on (mod 64)
             {
                 const bool wrap = slot0 + B >= 64u;
-                const uint32_t dw = wrap ? (uint32_t)(B * 80) - 64u * 80u : (uint32_t)(B * 80);
-                const uint32_t de = wrap ? (uint32_t)(B * 16) - 64u * 16u : (uint32_t)(B * 16);
+                const uint32_t dw = wrap ? (uint32_t)(B * WB) - 64u * (uint32_t)WB : (uint32_t)(B * WB);
+                const uint32_t de = wrap ? (uint32_t)(B * EB) - 64u * (uint32_t)EB : (uint32_t)(B * EB);
                 slot0 = (slot0 + B) & 63u;
                 w_blk += dw;
 #pragma unroll
@@ -1046,24 +1100,25 @@ banded_long_kernel(const LongArgs a)
     if (sub != (n_stripes - 1) % wpr) return;
     const int NF = M->NF;
     int32_t* __restrict__ ftb = a.ftb + slot * 32;
+    const T* __restrict__ fin_w = LT::fin_w(M);
     for (int f = 0; f < NF; ++f) {
         const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
-        double best = kNegInf;
+        T best = kNI;
         int arg = 0x7fffffff;
         for (int k = k0 + lane; k < k1; k += 32) {
             const int code = M->fin_src[k];
-            const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
-            const double cand = sv + M->fin_w[k];
+            const T sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
+            const T cand = sv + fin_w[k];
             if (cand > best) { best = cand; arg = k; }
         }
-        warp_argmax_first(best, arg);
+        warp_argmax_first_t(best, arg);
         if (lane == 0) {
             s_fval[warp][f] = best;
-            ftb[f] = (best > kNegInf) ? M->fin_src[arg] : 0;
+            ftb[f] = (best > kNI) ? M->fin_src[arg] : 0;
         }
         __syncwarp();
     }
-    if (lane == 0) a.logp[q] = s_fval[warp][M->end_final];
+    if (lane == 0) a.logp[q] = (double)s_fval[warp][M->end_final];
 }
 
 // =============================================================================================

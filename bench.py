@@ -795,14 +795,15 @@ class ShardRunner(object):
         goff, off = wl["group_off"], wl["seq_off"]
         flags = engine.DEVICE_BUFFERS | engine.WANT_SUMMARY
         chunk = chunk_loci if (compile_in_region and chunk_loci > 0) else n_loci
-        # chunk boundaries: the first chunks are small (1/8, 1/4, 1/2 of a chunk), because nothing runs on
-        # the device while the first one is compiled
+        # chunk boundaries: nothing runs on the device while the first chunk is compiled, so the chunks start
+        # small and grow by half each time -- slowly enough that decoding chunk k still covers compiling chunk
+        # k+1 when a rank has only a few host threads (8 ranks on a 32-core box: 24 us vs 44 us per locus)
         bounds, lo = [0], 0
-        ramp = [8, 4, 2] if (compile_in_region and 0 < chunk < n_loci) else []
+        size = max(chunk // 64, 128) if (compile_in_region and 0 < chunk < n_loci) else max(chunk, 1)
         while lo < n_loci:
-            size = max(chunk // ramp.pop(0), 64) if ramp else max(chunk, 1)
             lo = min(n_loci, lo + size)
             bounds.append(lo)
+            size = min(max(chunk, 1), size + size // 2)
         compile_ms, prev = 0.0, None
         self.e0.record(self.stream)
         # reads: the first chunk's on the compute stream, every later chunk's on a side stream while the chunk

@@ -738,3 +738,36 @@ def test_random_shapes_native_models_and_long_reads_vs_oracle(ctx, seed, monkeyp
         assert same_bits(res.logp, want_lp), (seed, len(left), len(right), copies, eps)
         assert_paths_equal([res.path(i) for i in range(len(res))], want_paths, "native + long reads")
         dm.close()
+
+
+@pytest.mark.parametrize("wpr", [1, 8])
+def test_fp32_mode_on_long_reads(ctx, wpr, monkeypatch):
+    """The optional fp32 mode covers the striped long-read kernel too (the same kernel instantiated for
+    float: float image, float carry rows): bit-equal to the float restatement of the reference recurrence
+    (oracle_viterbi_f32), within the stated tolerance of the fp64 result."""
+    from advntr_b200 import engine, read_matcher, synth
+    monkeypatch.setenv("ADVHMM_LONG_WPR", str(wpr))
+    rng = random.Random(3200 + wpr)
+    ru = synth.rand_dna(rng, 37)
+    left, right = synth.rand_dna(rng, 100), synth.rand_dna(rng, 100)
+    model = read_matcher.get_read_matcher_model(left, right, [ru, synth.substitute(rng, ru, 0.1)], 40, error_rate=0.3)
+    dm = engine.DeviceModel(ctx, model.baked)
+    assert dm.info.smem_bytes > 227 * 1024
+    reads = [synth.sequencing_errors(rng, left + ru * k + right, 0.02, 0.05, 0.05) for k in (2, 9, 17, 33, 60)]
+    reads += [reads[2][:161], reads[3][:320], reads[3][:321], ""]
+    codes = [oracle.encode(r) for r in reads]
+    om = oracle.OracleModel(model.baked)
+    lp32, paths32 = om.viterbi(codes, fp32=True)
+    res = dm.viterbi(codes, precision="fp32")
+    assert same_bits(res.logp, lp32)
+    assert_paths_equal([res.path(i) for i in range(len(res))], paths32, "fp32 long reads")
+    lp64, _ = om.viterbi(codes)
+    assert np.all(np.abs(res.logp - lp64) <= 2e-5 * np.abs(lp64) + 2e-5)
+    # and a locus model (native compiler) builds its float tables on first use
+    from advntr_b200 import fast_compile
+    nat = fast_compile.compile_many([(left, right, [ru, synth.substitute(random.Random(3200 + wpr + 1), ru, 0.1)], 40, 0.3)], ctx)[0]
+    r2 = nat._device_model().viterbi(codes[:4], precision="fp32")
+    lp_n, _ = oracle.OracleModel(nat.baked).viterbi(codes[:4], fp32=True)
+    assert same_bits(r2.logp, lp_n)
+    nat._release_engine()
+    dm.close()
