@@ -723,10 +723,10 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
                     f = &fam_short;
                     pl.max_P_short = std::max(pl.max_P_short, mod->NCpad);
                     pl.max_smem_short = std::max(pl.max_smem_short, mod->banded_smem);
-                } else if (!forward) {
-                    f = &fam_long;
+                } else {
+                    f = &fam_long;                  // (forward too: the long-read kernel's log-sum-exp instantiation)
                     pl.max_P_long = std::max(pl.max_P_long, mod->NCpad);
-                }                                   // forward of long reads: generic kernel
+                }
             }
             if (f == &fam_generic) pl.max_m_generic = std::max(pl.max_m_generic, mod->m);
             f->max_len = std::max(f->max_len, len);
@@ -989,7 +989,11 @@ int run_batch(advhmm_context* ctx, advhmm_model* const* models, int n_models, co
         la.carry = reinterpret_cast<double*>(wl + lo_carry); la.carry_stride = 3 * Pl;
         la.ftb = reinterpret_cast<int32_t*>(wl + lo_ftb);
         la.wpr = long_wpr;
-        if (fp32) {
+        if (forward) {
+            if (int rc = allow_max_dynamic_smem(ctx, banded_long_kernel<double, true>)) return rc;
+            ProfScope prof(ctx, 0);
+            banded_long_kernel<double, true><<<tile1 - tile0, kLongWarps * 32, kLongWarps * sizeof(LongRing<double>), ctx->stream>>>(la);
+        } else if (fp32) {
             if (int rc = allow_max_dynamic_smem(ctx, banded_long_kernel<float>)) return rc;
             ProfScope prof(ctx, 0);
             banded_long_kernel<float><<<tile1 - tile0, kLongWarps * 32, kLongWarps * sizeof(LongRing<float>), ctx->stream>>>(la);

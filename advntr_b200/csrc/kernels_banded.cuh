@@ -833,10 +833,13 @@ __device__ __forceinline__ void warp_argmax_first_t(float& v, int& idx)
     }
 }
 
-template <typename T>
+// FWD (double only): the forward algorithm (log_probability) on the same stripes -- log-sum-exp in place of the
+// max, emission added after the sum (hmm.pyx:1444), no traceback; first row from the forward table M->f1.
+template <typename T, bool FWD = false>
 __global__ void __launch_bounds__(kLongWarps * 32, 2)
 banded_long_kernel(const LongArgs a)
 {
+    static_assert(!FWD || std::is_same<T, double>::value, "forward runs in double");
     using LT = LongT<T>;
     constexpr int RPL = kLongRPL, H = 32 * RPL, B = kRingBlk, WB = LT::WB, EB = LT::EB;
     const T kNI = (T)kNegInf;
@@ -858,7 +861,7 @@ banded_long_kernel(const LongArgs a)
     const size_t slot = (size_t)(item - a.chunk_base);
     const int n = a.rlen[q];
     if (n == 0) {
-        if (lane == 0 && sub == 0) a.logp[q] = (double)LT::empty(M);
+        if (lane == 0 && sub == 0) a.logp[q] = FWD ? M->logp_empty_fwd : (double)LT::empty(M);
         return;
     }
     // progress flags: release store by the lane that wrote the carried values, acquire load by the consumer
@@ -883,7 +886,7 @@ banded_long_kernel(const LongArgs a)
     LongRing<T>& ring = reinterpret_cast<LongRing<T>*>(smem_raw)[warp];
     const unsigned char* __restrict__ img = LT::image(M);
     const unsigned char* __restrict__ img_e = img + (size_t)LT::kE * P;
-    const unsigned char* __restrict__ img_v1 = img + (size_t)LT::kV1 * P;
+    const unsigned char* __restrict__ img_v1 = FWD ? reinterpret_cast<const unsigned char*>(M->f1) : img + (size_t)LT::kV1 * P;
     const uint32_t* __restrict__ pk = a.pk + a.pk_off[q];
     T* __restrict__ vfin = reinterpret_cast<T*>(a.vfin + slot * a.vfin_stride);        // (the float build uses half of it)
     T* __restrict__ carry = reinterpret_cast<T*>(a.carry + slot * a.carry_stride);
@@ -1014,8 +1017,13 @@ banded_long_kernel(const LongArgs a)
                     lds_pair(e_blk[j] + (uint32_t)i * (uint32_t)EB, eI, eM);
                     eIr[j] = eI;
                     const T oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-                    nM[j] = max3_t<6 * j + 2>((oI + wMI) + eM, (oM + wMM) + eM, (oD + wMD) + eM, word);
-                    nD[j] = max3_t<6 * j + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word);
+                    if constexpr (FWD) {
+                        nM[j] = lse3(oI + wMI, oM + wMM, oD + wMD) + eM;
+                        nD[j] = lse3(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD);
+                    } else {
+                        nM[j] = max3_t<6 * j + 2>((oI + wMI) + eM, (oM + wMM) + eM, (oD + wMD) + eM, word);
+                        nD[j] = max3_t<6 * j + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word);
+                    }
                 });
                 if (FIRST && first_row) {
                     T fI, fM;
@@ -1031,19 +1039,22 @@ banded_long_kernel(const LongArgs a)
 #pragma unroll
                     for (int j = 0; j < RPL; ++j) {
                         const T cand = nD[j] + aw;
-                        if (cand > acc[j]) { acc[j] = cand; acc_tb[j] = (uint16_t)c; }   // stored as it changes (see banded_sweep)
+                        if constexpr (FWD) acc[j] = lse2(acc[j], cand);
+                        else if (cand > acc[j]) { acc[j] = cand; acc_tb[j] = (uint16_t)c; }   // stored as it changes (see banded_sweep)
                     }
                 }
                 T uI = uI0, uM = uM0, uD = uD0;
                 static_for<0, RPL>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    T vI = max3_t<6 * j>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word);
+                    T vI;
+                    if constexpr (FWD) vI = lse3(uI + wII, uM + wIM, uD + wID) + eIr[j];
+                    else vI = max3_t<6 * j>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word);
                     if (FIRST && j == 0 && first_row) vI = eIr[0];
                     uI = vI; uM = nM[j]; uD = nD[j];
                     cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
                 });
                 bI = uI0; bM = uM0; bD = uD0;
-                tbw_t[t] = word;
+                if constexpr (!FWD) tbw_t[t] = word;
                 if (!LAST && carry_out) {                           // full stripe: lane 31 owns its last position
                     carry_t[t] = cI[RPL - 1]; carry_t[(size_t)P + t] = cM[RPL - 1]; carry_t[(size_t)2 * P + t] = cD[RPL - 1];
                 }
@@ -1101,6 +1112,32 @@ banded_long_kernel(const LongArgs a)
     const int NF = M->NF;
     int32_t* __restrict__ ftb = a.ftb + slot * 32;
     const T* __restrict__ fin_w = LT::fin_w(M);
+    if constexpr (FWD) {
+        for (int f = 0; f < NF; ++f) {
+            const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
+            double mx = kNegInf;
+            for (int k = k0 + lane; k < k1; k += 32) {
+                const int code = M->fin_src[k];
+                const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
+                mx = fmax(mx, sv + M->fin_w[k]);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, shfl_xor_f64(mx, off));
+            double sum = 0.0;
+            if (mx > kNegInf)
+                for (int k = k0 + lane; k < k1; k += 32) {
+                    const int code = M->fin_src[k];
+                    const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
+                    sum += exp(sv + M->fin_w[k] - mx);
+                }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += shfl_xor_f64(sum, off);
+            if (lane == 0) s_fval[warp][f] = (mx > kNegInf) ? mx + log(sum) : kNegInf;
+            __syncwarp();
+        }
+        if (lane == 0) a.logp[q] = s_fval[warp][M->end_final];
+        return;
+    }
     for (int f = 0; f < NF; ++f) {
         const int k0 = M->fin_off[f], k1 = M->fin_off[f + 1];
         T best = kNI;

@@ -771,3 +771,29 @@ def test_fp32_mode_on_long_reads(ctx, wpr, monkeypatch):
     assert same_bits(r2.logp, lp_n)
     nat._release_engine()
     dm.close()
+
+
+@pytest.mark.parametrize("wpr", [1, 4])
+def test_forward_on_long_reads_banded(ctx, wpr, monkeypatch):
+    """log_probability of reads beyond the register wavefront's 320 bases, and of any read of a model whose
+    tables exceed shared memory: the striped long-read kernel instantiated with log-sum-exp (round 1 sent
+    these to the generic kernel).  1e-9 relative against the C restatement of hmm.pyx:1371-1484; the generic
+    forward kernel must agree too."""
+    from advntr_b200 import engine, read_matcher, synth
+    monkeypatch.setenv("ADVHMM_LONG_WPR", str(wpr))
+    rng = random.Random(640 + wpr)
+    ru = synth.rand_dna(rng, 29)
+    left, right = synth.rand_dna(rng, 100), synth.rand_dna(rng, 100)
+    small = read_matcher.get_read_matcher_model(left, right, [ru], 6, error_rate=0.05)       # image fits in shared memory
+    big = read_matcher.get_read_matcher_model(left, right, [ru], 45, error_rate=0.3)          # it does not
+    for model in (small, big):
+        dm = engine.DeviceModel(ctx, model.baked)
+        reads = [synth.sequencing_errors(rng, left + ru * k + right, 0.02, 0.03, 0.03) for k in (1, 5, 12, 30)]
+        reads += [reads[3][:321], reads[3][:160], reads[2][:100], "", "T"]
+        codes = [oracle.encode(r) for r in reads]
+        want = oracle.OracleModel(model.baked).log_probability(codes)
+        got = dm.log_probability(codes)
+        assert np.allclose(got, want, rtol=1e-9, atol=0), (got, want)
+        gen = dm.log_probability(codes, force_generic=True)
+        assert np.allclose(gen, want, rtol=1e-9, atol=0)
+        dm.close()
