@@ -485,8 +485,9 @@ class DeviceModel(object):
                              fp32=(precision == "fp32"), want_summary=want_summary)
 
     def log_probability(self, codes, force_generic=False):
-        """Forward log-probabilities (``hmm.pyx:1258-1313``): banded wavefront kernel for reads up to
-        320 bases on profile-shaped models, generic kernel otherwise (or with ``force_generic``)."""
+        """Forward log-probabilities (``hmm.pyx:1258-1313``): profile-shaped models run on the banded kernels
+        (register wavefront up to 320 bases, the striped long-read kernel beyond and for models larger than
+        shared memory), anything else -- or everything with ``force_generic`` -- on the generic kernel."""
         seqs, off = pack_reads(codes)
         R = len(codes)
         logp = np.empty(R, dtype=np.float64)
