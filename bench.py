@@ -312,9 +312,9 @@ class Dist(object):
             raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback of the hot path")
         torch.cuda.set_device(self.local)
         if self.world > 1:
-            # NCCL prints its version banner to stdout; the contract is ONE JSON line on stdout
-            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-                os.environ["NCCL_DEBUG"] = "WARN"
+            # whatever NCCL_DEBUG level the launcher asks for (its version banner included) goes to stderr:
+            # the contract is ONE JSON line on stdout
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
     def barrier(self):
