@@ -6,7 +6,9 @@
 //
 // Files: engine_types.cuh (handles, device descriptors), kernels_common.cuh (TMA / mbarrier /
 // shuffle helpers, pack kernel), kernels_banded.cuh, kernels_generic.cuh, model_compile.hpp
-// (host-side graph analysis), this file (model upload, batch planning, launches, C-ABI).
+// (host-side graph analysis of one baked model), locus_compile.hpp (native compiler of the
+// read-matcher models of whole batches of loci: shape structures, parameter chains, device tables),
+// this file (model upload, batch planning, launches, C-ABI).
 //
 // Kernels (all hand-written, no tensor cores -- this is max-plus DP, not a contraction):
 //   pack_reads_kernel        byte codes -> 2-bit packed reads (+ reverse complement, validation)
@@ -16,9 +18,11 @@
 //                            shared memory with one TMA bulk copy per CTA; 6-bit traceback per
 //                            (position, column) packed into one word per lane and step.
 //   banded_fill_f32_kernel   the same schedule in float (optional ADVHMM_FP32 mode)
-//   banded_long_kernel       long reads / models larger than shared memory: 160-position
-//                            stripes, carry through HBM, the model image streamed through a
-//                            per-warp ring in shared memory by TMA bulk copies
+//   banded_long_kernel<T,FWD> long reads / models larger than shared memory: 160-position
+//                            stripes dealt to 1..8 warps per read, carry through HBM with
+//                            release / acquire progress flags, the model image streamed through a
+//                            per-warp ring in shared memory by TMA bulk copies; instantiated for
+//                            double (Viterbi), float (ADVHMM_FP32) and double forward
 //   banded_backtrack_kernel  device backtrack to the state path + on-device path reducers
 //   generic_fill_kernel<FWD> any baked model: row-synchronous CSR kernel, silent states by level;
 //                            FWD = log_probability (sum-product with the reference's pair_lse)

@@ -12,7 +12,7 @@ def load(name):
     lines = [l for l in open(path).read().strip().splitlines() if l.startswith("{")]
     if not lines:
         return None
-    shutil.copy(path, os.path.join(P, name + ".json"))
+    open(os.path.join(P, name + ".json"), "w").write(lines[-1] + "\n")     # the JSON line only (older runs had an NCCL banner before it)
     return json.loads(lines[-1])
 
 
