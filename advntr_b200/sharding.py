@@ -46,3 +46,25 @@ def gather_results(local, owner, rank, world_size, group=None):
     if any(v is None for v in out):
         raise RuntimeError("some units were not decoded by any rank")
     return out
+
+
+def gathered_row_of_every_read(owner, reads_per_unit, rows_max):
+    """Where the reads of every unit sit in the table an ``all_gather`` of the per-rank result rows gives.
+
+    Each rank decodes its units in ascending unit order and writes one result row per read, padded to
+    ``rows_max`` rows per rank; the gathered table is rank-major.  Returns an int64 array ``idx`` with one
+    entry per read in UNIT order: row ``idx[k]`` of the gathered table is read ``k``."""
+    import numpy as np
+    owner = np.asarray(owner)
+    n = np.asarray(reads_per_unit, dtype=np.int64)
+    first = np.zeros(len(n) + 1, dtype=np.int64)
+    np.cumsum(n, out=first[1:])
+    idx = np.empty(int(first[-1]), dtype=np.int64)
+    for r in range(int(owner.max()) + 1 if len(owner) else 0):
+        pos = r * int(rows_max)
+        for u in np.nonzero(owner == r)[0]:
+            idx[first[u]:first[u + 1]] = pos + np.arange(n[u])
+            pos += int(n[u])
+        if pos > (r + 1) * int(rows_max):
+            raise ValueError("rank %d holds more rows than rows_max" % r)
+    return idx

@@ -905,15 +905,11 @@ def strong_scaling_leg(args, D, ctx, stream, generator, n_loci, steps, resident=
         if check is not None:
             # rows of rank r = its loci in ascending id, reads in generator order; rank 0 decoded ALL loci
             # by itself before (reads in locus order): the gathered table must hold exactly those rows
+            from advntr_b200 import sharding
             want_lp, want_summ = check
-            first = np.zeros(n_loci + 1, dtype=np.int64)
-            np.cumsum(reads_per_locus, out=first[1:])
-            for r in range(world):
-                ids_r = np.nonzero(owner == r)[0]
-                idx = np.concatenate([np.arange(first[i], first[i + 1]) for i in ids_r]) if len(ids_r) else np.zeros(0, dtype=np.int64)
-                rows = res[r * R_max:r * R_max + len(idx)]
-                ok = ok and bool(np.array_equal(rows[:, 0], want_lp.view(np.int64)[idx]))
-                ok = ok and bool(np.array_equal(np.ascontiguousarray(rows[:, 1:]).view(np.int32).reshape(-1, 8), want_summ[idx]))
+            rows = res[sharding.gathered_row_of_every_read(owner, reads_per_locus, R_max)]     # locus order
+            ok = ok and bool(np.array_equal(rows[:, 0], want_lp.view(np.int64)))
+            ok = ok and bool(np.array_equal(np.ascontiguousarray(rows[:, 1:]).view(np.int32).reshape(-1, 8), want_summ))
             if not ok:
                 raise SystemExit("strong-scaling leg: the gathered results differ from rank 0's own decode of all loci")
         out = {"what": "loci 1..%d split by sharding.lpt_assign over %d rank(s); per rank: pinned reads H2D + decode "

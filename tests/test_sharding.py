@@ -79,3 +79,48 @@ def test_cost_estimate_matches_the_generators_and_balances_config2():
         owner, load = sharding.lpt_assign(est, world)
         assert (max(load) - min(load)) / max(load) < 5e-3
         assert sorted(np.bincount(owner, minlength=world).tolist())[0] > 6719 // world - 60
+
+
+def _gather_worker(rank, world, port, out_dir):
+    import numpy as np
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from advntr_b200 import synth
+    n_loci = 300
+    est = [synth.locus_cost_estimate(i, "config2") for i in range(1, n_loci + 1)]
+    owner, _ = sharding.lpt_assign([e[1] for e in est], world)      # every rank computes the same assignment
+    owner = np.asarray(owner)
+    reads = np.asarray([e[0] for e in est], dtype=np.int64)
+    counts = [int(reads[owner == r].sum()) for r in range(world)]
+    rows_max = max(counts)
+    # this rank's result rows: (locus id, read index within the locus), its loci in ascending order
+    mine = np.nonzero(owner == rank)[0]
+    rows = torch.zeros((rows_max, 2), dtype=torch.int64)
+    k = 0
+    for u in mine:
+        for j in range(int(reads[u])):
+            rows[k, 0], rows[k, 1] = int(u), j
+            k += 1
+    table = torch.empty((world * rows_max, 2), dtype=torch.int64)
+    dist.all_gather_into_tensor(table, rows)
+    if rank == 0:
+        idx = sharding.gathered_row_of_every_read(owner, reads, rows_max)
+        got = table.numpy()[idx]
+        want = np.array([(u, j) for u in range(n_loci) for j in range(int(reads[u]))], dtype=np.int64)
+        np.save(os.path.join(out_dir, "ok.npy"), np.array([int(np.array_equal(got, want)), len(want), len(set(owner.tolist()))]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather_of_result_rows(tmp_path):
+    """The strong-scaling legs of bench.py gather one result row per read with ONE all_gather of the
+    per-rank tables (NCCL on the GPUs; gloo here) and put them back into locus order with
+    sharding.gathered_row_of_every_read: two ranks, 300 config-2 loci, every read's row must land where the
+    single-rank order has it."""
+    import numpy as np
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ok, n_rows, ranks_used = np.load(os.path.join(str(tmp_path), "ok.npy"))
+    assert ok == 1 and n_rows > 40000 and ranks_used == 2
