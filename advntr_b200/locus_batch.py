@@ -180,8 +180,12 @@ class LocusDecoder(object):
         vpaths += [(seq, self._vpath(res, i)) for i, seq in enumerate(ref)]
         copies = read_matcher.copies_for_read_length(self.read_length, len(self.pattern))
         flank = self.read_length                      # vntr_finder.py:681-683
-        return read_matcher.get_read_matcher_model(self.left_flank[-flank:], self.right_flank[:flank], None,
-                                                   copies, vpaths, error_rate=self.error_rate)
+        # get_read_matcher_model(..., vpaths) estimates the repeat-unit profile from the alignment of the repeat
+        # segments the paths mark out (hmm_utils.py:427-429); everything else is the model of that alignment,
+        # which the native compiler builds (tests: update_model.npz, made by the reference's own call)
+        alignment = path_utils.get_multiple_alignment_of_repeats_from_reads(vpaths)
+        return fast_compile.get_read_matcher_model(self.left_flank[-flank:], self.right_flank[:flank], alignment,
+                                                   copies, error_rate=self.error_rate)
 
     def frameshift_candidate(self, selected):
         """Most frequent frame-shifting indel state among the selected reads and its count

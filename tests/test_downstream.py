@@ -93,6 +93,13 @@ def test_update_model_tables_bit_identical(down):
     assert list(z["scalars"]) == [b["n_states"], b["silent_start"], b["start_index"], b["end_index"], b["finite"]]
     assert np.array_equal(b["in_off"], z["in_off"]) and np.array_equal(b["in_src"], z["in_src"])
     assert same_bits(b["in_logp"], z["in_logp"]) and same_bits(b["emis"], z["emis"])
+    # the native compiler, given the alignment the paths mark out, builds the same model (what
+    # LocusDecoder.updated_model does)
+    from advntr_b200 import fast_compile
+    nat = fast_compile.get_read_matcher_model(left[-150:], right[:150], inp["alignment"], copies)
+    assert [s.name for s in nat.states] == str(z["names"]).split("\n")
+    assert np.array_equal(nat.baked["in_src"], z["in_src"])
+    assert same_bits(nat.baked["in_logp"], z["in_logp"]) and same_bits(nat.baked["emis"], z["emis"])
     # and the reads decoded on it give the reference's paths (oracle restatement here, device below)
     lp, vps = _oracle_decoder(new)(inp["reads"])
     assert same_bits(lp, z["logp"])
