@@ -15,7 +15,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG, "csrc", "advhmm.cu")
 DEPS = [SRC] + [os.path.join(PKG, "csrc", f) for f in
-                ("model_compile.hpp", "locus_compile.hpp", "engine_types.cuh", "kernels_common.cuh", "kernels_banded.cuh",
+                ("model_compile.hpp", "locus_compile.hpp", "locus_calls.hpp", "engine_types.cuh", "kernels_common.cuh", "kernels_banded.cuh",
                  "kernels_generic.cuh", "kernels_kfilter.cuh")] + [os.path.join(os.path.dirname(PKG), "include", "advhmm.h")]
 LIB = os.path.join(PKG, "libadvhmm.so")
 

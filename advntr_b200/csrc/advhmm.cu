@@ -8,6 +8,7 @@
 // shuffle helpers, pack kernel), kernels_banded.cuh, kernels_generic.cuh, model_compile.hpp
 // (host-side graph analysis of one baked model), locus_compile.hpp (native compiler of the
 // read-matcher models of whole batches of loci: shape structures, parameter chains, device tables),
+// locus_calls.hpp (host: per-read results of many loci -> recruitment, spanning test, genotype calls),
 // this file (model upload, batch planning, launches, C-ABI).
 //
 // Kernels (all hand-written, no tensor cores -- this is max-plus DP, not a contraction):
@@ -34,6 +35,7 @@
 // skip / reorder the candidates it does.
 #include "kernels_generic.cuh"
 #include "kernels_kfilter.cuh"
+#include "locus_calls.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -1928,6 +1930,62 @@ int advhmm_kfilter_scan(advhmm_kfilter* kf, const char* seqs, const int64_t* seq
         CU_TRY(cudaMemcpyAsync(hit_locus, d_l, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(cudaMemcpyAsync(hit_count, d_c, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return ADVHMM_OK;
+}
+
+// ---- the step after the path: per-read results of many loci -> genotype calls (host, all threads) ----
+int advhmm_genotypes_from_summaries(int64_t n_loci, const int64_t* group_off, const int32_t* n_mapped,
+                                    const int32_t* n_unmapped, const double* min_score,
+                                    const double* logp, const advhmm_read_summary* summaries, const int32_t* path_len,
+                                    const int64_t* seq_off, uint32_t flags, int32_t min_repeat_bp, int32_t n_threads,
+                                    advhmm_locus_call* out, uint8_t* read_class)
+{
+    if (n_loci < 0 || (n_loci > 0 && (!group_off || !n_mapped || !n_unmapped || !logp || !summaries || !path_len || !seq_off || !out)))
+        return set_error(ADVHMM_EINVAL, "null argument");
+    if (flags & ~(ADVHMM_CALL_ACCURACY_FILTER | ADVHMM_CALL_HAPLOID)) return set_error(ADVHMM_EINVAL, "unknown flag");
+    for (int64_t g = 0; g < n_loci; ++g) {
+        if (n_mapped[g] < 0 || n_unmapped[g] < 0 || group_off[g] < 0 ||
+            group_off[g + 1] - group_off[g] != (int64_t)n_mapped[g] + 2 * (int64_t)n_unmapped[g])
+            return set_error(ADVHMM_EINVAL, "locus %lld: group of %lld reads does not hold %d mapped reads + 2 x %d unmapped reads",
+                             (long long)g, (long long)(group_off[g + 1] - group_off[g]), n_mapped[g], n_unmapped[g]);
+    }
+    try {
+        if (read_class && n_loci) memset(read_class + group_off[0], 0, (size_t)(group_off[n_loci] - group_off[0]));
+        const calls::ReadView R{logp, summaries, path_len, seq_off};
+        const bool acc = flags & ADVHMM_CALL_ACCURACY_FILTER, hap = flags & ADVHMM_CALL_HAPLOID;
+        const int nt = n_threads > 0 ? n_threads : rm::default_threads();
+        // loci in blocks so that a worker takes a few hundred microseconds of work per grab
+        const int64_t block = 64, n_blocks = (n_loci + block - 1) / block;
+        rm::parallel_for((size_t)n_blocks, nt, [&](size_t b, int) {
+            for (int64_t g = (int64_t)b * block; g < std::min<int64_t>(n_loci, ((int64_t)b + 1) * block); ++g)
+                calls::call_locus(R, group_off[g], n_mapped[g], n_unmapped[g], min_score ? min_score[g] : NAN, acc, hap,
+                                  min_repeat_bp, out[g], read_class);
+        });
+    } catch (const std::bad_alloc&) {
+        return set_error(ADVHMM_ENOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        return set_error(ADVHMM_EINVAL, "%s", e.what());
+    }
+    return ADVHMM_OK;
+}
+
+int advhmm_genotypes_from_counts(int64_t n_lists, const int32_t* observed, const int64_t* obs_off, uint32_t flags,
+                                 advhmm_locus_call* out)
+{
+    if (n_lists < 0 || (n_lists > 0 && (!obs_off || !out))) return set_error(ADVHMM_EINVAL, "null argument");
+    if (flags & ~(ADVHMM_CALL_ACCURACY_FILTER | ADVHMM_CALL_HAPLOID)) return set_error(ADVHMM_EINVAL, "unknown flag");
+    try {
+        for (int64_t i = 0; i < n_lists; ++i) {
+            if (obs_off[i + 1] < obs_off[i]) return set_error(ADVHMM_EINVAL, "obs_off must not decrease");
+            std::vector<int32_t> v(observed + obs_off[i], observed + obs_off[i + 1]);
+            if (flags & ADVHMM_CALL_ACCURACY_FILTER) v = calls::drop_unsupported(v);
+            const calls::Genotype g = calls::genotype_from_observed(v.data(), v.size(), flags & ADVHMM_CALL_HAPLOID);
+            out[i] = advhmm_locus_call{g.found ? 1 : 0, g.c1, g.c2, (int32_t)(obs_off[i + 1] - obs_off[i]), (int32_t)v.size(), 0,
+                                       g.max_prob};
+        }
+    } catch (const std::bad_alloc&) {
+        return set_error(ADVHMM_ENOMEM, "out of host memory");
     }
     return ADVHMM_OK;
 }

@@ -19,6 +19,10 @@ WANT_PATH, BOTH_STRANDS, FP32, FORCE_GENERIC, WANT_SUMMARY, DEVICE_BUFFERS, DEVI
 SUMMARY_DTYPE = np.dtype([(n, np.int32) for n in ("repeats", "n_match", "repeat_bp", "left_bp", "right_bp",
                                                    "left_hits", "right_hits", "unit_starts_ends")])
 KIND_GENERIC, KIND_BANDED = 0, 1
+CALL_ACCURACY_FILTER, CALL_HAPLOID = 0x1, 0x2
+# ``advhmm_locus_call``: what the native stage after the decode returns per locus
+CALL_DTYPE = np.dtype([("has_call", np.int32), ("c1", np.int32), ("c2", np.int32), ("recruited", np.int32),
+                       ("spanning", np.int32), ("flanking", np.int32), ("max_prob", np.float64)], align=True)
 
 EXPORTS = (
     "advhmm_context_create", "advhmm_context_destroy", "advhmm_context_synchronize",
@@ -31,6 +35,7 @@ EXPORTS = (
     "advhmm_last_error", "advhmm_abi_version", "advhmm_encode_acgt",
     "advhmm_set_vexp", "advhmm_models_create_for_loci", "advhmm_shape_cache_clear",
     "advhmm_model_dims_get", "advhmm_model_tables_get", "advhmm_model_banded_tables_get",
+    "advhmm_genotypes_from_summaries", "advhmm_genotypes_from_counts",
 )
 
 
@@ -130,6 +135,8 @@ def load_library():
         lib.advhmm_model_dims_get.argtypes = [vp, C.POINTER(ModelDims)]
         lib.advhmm_model_tables_get.argtypes = [vp, vp, vp, vp, vp, vp]
         lib.advhmm_model_banded_tables_get.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp]
+        lib.advhmm_genotypes_from_summaries.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp, u32, i32, i32, vp, vp]
+        lib.advhmm_genotypes_from_counts.argtypes = [i64, vp, vp, u32, vp]
         # parameter chains go through numpy.exp, as the reference's do (the library's default is libm)
         lib.advhmm_set_vexp(_vexp_keepalive, None)
         _lib = lib
@@ -174,6 +181,55 @@ def pack_reads(codes):
     for c, a, b in zip(codes, off[:-1], off[1:]):
         flat[a:b] = c
     return flat, off
+
+
+def genotypes_from_summaries(group_off, n_mapped, n_unmapped, min_score, logp, summaries, path_len, seq_off,
+                             accuracy_filter=False, is_haploid=False, min_repeat_bp=2, threads=0, want_read_class=False):
+    """``advhmm_genotypes_from_summaries``: the per-read results of many loci (what
+    ``advhmm_viterbi_multi_summary`` returned) -> one ``CALL_DTYPE`` record per locus, on all host
+    threads.  ``min_score``: one float per locus, NaN (or None for all) = no minimum score known.
+    -> (calls, read_class or None)."""
+    group_off = np.ascontiguousarray(group_off, dtype=np.int64)
+    n_loci = len(group_off) - 1
+    n_mapped = np.ascontiguousarray(n_mapped, dtype=np.int32)
+    n_unmapped = np.ascontiguousarray(n_unmapped, dtype=np.int32)
+    if len(n_mapped) != n_loci or len(n_unmapped) != n_loci:
+        raise ValueError("one (mapped, unmapped) pair per locus")
+    score = None if min_score is None else np.ascontiguousarray(min_score, dtype=np.float64)
+    if score is not None and len(score) != n_loci:
+        raise ValueError("one minimum score per locus")
+    logp = np.ascontiguousarray(logp, dtype=np.float64)
+    summaries = np.ascontiguousarray(summaries, dtype=SUMMARY_DTYPE)
+    path_len = np.ascontiguousarray(path_len, dtype=np.int32)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+    n_reads = int(group_off[-1]) if n_loci else 0
+    if min(len(logp), len(summaries), len(path_len), len(seq_off) - 1) < n_reads:
+        raise ValueError("per-read arrays are shorter than group_off says")
+    calls = np.zeros(n_loci, dtype=CALL_DTYPE)
+    read_class = np.zeros(max(n_reads, 1), dtype=np.uint8) if want_read_class else None
+    flags = (CALL_ACCURACY_FILTER if accuracy_filter else 0) | (CALL_HAPLOID if is_haploid else 0)
+    _check(load_library().advhmm_genotypes_from_summaries(
+        n_loci, group_off.ctypes.data, n_mapped.ctypes.data, n_unmapped.ctypes.data,
+        score.ctypes.data if score is not None else None, logp.ctypes.data, summaries.ctypes.data, path_len.ctypes.data,
+        seq_off.ctypes.data, flags, int(min_repeat_bp), int(threads), calls.ctypes.data,
+        read_class.ctypes.data if want_read_class else None))
+    return calls, (read_class[:n_reads] if want_read_class else None)
+
+
+def genotypes_from_counts(count_lists, accuracy_filter=False, is_haploid=False):
+    """``advhmm_genotypes_from_counts``: ``find_genotype_based_on_observed_repeats`` for many lists of
+    observed repeat counts -> ``CALL_DTYPE`` records (``has_call`` 0 = the reference's ``None``)."""
+    n = len(count_lists)
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        np.cumsum(np.fromiter(map(len, count_lists), dtype=np.int64, count=n), out=off[1:])
+    flat = np.zeros(max(int(off[-1]), 1), dtype=np.int32)
+    for c, a, b in zip(count_lists, off[:-1], off[1:]):
+        flat[a:b] = c
+    calls = np.zeros(n, dtype=CALL_DTYPE)
+    flags = (CALL_ACCURACY_FILTER if accuracy_filter else 0) | (CALL_HAPLOID if is_haploid else 0)
+    _check(load_library().advhmm_genotypes_from_counts(n, flat.ctypes.data, off.ctypes.data, flags, calls.ctypes.data))
+    return calls
 
 
 class LociColumns(object):

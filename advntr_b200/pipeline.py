@@ -11,8 +11,8 @@ their reads one by one (``vntr_finder.py:727-767``).  Here
    in ONE ``advhmm_viterbi_multi_summary`` call; the backtrack kernels reduce every path on the
    device to the handful of numbers adVNTR reads off it (``advhmm_read_summary``), so no state path
    crosses the bus;
-3. recruitment (``recruit_read``), the spanning test and the genotype statistics run per locus on
-   those numbers (numpy, no per-read Python).
+3. recruitment (``recruit_read``), the spanning test and the genotype statistics of all loci run on those
+   numbers in one native call on all host threads (``advhmm_genotypes_from_summaries``).
 
 Decisions are the ones ``LocusDecoder`` makes read by read from full paths (tests/test_pipeline.py
 checks they are identical).  The caller either passes the mapped reads per locus (``genotype``) or an
@@ -138,17 +138,41 @@ class GenotypingRun(object):
         models = [d.model._device_model() for d in self.decoders]
         res = self.ctx._run(models, np.asarray(goff, dtype=np.int64), seqs, off, False, False, False, None,
                             want_summary=True)
-        lens = (off[1:] - off[:-1]).astype(np.float64)
-        calls = genotypes_from_summaries(res.logp, res.summaries, res.path_len, lens, goff, layout,
-                                         [d.min_score_to_select_a_read() for d in self.decoders],
-                                         accuracy_filter, is_haploid, self.decoders[0].min_repeat_bp_to_add_read
-                                         if self.decoders else 2)
+        calls = native_genotypes_from_summaries(res.logp, res.summaries, res.path_len, off, goff, layout,
+                                                [d.min_score_to_select_a_read() for d in self.decoders],
+                                                accuracy_filter, is_haploid, self.decoders[0].min_repeat_bp_to_add_read
+                                                if self.decoders else 2)
         return {dec.id: c for dec, c in zip(self.decoders, calls)}
+
+
+def native_genotypes_from_summaries(logp, S, path_len, seq_off, goff, layout, scores, accuracy_filter=False,
+                                    is_haploid=False, min_repeat_bp=2, threads=0):
+    """The step after the decode for all loci in ONE native call (``advhmm_genotypes_from_summaries``, all
+    host threads): same arguments as ``genotypes_from_summaries`` except that the read offsets are passed
+    instead of the lengths; same list of result dicts (tests/test_locus_calls.py compares the two)."""
+    goff = np.asarray(goff, dtype=np.int64)
+    score = np.array([np.nan if s is None else s for s in scores], dtype=np.float64)
+    calls, cls = engine.genotypes_from_summaries(goff, [m for m, _ in layout], [u for _, u in layout], score, logp, S,
+                                                 path_len, seq_off, accuracy_filter, is_haploid, min_repeat_bp, threads,
+                                                 want_read_class=True)
+    repeats = np.asarray(S["repeats"])
+    out = []
+    for g, c in enumerate(calls):
+        a, b = int(goff[g]), int(goff[g + 1])
+        k, r = cls[a:b], repeats[a:b]
+        out.append({"copy_numbers": (int(c["c1"]), int(c["c2"])) if c["has_call"] else None,
+                    "recruited_reads_count": int(c["recruited"]), "spanning_reads_count": int(c["spanning"]),
+                    "flanking_reads_count": int(c["flanking"]), "maximum_likelihood": float(c["max_prob"]),
+                    "covered_repeats": r[k == 1].tolist(),
+                    "flanking_repeats": [] if accuracy_filter else sorted(r[k == 2].tolist())})
+    return out
 
 
 def genotypes_from_summaries(logp, S, path_len, lens, goff, layout, scores, accuracy_filter=False, is_haploid=False,
                              min_repeat_bp=2):
-    """Recruitment (``recruit_read``, ``vntr_finder.py:179-190``), the better strand of every unmapped read
+    """The literal numpy / Python form of the step after the decode (the checker of the native
+    ``advhmm_genotypes_from_summaries``, which ``GenotypingRun`` uses).
+    Recruitment (``recruit_read``, ``vntr_finder.py:179-190``), the better strand of every unmapped read
     (``:235-254``), the spanning test (``:311-322``) and the genotype statistics (``:846-875``) of every locus
     from the per-read device results: ``logp``, the on-device path summaries ``S`` (``advhmm_read_summary``
     records), ``path_len`` (< 0: impossible read) and the read lengths.  ``layout[g]`` = (mapped reads,

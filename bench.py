@@ -547,18 +547,25 @@ def run_ours(args):
         n_chunks = 4
         chunk = (len(models) + n_chunks - 1) // n_chunks
 
-        def pipeline_pass(cold, chunked=True):
+        decoys2 = 2 * args.decoys
+        n_map = np.ascontiguousarray(np.diff(goff) - decoys2, dtype=np.int32)      # per locus: mapped reads, then both
+        n_unm = np.full(len(models), args.decoys, dtype=np.int32)                  # strands of every unmapped read
+
+        def pipeline_pass(cold, chunked=True, calls=False):
             if cold:
                 lib.advhmm_shape_cache_clear()
             torch.cuda.synchronize()
             t_a = time.perf_counter()
-            _, comp_ms = runner.one_pass(True, chunk if chunked else len(models))
+            _, comp_ms = runner.one_pass(True, chunk if chunked else len(models), calls=(n_map, n_unm) if calls else None)
             return (time.perf_counter() - t_a) * 1e3, comp_ms
 
         pipeline_pass(True)                             # warm-up of the route itself (staging buffers, memory pool)
         cold = [pipeline_pass(True) for _ in range(args.steps)]
         warm = [pipeline_pass(False) for _ in range(args.steps)]
         serial = [pipeline_pass(True, chunked=False) for _ in range(args.steps)]
+        pipeline_pass(True, calls=True)
+        to_calls = [pipeline_pass(True, calls=True) for _ in range(args.steps)]
+        pipeline_calls = runner.calls.copy()
         if not args.no_e2e:
             got = runner.h_all.numpy()[:R]
             assert np.array_equal(got[:, 0], h_logp.numpy().view(np.int64)), "pipeline scores differ from the resident-model route"
@@ -567,7 +574,7 @@ def run_ours(args):
         pipeline = {"cold_ms": float(np.mean([c[0] for c in cold])), "cold_compile_ms": float(np.mean([c[1] for c in cold])),
                     "warm_ms": float(np.mean([c[0] for c in warm])), "warm_compile_ms": float(np.mean([c[1] for c in warm])),
                     "serial_ms": float(np.mean([c[0] for c in serial])), "serial_compile_ms": float(np.mean([c[1] for c in serial])),
-                    "chunks": n_chunks}
+                    "calls_ms": float(np.mean([c[0] for c in to_calls])), "chunks": n_chunks}
         del runner
 
     # ---- extra (reported, not the headline): fp32 mode; the pageable drop-in route ----------------
@@ -614,10 +621,28 @@ def run_ours(args):
             layout = [(int(goff[g + 1] - goff[g]) - decoys2, args.decoys) for g in range(len(models))]
             Sv = h_summ.numpy().view(engine.SUMMARY_DTYPE).reshape(-1)
             tg = time.perf_counter()
-            calls = _pl.genotypes_from_summaries(h_logp.numpy(), Sv, h_plen.numpy(), np.diff(off).astype(np.float64),
-                                                 goff, layout, [None] * len(models))
-            extra["genotype_stage_loci_per_s"] = len(models) / (time.perf_counter() - tg)
+            with np.errstate(all="ignore"):
+                calls = _pl.genotypes_from_summaries(h_logp.numpy(), Sv, h_plen.numpy(), np.diff(off).astype(np.float64),
+                                                     goff, layout, [None] * len(models))
+            extra["genotype_stage_python_loci_per_s"] = len(models) / (time.perf_counter() - tg)
             extra["loci_with_a_genotype"] = sum(1 for c in calls if c["copy_numbers"] is not None)
+            # the same stage in the library (advhmm_genotypes_from_summaries, all host threads / one thread)
+            lm, lu = [m for m, _ in layout], [u for _, u in layout]
+            for key, nt in (("genotype_stage_loci_per_s", 0), ("genotype_stage_one_thread_loci_per_s", 1)):
+                tg = time.perf_counter()
+                for _ in range(5):
+                    nat, _ = engine.genotypes_from_summaries(goff, lm, lu, None, h_logp.numpy(), Sv, h_plen.numpy(), off, threads=nt)
+                extra[key] = 5 * len(models) / (time.perf_counter() - tg)
+            same = all((c["copy_numbers"] == ((int(n["c1"]), int(n["c2"])) if n["has_call"] else None)) and
+                       c["recruited_reads_count"] == n["recruited"] and c["spanning_reads_count"] == n["spanning"] and
+                       c["flanking_reads_count"] == n["flanking"] and
+                       (float(c["maximum_likelihood"]) == float(n["max_prob"]) or np.isnan(n["max_prob"]))
+                       for c, n in zip(calls, nat))
+            if pipeline is not None:
+                same = same and nat.tobytes() == pipeline_calls.tobytes()      # the pipeline leg ended in the same records
+            if not same:
+                raise SystemExit("native genotype stage differs from the Python form")
+            extra["genotype_stage_equal_to_python_form"] = True
         # pageable drop-in route: model.viterbi_batch(list of str) -> (logp, paths) per locus, Python objects
         if rank == 0:
             from advntr_b200 import fast_compile
@@ -653,7 +678,8 @@ def run_ours(args):
     # ---- max over ranks -------------------------------------------------------------------------
     ms_all, e2e_all = D.reduce([ms, e2e_ms or 0.0], "max")
     reads_all, cells_all, relax_all = D.reduce([float(R), stats["cells"], stats["relaxations"]], "sum")
-    pipe_all = D.reduce([pipeline["cold_ms"], pipeline["warm_ms"], pipeline["serial_ms"]], "max") if pipeline else None
+    pipe_all = D.reduce([pipeline["cold_ms"], pipeline["warm_ms"], pipeline["serial_ms"], pipeline["calls_ms"]], "max") \
+        if pipeline else None
     loci_all = D.reduce([float(len(models))], "sum")[0]
 
     if rank == 0:
@@ -676,7 +702,7 @@ def run_ours(args):
                            "gcups": cells_all * K / (e2e_all * 1e-3) / 1e9,
                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_all / K}
         if pipeline:
-            cold_ms, warm_ms, serial_ms = pipe_all
+            cold_ms, warm_ms, serial_ms, calls_ms = pipe_all
             line["pipeline"] = {
                 "what": "per rank: locus descriptions (flank codes, aligned repeat segments) + pinned host reads in -> "
                         "H2D -> per chunk of loci advhmm_models_create_for_loci (profiles, parameter chains, device "
@@ -695,6 +721,11 @@ def run_ours(args):
                 "warm": {"loci_per_s": loci_all / (warm_ms * 1e-3), "reads_per_s": reads_all / (warm_ms * 1e-3),
                          "ms_per_step": warm_ms, "compile_ms": pipeline["warm_compile_ms"],
                          "note": "shapes cached (a second sample of the same panel); models still compiled per step"},
+                "cold_to_genotypes": {"loci_per_s": loci_all / (calls_ms * 1e-3), "reads_per_s": reads_all / (calls_ms * 1e-3),
+                                      "ms_per_step": calls_ms,
+                                      "note": "the cold pass carried on to the end of the reference's per-locus loop: per-read "
+                                              "results to the host (44 B/read) and advhmm_genotypes_from_summaries on all host "
+                                              "threads (recruit_read, strand choice, spanning test, genotype call of every locus)"},
                 "host_threads": compile_threads()}
         if extra:
             ex = {}
@@ -712,9 +743,14 @@ def run_ours(args):
                                            "ru_concordance = share of reads whose repeat count equals the fp64 one"}
             if "genotype_stage_loci_per_s" in extra:
                 ex["genotype_stage"] = {"value": extra["genotype_stage_loci_per_s"], "unit": "loci/s",
+                                        "one_thread": extra["genotype_stage_one_thread_loci_per_s"],
+                                        "python_form": extra["genotype_stage_python_loci_per_s"],
+                                        "equal_to_python_form": extra["genotype_stage_equal_to_python_form"],
                                         "loci_with_a_genotype": extra["loci_with_a_genotype"],
-                                        "note": "pipeline.genotypes_from_summaries on the summaries of all loci: recruitment, "
-                                                "strand choice, spanning test, genotype likelihoods (host numpy / Python, one process)"}
+                                        "note": "advhmm_genotypes_from_summaries on the summaries of all loci: recruitment, "
+                                                "strand choice, spanning test, genotype likelihoods (native host code, all "
+                                                "threads / one thread); python_form = pipeline.genotypes_from_summaries, the "
+                                                "numpy / Python statement of the same stage (its checker), one process"}
             if "pageable_reads_per_s" in extra:
                 ex["pageable_python_route"] = {"value": extra["pageable_reads_per_s"], "unit": "reads/s",
                                                "loci": extra["pageable_loci"],
@@ -788,8 +824,12 @@ class ShardRunner(object):
         n = D.world * self.rows_max if D.rank == 0 else self.rows_max
         self.h_all = torch.empty((n, 5), dtype=torch.int64).pin_memory()
 
-    def one_pass(self, compile_in_region=False, chunk_loci=0, gather=False):
-        """-> (device ms of this rank's own work, host ms spent inside model compilation)."""
+    def one_pass(self, compile_in_region=False, chunk_loci=0, gather=False, calls=None):
+        """-> (device ms of this rank's own work, host ms spent inside model compilation).
+        ``calls`` = (n_mapped, n_unmapped) per locus: the per-read results go to the host as three plain arrays
+        and the native step after the decode (advhmm_genotypes_from_summaries: recruitment, strand choice,
+        spanning test, genotype call of every locus, all host threads) runs on them; ``self.calls`` holds its
+        records."""
         torch, engine, lib, ctx = self.D.torch, self.engine, self.lib, self.ctx
         wl, R, n_loci = self.wl, self.R, self.n_loci
         goff, off = wl["group_off"], wl["seq_off"]
@@ -843,6 +883,22 @@ class ShardRunner(object):
                 if prev is not None:
                     destroy_models(*prev)                          # freed in stream order: no wait for the device
                 prev = (hs, hi - lo)
+        if calls is not None:
+            if not hasattr(self, "h_logp"):
+                self.h_logp = torch.empty(max(R, 1), dtype=torch.float64).pin_memory()
+                self.h_summ = torch.empty((max(R, 1), 8), dtype=torch.int32).pin_memory()
+                self.h_plen = torch.empty(max(R, 1), dtype=torch.int32).pin_memory()
+            self.e1.record(self.stream)
+            self.h_logp.copy_(self.d_logp, non_blocking=True)
+            self.h_summ.copy_(self.d_summ, non_blocking=True)
+            self.h_plen.copy_(self.d_plen, non_blocking=True)
+            torch.cuda.synchronize()
+            if prev is not None:
+                destroy_models(*prev)
+            self.calls, _ = engine.genotypes_from_summaries(
+                goff, calls[0], calls[1], None, self.h_logp.numpy(), self.h_summ.numpy().view(engine.SUMMARY_DTYPE).reshape(-1),
+                self.h_plen.numpy(), off)
+            return self.e0.elapsed_time(self.e1), compile_ms
         if R:
             self.d_res[:R, 0] = self.d_logp[:R].view(torch.int64)
             self.d_res[:R, 1:] = self.d_summ[:R].view(torch.int64).reshape(R, 4)

@@ -253,6 +253,38 @@ int advhmm_viterbi_multi_summary(advhmm_context* ctx,
                                  int32_t* path, int64_t path_cap, int64_t* path_total,
                                  advhmm_read_summary* summaries);
 
+/* ---- from the per-read results of many loci to their genotype calls (the step after the path) ----
+ * Replaces, for whole batches of loci and on all host threads, what VNTRFinder does with the Viterbi
+ * results of a locus's reads: recruit_read (vntr_finder.py:179-190), the better strand of every filtered
+ * unmapped read (:235-254), the spanning test (:311-322), spanning + flanking repeat counts (:846-875)
+ * and find_genotype_based_on_observed_repeats (:486-532).  Host code: the inputs are what
+ * advhmm_viterbi_multi_summary delivered (host arrays).  Locus g owns reads group_off[g] ..
+ * group_off[g+1]-1: first its n_mapped[g] mapped reads, then BOTH strands (forward, reverse complement)
+ * of its n_unmapped[g] keyword-filtered unmapped reads.  min_score[g] = the locus's minimum Viterbi
+ * score (scaled_score * read length, vntr_finder.py:166-177) or NaN when none is known (recruit_read's
+ * fallback rule).  max_prob is the reference's float (same factors, same order, libm pow).
+ * read_class (optional, [n_reads]): 0 not recruited, 1 spanning read, 2 flanking read. */
+#define ADVHMM_CALL_ACCURACY_FILTER 0x1u   /* settings / --accuracy-filter: drop counts seen < 3 times, no flanking reads */
+#define ADVHMM_CALL_HAPLOID         0x2u   /* --haploid */
+typedef struct advhmm_locus_call {
+    int32_t has_call;        /* 0: nothing observed (the reference returns None)                  */
+    int32_t c1, c2;          /* the genotype's two copy numbers (c2 = 0: one allele observed)     */
+    int32_t recruited;       /* reads that passed recruit_read                                     */
+    int32_t spanning;        /* of those, spanning reads that entered the call                    */
+    int32_t flanking;        /* flanking reads                                                     */
+    double  max_prob;        /* posterior of the call (1e-20 when has_call = 0)                    */
+} advhmm_locus_call;
+int advhmm_genotypes_from_summaries(int64_t n_loci, const int64_t* group_off, const int32_t* n_mapped,
+                                    const int32_t* n_unmapped, const double* min_score,
+                                    const double* logp, const advhmm_read_summary* summaries, const int32_t* path_len,
+                                    const int64_t* seq_off, uint32_t flags, int32_t min_repeat_bp, int32_t n_threads,
+                                    advhmm_locus_call* calls, uint8_t* read_class);
+/* find_genotype_based_on_observed_repeats (vntr_finder.py:486-532) for count lists: list i =
+ * observed[obs_off[i] .. obs_off[i+1]) (PacBio spanning reads, :566-585: with ADVHMM_CALL_ACCURACY_FILTER
+ * counts seen < 3 times are dropped first). */
+int advhmm_genotypes_from_counts(int64_t n_lists, const int32_t* observed, const int64_t* obs_off, uint32_t flags,
+                                 advhmm_locus_call* calls);
+
 /* ---- keyword pre-filter (the step before the hot path) ----------------------------------------
  * Replaces the Aho-Corasick scan of the `adVNTR-Filtering` binary (filtering/main.cc:229-300,
  * fed by genome_analyzer.py:173-197): count, for every read and locus, the occurrences of the
