@@ -38,6 +38,7 @@
 #include "locus_calls.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <set>
 #include <unordered_map>
@@ -1987,6 +1988,58 @@ int advhmm_genotypes_from_counts(int64_t n_lists, const int32_t* observed, const
     } catch (const std::bad_alloc&) {
         return set_error(ADVHMM_ENOMEM, "out of host memory");
     }
+    return ADVHMM_OK;
+}
+
+int advhmm_frameshift_candidates(int64_t n_loci, const int64_t* group_off, const int32_t* pattern_len, const double* min_score,
+                                 const int64_t* state_off, const uint8_t* state_class, const int32_t* state_label,
+                                 const double* logp, const advhmm_read_summary* summaries, const int32_t* path_len,
+                                 const int64_t* path_off, const int32_t* path, const uint8_t* seqs, const int64_t* seq_off,
+                                 int32_t n_threads, advhmm_frameshift_call* out)
+{
+    if (n_loci < 0 || (n_loci > 0 && (!group_off || !pattern_len || !state_off || !state_class || !state_label || !logp ||
+                                      !summaries || !path_len || !path_off || !path || !seqs || !seq_off || !out)))
+        return set_error(ADVHMM_EINVAL, "null argument");
+    for (int64_t g = 0; g < n_loci; ++g)
+        if (group_off[g] < 0 || group_off[g + 1] < group_off[g] || state_off[g + 1] < state_off[g])
+            return set_error(ADVHMM_EINVAL, "locus %lld: offsets must not decrease", (long long)g);
+    std::atomic<int64_t> bad{-1};
+    try {
+        const calls::ReadView R{logp, summaries, path_len, seq_off};
+        const int nt = n_threads > 0 ? n_threads : rm::default_threads();
+        const int64_t block = 16, n_blocks = (n_loci + block - 1) / block;
+        rm::parallel_for((size_t)n_blocks, nt, [&](size_t b, int) {
+            std::vector<calls::Mutation> mut;
+            std::vector<int32_t> lengths;
+            std::vector<std::pair<int32_t, int32_t>> first_visit;
+            for (int64_t g = (int64_t)b * block; g < std::min<int64_t>(n_loci, ((int64_t)b + 1) * block); ++g) {
+                mut.clear();
+                const int64_t n_states = state_off[g + 1] - state_off[g];
+                advhmm_frameshift_call c{};
+                c.base = -1;
+                for (int64_t i = group_off[g]; i < group_off[g + 1]; ++i) {
+                    if (!calls::recruit_read(R, i, min_score ? min_score[g] : NAN, calls::flank_rate(summaries[i]))) continue;
+                    ++c.selected;
+                    c.repeat_bp += summaries[i].repeat_bp;
+                    const int32_t* p = path + path_off[i];
+                    for (int32_t k = 0; k < path_len[i]; ++k)
+                        if (p[k] < 0 || p[k] >= n_states) { bad.store(i); return; }
+                    calls::frameshift_mutations_of_read(
+                        calls::PathView{p, path_len[i], state_class + state_off[g], state_label + state_off[g], seqs + seq_off[i]},
+                        pattern_len[g], mut, lengths, first_visit);
+                }
+                if (const calls::Mutation* m = calls::frameshift_candidate(mut)) {
+                    c.kind = m->kind; c.column = m->column; c.base = m->base; c.count = m->count;
+                }
+                out[g] = c;
+            }
+        });
+    } catch (const std::bad_alloc&) {
+        return set_error(ADVHMM_ENOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        return set_error(ADVHMM_EINVAL, "%s", e.what());
+    }
+    if (bad.load() >= 0) return set_error(ADVHMM_EINVAL, "read %lld: a path entry is not a state of its locus's model", (long long)bad.load());
     return ADVHMM_OK;
 }
 

@@ -148,11 +148,11 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
 #pragma unroll
     for (int j = 0; j < RPL; ++j) { cI[j] = cM[j] = cD[j] = acc[j] = kNegInf; }
     double bI = kNegInf, bM = kNegInf, bD = kNegInf;   // row above my block, previous column
-    const bool store_last = ALIGNED && lane == ln;
     // lane-skewed views: index them with the step t (column c = t - lane).  The empty asm keeps
     // ptxas from re-deriving these addresses inside the loop.
     uint32_t* tbw_t = tbw - (ptrdiff_t)lane * NW;
-    double* vfin_t = vfin - lane;
+    double* vfin_t = vfin - 3 * lane;                   // interleaved: vfin[3 c + {0, 1, 2}] = I, M, D of column c
+    const uint32_t store_flag = ALIGNED ? (uint32_t)(lane == ln) : 0u;
     uint32_t w_t = s_base - (uint32_t)lane * 80u;       // + 80 t  -> w10[c]
     uint32_t e_t[RPL];                                  // + 16 t  -> e2[sym_j][c]
 #pragma unroll
@@ -163,8 +163,9 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
     // skewed wavefront).  The steady phase, where every lane has a column, runs without the test and
     // without the divergence scope around it, so that consecutive steps form one basic block and the
     // tail of the I-slot chain of step t can overlap the M / D work of step t+1 (kStepUnroll).
-    auto step = [&](const int t, auto guard_c) {
+    auto step = [&](const int t, auto guard_c, auto acc_c) {
         constexpr bool GUARD = decltype(guard_c)::value;
+        constexpr bool ACC = decltype(acc_c)::value;       // some lane may sit on the collector's column in this step
         // the row above my block at column c was finished by lane-1 in the previous step
         const double uI0 = shfl_up_f64(cI[RPL - 1], 1);
         const double uM0 = shfl_up_f64(cM[RPL - 1], 1);
@@ -207,7 +208,7 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
         }
         // collector (end_repeating_pattern_match): D of its column is the best unit_end so far.
         // Both cases are rare per lane (1 and `copies` columns of NC), hence real branches.
-        if (c == acc_col) {
+        if (ACC && c == acc_col) {
 #pragma unroll
             for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
         }
@@ -247,27 +248,38 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
         else reinterpret_cast<uint2*>(tbw_t)[t] = make_uint2(word[0], word[NW - 1]);
 #endif
         if (ALIGNED) {
-            if (store_last) { vfin_t[t] = cI[RPL - 1]; vfin_t[P + t] = cM[RPL - 1]; vfin_t[2 * P + t] = cD[RPL - 1]; }
+            // predicated stores, no branch: the step stays one basic block up to the collector
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
+                         "@p st.global.f64 [%0], %1;\n\t@p st.global.f64 [%0+8], %2;\n\t@p st.global.f64 [%0+16], %3;\n\t}"
+                         :: "l"(vfin_t + 3 * t), "d"(cI[RPL - 1]), "d"(cM[RPL - 1]), "d"(cD[RPL - 1]), "r"(store_flag) : "memory");
         } else if (lane == ln) {
             double fI = cI[0], fM = cM[0], fD = cD[0];
 #pragma unroll
             for (int j = 1; j < RPL; ++j)
                 if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
-            vfin_t[t] = fI; vfin_t[P + t] = fM; vfin_t[2 * P + t] = fD;
+            vfin_t[3 * t] = fI; vfin_t[3 * t + 1] = fM; vfin_t[3 * t + 2] = fD;
         }
     };
     // Lanes >= nl have no read positions: in the steady phase they run along (results land in their
     // own registers and in traceback words nobody reads), in the guarded phases they skip.
-    const int steps = NC + nl - 1;
-    const int t_steady = steps < 31 ? steps : 31, t_down = NC > t_steady ? NC : t_steady;
+    const int NCu = __reduce_max_sync(0xffffffffu, NC);
+    const int steps = __reduce_max_sync(0xffffffffu, NC + nl - 1);
+    const int t_steady = steps < 31 ? steps : 31, t_down = NCu > t_steady ? NCu : t_steady;
+    // lane L reaches the collector's column at step acc_col + L: only the 32 steps from acc_col on carry the select
+    const int accu = __reduce_max_sync(0xffffffffu, acc_col);
+    const int t_acc0 = min(max(accu, t_steady), t_down), t_acc1 = min(max(accu + 32, t_steady), t_down);
 #pragma unroll 1
-    for (int t = 0; t < t_steady; ++t) step(t, std::true_type{});
+    for (int t = 0; t < t_steady; ++t) step(t, std::true_type{}, std::true_type{});
     // unrolled x3 for reads up to 160 bp (+4.5 % measured, 2..6 alike, 8 outgrows the instruction cache);
     // 6 and 7 rows per lane spill at 128 registers and stay rolled; 8..10 rows (255 registers) take x2 (+1..2 %)
 #pragma unroll (RPL <= 5 ? kStepUnroll : RPL >= 8 ? 2 : 1)
-    for (int t = t_steady; t < t_down; ++t) step(t, std::false_type{});
+    for (int t = t_steady; t < t_acc0; ++t) step(t, std::false_type{}, std::false_type{});
 #pragma unroll 1
-    for (int t = t_down; t < steps; ++t) step(t, std::true_type{});
+    for (int t = t_acc0; t < t_acc1; ++t) step(t, std::false_type{}, std::true_type{});
+#pragma unroll (RPL <= 5 ? kStepUnroll : RPL >= 8 ? 2 : 1)
+    for (int t = t_acc1; t < t_down; ++t) step(t, std::false_type{}, std::false_type{});
+#pragma unroll 1
+    for (int t = t_down; t < steps; ++t) step(t, std::true_type{}, std::true_type{});
     // (which unit_end fed the collector, per read position, was stored as it changed: acc_tb, read by
     // the backtrack only and only for rows whose collector value is finite)
 }
@@ -299,12 +311,12 @@ banded_fill_kernel(const BandedArgs a)
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     mbar_wait(&s_bar, 0);
-    if (warp >= tile.cnt) return;
+    if (__reduce_max_sync(0xffffffffu, (int)(warp >= tile.cnt))) return;
 
     const int item = tile.first + warp;
     const int q = a.order[item];
     const size_t slot = (size_t)(item - a.chunk_base);
-    const int n = a.rlen[q];
+    const int n = __reduce_max_sync(0xffffffffu, a.rlen[q]);
     if (n == 0) {
         if (lane == 0) a.logp[q] = M->logp_empty;
         return;
@@ -343,7 +355,7 @@ banded_fill_kernel(const BandedArgs a)
         int arg = 0x7fffffff;
         for (int k = k0 + lane; k < k1; k += 32) {
             const int code = M->fin_src[k];
-            const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[code];
+            const double sv = code < 0 ? s_fval[warp][-(code + 1)] : vfin[3 * (code % P) + code / P];
             const double cand = sv + M->fin_w[k];
             if (cand > best) { best = cand; arg = k; }
         }
@@ -994,8 +1006,9 @@ banded_long_kernel(const LongArgs a)
             __syncwarp();
             const T* cr = &ring.carry[sb & 1][0][0];
 
-            auto step = [&](const int i, auto guard_c) {
+            auto step = [&](const int i, auto guard_c, auto acc_c) {
                 constexpr bool GUARD = decltype(guard_c)::value;
+                constexpr bool ACC = decltype(acc_c)::value;        // some lane may reach the collector's column in this block
                 const int t = t0 + i;
                 T uI0 = shfl_up_t(cI[RPL - 1]);
                 T uM0 = shfl_up_t(cM[RPL - 1]);
@@ -1031,7 +1044,7 @@ banded_long_kernel(const LongArgs a)
                     nM[0] = fM;
                     eIr[0] = fI;
                 }
-                if (c == acc_col) {
+                if (ACC && c == acc_col) {
 #pragma unroll
                     for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
                 }
@@ -1068,13 +1081,15 @@ banded_long_kernel(const LongArgs a)
             };
             // steady blocks: every lane has a column at every step (lanes beyond the stripe's last row run
             // along, as in banded_sweep); boundary blocks test per step
-            if (t0 >= 31 && t0 + B <= NC && t0 + B <= steps) {
+            // (the lanes of a block sit on columns t0 - 31 .. t0 + B - 1: the three blocks that can touch the
+            // collector's column take the guarded loop, which carries its select)
+            if (t0 >= 31 && t0 + B <= NC && t0 + B <= steps && (acc_col < t0 - 31 || acc_col >= t0 + B)) {
 #pragma unroll (kLongUnroll)
-                for (int i = 0; i < B; ++i) step(i, std::false_type{});
+                for (int i = 0; i < B; ++i) step(i, std::false_type{}, std::false_type{});
             } else {
                 const int i_end = min(B, steps - t0);
 #pragma unroll 1
-                for (int i = 0; i < i_end; ++i) step(i, std::true_type{});
+                for (int i = 0; i < i_end; ++i) step(i, std::true_type{}, std::true_type{});
             }
             // the next block starts 16 ring slots further on (mod 64)
             {

@@ -154,6 +154,15 @@ inline double flank_rate(const advhmm_read_summary& s)
     return right < left ? right : left;
 }
 
+// recruit_read (vntr_finder.py:179-190); `score` NaN = no minimum Viterbi score known for the locus
+inline bool recruit_read(const ReadView& R, int64_t i, double score, double rate)
+{
+    const bool possible = R.path_len[i] >= 0;
+    if (score == score) return R.logp[i] > score && rate >= 0.9 && possible;
+    const double len = (double)(R.seq_off[i + 1] - R.seq_off[i]);
+    return (double)R.S[i].n_match >= 0.9 * len && R.logp[i] > -len && rate >= 0.9 && possible;
+}
+
 // One locus: reads [a, a + n_mapped) are its mapped reads, then both strands of n_unm filtered unmapped reads.
 // `score` NaN = no minimum Viterbi score known for the locus (recruit_read's fallback rule).
 inline void call_locus(const ReadView& R, int64_t a, int32_t n_mapped, int32_t n_unm, double score, bool accuracy_filter,
@@ -164,15 +173,7 @@ inline void call_locus(const ReadView& R, int64_t a, int32_t n_mapped, int32_t n
     auto consider = [&](int64_t i) {
         const advhmm_read_summary& s = R.S[i];
         const double rate = flank_rate(s);
-        const bool possible = R.path_len[i] >= 0;
-        bool keep;
-        if (score == score) {
-            keep = R.logp[i] > score && rate >= 0.9 && possible;
-        } else {
-            const double len = (double)(R.seq_off[i + 1] - R.seq_off[i]);
-            keep = (double)s.n_match >= 0.9 * len && R.logp[i] > -len && rate >= 0.9 && possible;
-        }
-        if (!keep) return;
+        if (!recruit_read(R, i, score, rate)) return;
         ++recruited;
         const bool spanning = rate >= 0.95 && s.left_bp > 5 && s.right_bp > 5;
         (spanning ? covered : flanking).push_back(s.repeats);
@@ -195,6 +196,83 @@ inline void call_locus(const ReadView& R, int64_t a, int32_t n_mapped, int32_t n
     out.spanning = n_spanning;
     out.flanking = n_flanking;
     out.max_prob = g.max_prob;
+}
+
+// ---------------------------------------------------------------------------------------------
+// --frameshift mode: find_frameshift_from_selected_reads up to its binomial test (vntr_finder.py:265-300)
+// on the full state paths of a locus's recruited reads.  The reference reads state NAMES; here a state is
+// its class byte (include/advhmm.h: kind / part, as for the on-device reducers) plus, for the insert and
+// delete states of the repeat units, the number in its name ("I7_2" -> 7).
+// ---------------------------------------------------------------------------------------------
+struct Mutation {
+    int kind, column, base, count;                  // kind 2 = I, 3 = D (class-byte kinds); base -1 for deletions
+};
+
+struct PathView {
+    const int32_t* path;                            // the whole path, model start / end states included
+    int32_t len;
+    const uint8_t* cls;                             // class byte per state of the model
+    const int32_t* label;                           // number in the name of a repeat-unit I / D state
+    const uint8_t* seq;                             // the read as it was decoded, codes 0..3
+};
+
+// adds the frame-shifting indel states of one read to `mut` (insertion order kept: a Python dict)
+inline void frameshift_mutations_of_read(const PathView& v, int pattern_len, std::vector<Mutation>& mut,
+                                         std::vector<int32_t>& lengths, std::vector<std::pair<int32_t, int32_t>>& first_visit)
+{
+    lengths.clear();
+    first_visit.clear();
+    const int32_t a = 1, b = v.len - 1;             // vpath[1:-1]
+    // lengths of the repeat units on the path (get_repeating_pattern_lengths, hmm_utils.py:122-141)
+    {
+        int32_t bp = 0, open_at = -1;
+        for (int32_t k = a; k < b; ++k) {
+            const uint8_t c = v.cls[v.path[k]];
+            const int kind = c & 7;
+            if (kind == 1 || kind == 2) ++bp;
+            if (kind == 5 && open_at >= 0) lengths.push_back(bp - open_at);
+            if (kind == 4) open_at = bp;
+        }
+    }
+    int32_t unit = -1, pos = 0;                     // pos: read bases emitted before the current state
+    for (int32_t k = a; k < b; ++k) {
+        const int32_t st = v.path[k];
+        const uint8_t c = v.cls[st];
+        const int kind = c & 7, part = (c >> 3) & 3;
+        const int32_t here = pos;
+        if (kind == 1 || kind == 2) ++pos;
+        if (kind == 2 && part == 3) {               // first visit of an insert state: the base it emitted then
+            size_t f = 0;
+            while (f < first_visit.size() && first_visit[f].first != st) ++f;
+            if (f == first_visit.size()) first_visit.emplace_back(st, here);
+        }
+        if (kind == 4) ++unit;
+        if (kind != 2 && kind != 3) continue;
+        if (part != 3) continue;                    // flank states: names end with "fix"
+        if (unit < 0 || unit >= (int32_t)lengths.size()) continue;
+        const int32_t len = lengths[unit];
+        if (len == pattern_len || std::abs(len - pattern_len) > 2) continue;
+        int base = -1;
+        if (kind == 2) {
+            size_t f = 0;
+            while (first_visit[f].first != st) ++f;
+            base = v.seq[first_visit[f].second];
+        }
+        const int column = v.label[st];
+        size_t m = 0;
+        while (m < mut.size() && !(mut[m].kind == kind && mut[m].column == column && mut[m].base == base)) ++m;
+        if (m == mut.size()) mut.push_back(Mutation{kind, column, base, 1});
+        else ++mut[m].count;
+    }
+}
+
+// sorted(mutations.items(), key=count)[-1]: the largest count, the LAST inserted among equals
+inline const Mutation* frameshift_candidate(const std::vector<Mutation>& mut)
+{
+    const Mutation* best = nullptr;
+    for (const Mutation& m : mut)
+        if (!best || m.count >= best->count) best = &m;
+    return best;
 }
 
 }  // namespace calls

@@ -23,6 +23,9 @@ CALL_ACCURACY_FILTER, CALL_HAPLOID = 0x1, 0x2
 # ``advhmm_locus_call``: what the native stage after the decode returns per locus
 CALL_DTYPE = np.dtype([("has_call", np.int32), ("c1", np.int32), ("c2", np.int32), ("recruited", np.int32),
                        ("spanning", np.int32), ("flanking", np.int32), ("max_prob", np.float64)], align=True)
+# ``advhmm_frameshift_call``
+FRAMESHIFT_DTYPE = np.dtype([("kind", np.int32), ("column", np.int32), ("base", np.int32), ("count", np.int32),
+                             ("selected", np.int32), ("reserved", np.int32), ("repeat_bp", np.int64)], align=True)
 
 EXPORTS = (
     "advhmm_context_create", "advhmm_context_destroy", "advhmm_context_synchronize",
@@ -35,7 +38,7 @@ EXPORTS = (
     "advhmm_last_error", "advhmm_abi_version", "advhmm_encode_acgt",
     "advhmm_set_vexp", "advhmm_models_create_for_loci", "advhmm_shape_cache_clear",
     "advhmm_model_dims_get", "advhmm_model_tables_get", "advhmm_model_banded_tables_get",
-    "advhmm_genotypes_from_summaries", "advhmm_genotypes_from_counts",
+    "advhmm_genotypes_from_summaries", "advhmm_genotypes_from_counts", "advhmm_frameshift_candidates",
 )
 
 
@@ -137,6 +140,7 @@ def load_library():
         lib.advhmm_model_banded_tables_get.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp]
         lib.advhmm_genotypes_from_summaries.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp, u32, i32, i32, vp, vp]
         lib.advhmm_genotypes_from_counts.argtypes = [i64, vp, vp, u32, vp]
+        lib.advhmm_frameshift_candidates.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
         # parameter chains go through numpy.exp, as the reference's do (the library's default is libm)
         lib.advhmm_set_vexp(_vexp_keepalive, None)
         _lib = lib
@@ -230,6 +234,39 @@ def genotypes_from_counts(count_lists, accuracy_filter=False, is_haploid=False):
     flags = (CALL_ACCURACY_FILTER if accuracy_filter else 0) | (CALL_HAPLOID if is_haploid else 0)
     _check(load_library().advhmm_genotypes_from_counts(n, flat.ctypes.data, off.ctypes.data, flags, calls.ctypes.data))
     return calls
+
+
+def frameshift_candidates(group_off, pattern_len, min_score, state_tables, logp, summaries, path_len, path_off, paths,
+                          seqs, seq_off, threads=0):
+    """``advhmm_frameshift_candidates``: the path-walking part of ``find_frameshift_from_selected_reads``
+    (``vntr_finder.py:265-300``) for many loci on all host threads.  ``state_tables[g]`` = (class bytes,
+    name numbers) of locus g's model (``path_utils.frameshift_state_tables``); the per-read arrays are what a
+    ``WANT_PATH | WANT_SUMMARY`` call returned.  -> ``FRAMESHIFT_DTYPE`` records."""
+    group_off = np.ascontiguousarray(group_off, dtype=np.int64)
+    n_loci = len(group_off) - 1
+    if len(state_tables) != n_loci or len(pattern_len) != n_loci:
+        raise ValueError("one pattern length and one pair of state tables per locus")
+    state_off = np.zeros(n_loci + 1, dtype=np.int64)
+    if n_loci:
+        np.cumsum([len(c) for c, _ in state_tables], out=state_off[1:])
+    cls = np.ascontiguousarray(np.concatenate([c for c, _ in state_tables]) if n_loci else np.zeros(1), dtype=np.uint8)
+    lab = np.ascontiguousarray(np.concatenate([l for _, l in state_tables]) if n_loci else np.zeros(1), dtype=np.int32)
+    plen_ = np.ascontiguousarray(pattern_len, dtype=np.int32)
+    score = None if min_score is None else np.ascontiguousarray(min_score, dtype=np.float64)
+    logp = np.ascontiguousarray(logp, dtype=np.float64)
+    summaries = np.ascontiguousarray(summaries, dtype=SUMMARY_DTYPE)
+    path_len = np.ascontiguousarray(path_len, dtype=np.int32)
+    path_off = np.ascontiguousarray(path_off, dtype=np.int64)
+    paths = np.ascontiguousarray(paths, dtype=np.int32)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+    out = np.zeros(n_loci, dtype=FRAMESHIFT_DTYPE)
+    _check(load_library().advhmm_frameshift_candidates(
+        n_loci, group_off.ctypes.data, plen_.ctypes.data, score.ctypes.data if score is not None else None,
+        state_off.ctypes.data, cls.ctypes.data, lab.ctypes.data, logp.ctypes.data, summaries.ctypes.data,
+        path_len.ctypes.data, path_off.ctypes.data, paths.ctypes.data, seqs.ctypes.data, seq_off.ctypes.data, int(threads),
+        out.ctypes.data))
+    return out
 
 
 class LociColumns(object):

@@ -110,9 +110,10 @@ def get_repeat_segments_from_visited_states_and_region(visited_states, region):
     return out
 
 
-def get_flanking_regions_matching_rate(vpath, sequence, left_flank, right_flank, accuracy_filter=False):
-    """Fraction of flank match states whose read base equals the flank base; the smaller of the
-    two flanks' rates (``hmm_utils.py:209-268``)."""
+def flank_match_counts(vpath, sequence, left_flank, right_flank):
+    """(hits, bases) per flank, keyed ``"prefix"`` (right flank) / ``"suffix"`` (left flank): flank match states
+    whose read base equals the flank base, and read bases spent in the flank (``hmm_utils.py:209-262``).
+    The on-device path reducers deliver the same four numbers (``advhmm_read_summary``)."""
     names = _names(vpath)
     deepest = -1                      # index of the last left-flank column the path used
     prev = names[0]
@@ -139,6 +140,13 @@ def get_flanking_regions_matching_rate(vpath, sequence, left_flank, right_flank,
                     bases[side] += 1
         if emits:
             pos += 1
+    return hits, bases
+
+
+def get_flanking_regions_matching_rate(vpath, sequence, left_flank, right_flank, accuracy_filter=False):
+    """Fraction of flank match states whose read base equals the flank base; the smaller of the
+    two flanks' rates (``hmm_utils.py:209-268``)."""
+    hits, bases = flank_match_counts(vpath, sequence, left_flank, right_flank)
     empty = 0.00001 if accuracy_filter else 1
     right = float(hits["prefix"]) / bases["prefix"] if bases["prefix"] else empty
     left = float(hits["suffix"]) / bases["suffix"] if bases["suffix"] else empty
@@ -267,6 +275,27 @@ def frameshift_mutations(selected, pattern_length):
             if abs(lengths[unit] - pattern_length) <= 2:
                 mutations[label] = mutations.get(label, 0) + 1
     return mutations, repeat_bp
+
+
+def frameshift_state_tables(names):
+    """(class byte, number in the name) of every state: what ``advhmm_frameshift_candidates`` reads instead of
+    the state names (``"I7_2"`` -> kind insert, repeat part, 7)."""
+    import numpy as np
+    cls = state_classes(names)
+    label = np.full(len(names), -1, dtype=np.int32)
+    for i, n in enumerate(names):
+        if (cls[i] & 7) in (2, 3) and ((cls[i] >> 3) & 3) == 3:
+            label[i] = int(n.split("_")[0][1:])
+    return cls, label
+
+
+def frameshift_label(call):
+    """The reference's mutation key (``'I7A'`` / ``'D12'``) of an ``advhmm_frameshift_call`` record, or None."""
+    if call["kind"] == 0:
+        return None
+    if call["kind"] == 2:
+        return "I%d%s" % (call["column"], "ACGT"[call["base"]])
+    return "D%d" % call["column"]
 
 
 def state_classes(names, emis=None):

@@ -134,6 +134,39 @@ class GenotypingRun(object):
             out[spec.id]["vntr_bp_in_mapped_reads"] = m["vntr_bp"]
         return out
 
+    def find_frameshifts(self, reads_by_locus):
+        """``--frameshift`` mode (``genome_analyzer.py:260``, ``vntr_finder.py:776-780``, ``:265-309``) for all
+        loci: every read decoded to its full state path in ONE device call, recruited reads walked by the native
+        consumer (``advhmm_frameshift_candidates``, all host threads), the binomial test per locus
+        (``identify_frameshift``, scipy).  ``reads_by_locus``: {locus id: the reads ``find_frameshift_from_alignment_file``
+        would select from (mapped reads of the region)}.  -> {locus id: the frame-shifting state label, e.g.
+        ``'I7A'`` / ``'D12'``, or None}; ``self.frameshift_records`` keeps the per-locus records."""
+        from . import path_utils
+        batch, goff = [], [0]
+        for dec in self.decoders:
+            batch += [r.upper() for r in reads_by_locus.get(dec.id, ()) if "N" not in r.upper()]
+            goff.append(len(batch))
+        seqs, off = engine.encode_batch(batch)
+        models = [d.model._device_model() for d in self.decoders]
+        goff = np.asarray(goff, dtype=np.int64)
+        res = self.ctx._run(models, goff, seqs, off, False, True, False, None, want_summary=True)
+        if not hasattr(self, "_fs_tables"):
+            self._fs_tables = [path_utils.frameshift_state_tables([s.name for s in d.model.states]) for d in self.decoders]
+        scores = [d.min_score_to_select_a_read() for d in self.decoders]
+        rec = engine.frameshift_candidates(goff, [len(d.pattern) for d in self.decoders],
+                                           [np.nan if s is None else s for s in scores], self._fs_tables, res.logp,
+                                           res.summaries, res.path_len, res.path_off, res.paths, seqs, off)
+        self.frameshift_records = rec
+        out = {}
+        for dec, c in zip(self.decoders, rec):
+            vntr_len = sum(len(seg) for seg in dec.segments)                        # reference_vntr.get_length()
+            coverage = float(c["repeat_bp"]) / vntr_len / 2
+            label = path_utils.frameshift_label(c)
+            # find_frameshift_from_selected_reads divides by the coverage (ZeroDivisionError without repeat bases)
+            shifted = coverage > 0 and genotype.identify_frameshift(coverage, int(c["count"]), 1 / coverage)
+            out[dec.id] = label if shifted else None
+        return out
+
     def _call(self, seqs, off, goff, layout, accuracy_filter, is_haploid):
         models = [d.model._device_model() for d in self.decoders]
         res = self.ctx._run(models, np.asarray(goff, dtype=np.int64), seqs, off, False, False, False, None,

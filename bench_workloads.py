@@ -256,11 +256,25 @@ def run_frameshift(args):
     h_poff = torch.empty(R, dtype=torch.int64).pin_memory()
     h_path = torch.empty(path_cap, dtype=torch.int32).pin_memory()
     h_total = C.c_int64(0)
+    h_summ = torch.zeros((R, 8), dtype=torch.int32).pin_memory()
 
     def step_host():
-        engine._check(lib.advhmm_viterbi_multi(ctx._h, handles, len(models), goff.ctypes.data, h_seqs.data_ptr(), off.ctypes.data,
-                                               R, engine.WANT_PATH, h_logp.data_ptr(), h_plen.data_ptr(), h_poff.data_ptr(),
-                                               h_path.data_ptr(), path_cap, C.byref(h_total)))
+        engine._check(lib.advhmm_viterbi_multi_summary(
+            ctx._h, handles, len(models), goff.ctypes.data, h_seqs.data_ptr(), off.ctypes.data, R,
+            engine.WANT_PATH | engine.WANT_SUMMARY, h_logp.data_ptr(), h_plen.data_ptr(), h_poff.data_ptr(), h_path.data_ptr(),
+            path_cap, C.byref(h_total), h_summ.data_ptr()))
+
+    # what advhmm_frameshift_candidates reads instead of state names, per model (made once, like the models)
+    state_tables = [path_utils.frameshift_state_tables([s.name for s in d.model.states]) for d in decoders]
+    pattern_len = [len(d.pattern) for d in decoders]
+
+    def calls_native(threads=0):
+        """The same calls from the library: recruit_read + the path walk of find_frameshift_from_selected_reads for
+        every locus on all host threads."""
+        rec = engine.frameshift_candidates(goff, pattern_len, None, state_tables, h_logp.numpy(),
+                                           h_summ.numpy().view(engine.SUMMARY_DTYPE).reshape(-1), h_plen.numpy(), h_poff.numpy(),
+                                           h_path.numpy(), seqs, off, threads=threads)
+        return [(path_utils.frameshift_label(c), int(c["count"])) for c in rec]
 
     def calls_from_flat():
         """The frameshift call of every locus from the flat path array of the C-ABI route."""
@@ -293,6 +307,19 @@ def run_frameshift(args):
     tc = time.perf_counter()
     calls = calls_from_flat()
     consumers_s = time.perf_counter() - tc
+    calls_native()
+    tc = time.perf_counter()
+    for _ in range(5):
+        nat_calls = calls_native()
+    native_s = (time.perf_counter() - tc) / 5
+    tc = time.perf_counter()
+    calls_native(threads=1)
+    native1_s = time.perf_counter() - tc
+    # one step carried on to the calls: decode + native consumers, wall clock
+    tc = time.perf_counter()
+    step_host()
+    calls_native()
+    to_calls_s = time.perf_counter() - tc
     # pageable Python route, per locus, as a drop-in caller of vntr_finder's loop would run it
     tp = time.perf_counter()
     py_calls = []
@@ -314,12 +341,13 @@ def run_frameshift(args):
                    if path_utils.recruit_read(lp[i], [(int(x), st[x]) for x in paths[i]], None, r, dec.left_flank, dec.right_flank)]
             oracle_same = oracle_same and dec.frameshift_candidate(sel)[0] == calls[g]
     agree = calls == py_calls
+    native_agree = nat_calls == calls
     with_indel = sum(1 for c in calls if c[0] is not None and c[1] >= 3)
     e2e_all = D.reduce([e2e_ms], "max")[0]
     reads_all, cells_all = D.reduce([float(R), cells], "sum")
     if D.rank == 0:
         K = args.steps
-        if not agree or oracle_same is False:
+        if not agree or not native_agree or oracle_same is False:
             raise SystemExit("frameshift workload: calls differ between routes / from the CPU oracle")
         line = {"metric": "viterbi_reads_per_s", "value": reads_all * K / (e2e_all * 1e-3), "unit": "reads/s",
                 "gcups": cells_all * K / (e2e_all * 1e-3) / 1e9, "n_gpus": D.world, "steps": K, "warmup": max(args.warmup, 3),
@@ -330,13 +358,19 @@ def run_frameshift(args):
                            "loci_per_gpu": len(loci), "reads_per_gpu": R, "want_path": True},
                 "note": "value = e2e: pinned host reads in, logp + full state paths out through advhmm_viterbi_multi",
                 "e2e": {"value": reads_all * K / (e2e_all * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(off[-1]),
-                        "d2h_bytes_per_step": R * 20 + int(h_total.value) * 4},
+                        "d2h_bytes_per_step": R * 52 + int(h_total.value) * 4},
                 "frameshift": {"loci": len(loci), "loci_with_an_indel_call_of_3_or_more_reads": with_indel,
                                "calls_equal_between_c_abi_and_python_routes": agree,
                                "calls_equal_to_cpu_oracle_paths": oracle_same, "oracle_loci": n_or,
+                               "native_consumers_reads_per_s": R / native_s,
+                               "native_consumers_one_thread_reads_per_s": R / native1_s,
+                               "native_calls_equal_to_python_consumers": native_agree,
+                               "reads_to_calls_reads_per_s": R / to_calls_s,
                                "python_consumers_reads_per_s": R / consumers_s,
-                               "note": "python_consumers = recruit_read + find_frameshift_from_selected_reads on the flat path "
-                                       "array (host Python, one process): the --frameshift ceiling of a Python caller"},
+                               "note": "native_consumers = advhmm_frameshift_candidates (recruit_read + the path walk of "
+                                       "find_frameshift_from_selected_reads for every locus, all host threads) on the flat path "
+                                       "array; reads_to_calls = one decode step + native consumers, wall clock; python_consumers "
+                                       "= the same logic in host Python, one process: what a Python caller is bound by"},
                 "pageable_python_route": {"value": R / py_s, "unit": "reads/s",
                                           "note": "LocusDecoder.select_reads + frameshift_candidate per locus: viterbi_batch(list "
                                                   "of str), (idx, State) lists, Python consumers; one process"},

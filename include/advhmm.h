@@ -285,6 +285,30 @@ int advhmm_genotypes_from_summaries(int64_t n_loci, const int64_t* group_off, co
 int advhmm_genotypes_from_counts(int64_t n_lists, const int32_t* observed, const int64_t* obs_off, uint32_t flags,
                                  advhmm_locus_call* calls);
 
+/* --frameshift mode (genome_analyzer.py:260, vntr_finder.py:776-780): find_frameshift_from_selected_reads up
+ * to its binomial test (vntr_finder.py:265-300) for many loci on all host threads, from the FULL state paths
+ * advhmm_viterbi_multi_summary returned with ADVHMM_WANT_PATH | ADVHMM_WANT_SUMMARY (host arrays).  Per locus:
+ * every read of group_off[g] .. group_off[g+1]-1 that passes recruit_read is walked; insert / delete states of
+ * repeat units whose emitted length is off by 1 or 2 bases from pattern_len[g] are counted per (state label,
+ * inserted base); the candidate is the most frequent one (the last one found among equals, as the reference's
+ * stable sort leaves it).  States are described by their class byte (as for advhmm_model_set_state_classes)
+ * and, for the I / D states of the repeat units, the number in the state's name ("I7_2" -> 7): state s of
+ * locus g is state_class / state_label[state_off[g] + s].  seqs = the reads as they were decoded (codes). */
+typedef struct advhmm_frameshift_call {
+    int32_t kind;            /* 0: no candidate, 2: insert state, 3: delete state (class-byte kinds)         */
+    int32_t column;          /* the number in the candidate state's name                                      */
+    int32_t base;            /* insert states: code of the base inserted at the first visit; otherwise -1     */
+    int32_t count;           /* occurrences over the recruited reads                                          */
+    int32_t selected;        /* reads that passed recruit_read                                                */
+    int32_t reserved;
+    int64_t repeat_bp;       /* repeating base pairs in the recruited reads (the coverage of the test)       */
+} advhmm_frameshift_call;
+int advhmm_frameshift_candidates(int64_t n_loci, const int64_t* group_off, const int32_t* pattern_len, const double* min_score,
+                                 const int64_t* state_off, const uint8_t* state_class, const int32_t* state_label,
+                                 const double* logp, const advhmm_read_summary* summaries, const int32_t* path_len,
+                                 const int64_t* path_off, const int32_t* path, const uint8_t* seqs, const int64_t* seq_off,
+                                 int32_t n_threads, advhmm_frameshift_call* calls);
+
 /* ---- keyword pre-filter (the step before the hot path) ----------------------------------------
  * Replaces the Aho-Corasick scan of the `adVNTR-Filtering` binary (filtering/main.cc:229-300,
  * fed by genome_analyzer.py:173-197): count, for every read and locus, the occurrences of the

@@ -119,3 +119,90 @@ def test_native_calls_refuse_inconsistent_groups():
         engine.genotypes_from_summaries([0, 4], [1], [1], None, *args)          # 1 + 2 x 1 != 4
     calls, cls = engine.genotypes_from_summaries([0, 4], [2], [1], None, *args, want_read_class=True)
     assert len(calls) == 1 and len(cls) == 4
+
+
+# ------------------------------------------------------------------ --frameshift mode
+def _summary_records(decoder, reads, logp, paths):
+    """The on-device reducers' records, stated on the host with path_utils (CPU test: no device)."""
+    from advntr_b200 import path_utils
+    st = decoder.model.states
+    S = np.zeros(len(reads), engine.SUMMARY_DTYPE)
+    vpaths = []
+    for i, (r, p) in enumerate(zip(reads, paths)):
+        vp = [(int(x), st[x]) for x in p]
+        vpaths.append(vp)
+        ps = path_utils.summarize(vp)
+        hits, bases = path_utils.flank_match_counts(vp, r, decoder.left_flank, decoder.right_flank)
+        S[i] = (ps.repeats, ps.n_match, ps.repeat_bp, ps.left_bp, ps.right_bp, hits["suffix"], hits["prefix"], 0)
+        assert (bases["suffix"], bases["prefix"]) == (ps.left_bp, ps.right_bp)
+    return S, vpaths
+
+
+def test_frameshift_candidates_equal_the_python_consumers():
+    """advhmm_frameshift_candidates vs recruit_read + find_frameshift_from_selected_reads' path walk
+    (path_utils.frameshift_mutations, LocusDecoder.frameshift_candidate) on CPU-oracle paths of loci whose
+    sample carries a 1 bp indel (bench_workloads.frameshift_locus_reads)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle
+    import bench_workloads
+    from advntr_b200 import locus_batch, path_utils
+    goff, tables, plen_pat, lp_all, S_all, pl_all, po_all, pa_all, codes_all, want = [0], [], [], [], [], [], [], [], [], []
+    at = 0
+    for lid in (3, 4, 7, 11, 19, 26):
+        loc, reads = bench_workloads.frameshift_locus_reads(lid, coverage=14)
+        dec = locus_batch.LocusDecoder(loc.left, loc.right, loc.segments, read_length=150, locus_id=lid)
+        codes = [oracle.encode(r) for r in reads]
+        lp, paths = oracle.OracleModel(dec.model.baked).viterbi(codes)
+        S, vpaths = _summary_records(dec, reads, lp, paths)
+        sel = [locus_batch.SelectedRead(r, float(lp[i]), vpaths[i]) for i, r in enumerate(reads)
+               if path_utils.recruit_read(lp[i], vpaths[i], None, r, dec.left_flank, dec.right_flank)]
+        (label, count), repeat_bp = dec.frameshift_candidate(sel)
+        want.append((label, count, repeat_bp, len(sel)))
+        tables.append(path_utils.frameshift_state_tables([s.name for s in dec.model.states]))
+        plen_pat.append(len(dec.pattern))
+        for i, p in enumerate(paths):
+            lp_all.append(lp[i]); pl_all.append(len(p)); po_all.append(at); pa_all.append(np.asarray(p, np.int32)); at += len(p)
+            codes_all.append(np.asarray(codes[i], np.uint8))
+        S_all.append(S)
+        goff.append(goff[-1] + len(reads))
+    seqs, off = engine.pack_reads(codes_all)
+    got = engine.frameshift_candidates(goff, plen_pat, None, tables, lp_all, np.concatenate(S_all), pl_all, po_all,
+                                       np.concatenate(pa_all), seqs, off, threads=2)
+    assert sum(1 for w in want if w[0] is not None and w[1] >= 3) >= 3          # the planted indels are seen
+    for w, g in zip(want, got):
+        assert (path_utils.frameshift_label(g), int(g["count"]), int(g["repeat_bp"]), int(g["selected"])) == w
+
+
+def test_frameshift_candidate_of_the_reference_callsite_golden():
+    """tests/golden/callsite_frameshift.json: the candidate, its count and the coverage the reference's own
+    VNTRFinder.find_frameshift_from_selected_reads arrives at (make_golden.py), from the native consumer on
+    CPU-oracle paths of the same reads."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle
+    from advntr_b200 import locus_batch, path_utils, read_matcher
+    case = json.load(open(os.path.join(GOLDEN, "callsite_frameshift.json")))
+    left, right, segs = case["left"], case["right"], case["segments"]
+    dec = locus_batch.LocusDecoder(left, right, segs, read_length=150, flank_size=150)
+    om = oracle.OracleModel(dec.model.baked)
+    both = [s for r in case["unmapped"] for s in (r, locus_batch.reverse_complement(r))]
+    lp_u, paths_u = om.viterbi([oracle.encode(s) for s in both])
+    reads = list(case["mapped"])
+    st = dec.model.states
+    for j in range(len(case["unmapped"])):                      # select_illumina_reads: the better strand, > 2 repeat bp
+        k = 2 * j + 1 if lp_u[2 * j] < lp_u[2 * j + 1] else 2 * j
+        if path_utils.get_number_of_repeat_bp_matches_in_vpath([(int(x), st[x]) for x in paths_u[k]]) > 2:
+            reads.append(both[k])
+    codes = [oracle.encode(r) for r in reads]
+    lp, paths = om.viterbi(codes)
+    S, _ = _summary_records(dec, reads, lp, paths)
+    seqs, off = engine.pack_reads([np.asarray(c, np.uint8) for c in codes])
+    plen = [len(p) for p in paths]
+    poff = np.concatenate([[0], np.cumsum(plen)[:-1]])
+    got = engine.frameshift_candidates([0, len(reads)], [len(dec.pattern)], None,
+                                       [path_utils.frameshift_state_tables([s.name for s in st])], lp, S, plen, poff,
+                                       np.concatenate([np.asarray(p, np.int32) for p in paths]), seqs, off)[0]
+    assert (path_utils.frameshift_label(got), int(got["count"])) == (case["frameshift_candidate"], case["frameshift_count"])
+    assert int(got["selected"]) == len(case["selected_sequences"])
+    assert float(got["repeat_bp"]) / (30 * len(segs)) / 2 == case["avg_bp_coverage"]

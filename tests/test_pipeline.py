@@ -78,3 +78,31 @@ def test_pipeline_equals_per_locus_decoders_and_recovers_alleles():
                       sorted(plain[lid]["copy_numbers"]) == truth[lid])
     assert right_calls >= len(truth) - 2, (right_calls, {l: (plain[l]["copy_numbers"], truth[l]) for l in truth})
     run.close()
+
+
+@pytest.mark.gpu
+def test_frameshift_mode_equals_per_locus_python_consumers():
+    """GenotypingRun.find_frameshifts (one device call with full paths + the native consumer) against the per-locus
+    route a reference-shaped caller takes (LocusDecoder.select_reads -> frameshift_candidate -> identify_frameshift)."""
+    import bench_workloads
+    from advntr_b200 import genotype, locus_batch, path_utils, pipeline
+    specs, reads = [], {}
+    for lid in (2, 5, 9, 14, 23, 31, 40):
+        loc, rs = bench_workloads.frameshift_locus_reads(lid, coverage=30)
+        specs.append(pipeline.LocusSpec(lid, loc.left, loc.right, loc.segments))
+        reads[lid] = rs
+    run = pipeline.GenotypingRun(specs)
+    got = run.find_frameshifts(reads)
+    n_calls = 0
+    for spec, rec in zip(specs, run.frameshift_records):
+        dec = locus_batch.LocusDecoder(spec.left_flank, spec.right_flank, spec.repeat_segments, 150, locus_id=spec.id)
+        selected = dec.select_reads(reads[spec.id])
+        (label, count), repeat_bp = dec.frameshift_candidate(selected)
+        assert (path_utils.frameshift_label(rec), int(rec["count"]), int(rec["repeat_bp"]), int(rec["selected"])) == \
+            (label, count, repeat_bp, len(selected))
+        coverage = float(repeat_bp) / sum(len(s) for s in spec.repeat_segments) / 2
+        want = label if genotype.identify_frameshift(coverage, count, 1 / coverage) else None
+        assert got[spec.id] == want
+        n_calls += want is not None
+    assert n_calls >= 3
+    run.close()
