@@ -1035,7 +1035,7 @@ def roofline(ctx, wl, stats, fill_ms, fill_n, bt_ms, bt_n, total_ms, steps):
     fp64_achieved = ops * steps / fill_s / 1e9 if fill_s > 0 else None
     # DRAM bytes per read of this kernel from the committed ncu --set full capture (not measurable in-run)
     traffic, traffic_src = None, None
-    for name in ("r2_fill_traffic.json", "r1_fill_traffic.json"):
+    for name in ("r2b_fill_traffic.json", "r2_fill_traffic.json", "r1_fill_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tpath) and fill_n:
             try:
