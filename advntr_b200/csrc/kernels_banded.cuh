@@ -152,11 +152,14 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
     // ptxas from re-deriving these addresses inside the loop.
     uint32_t* tbw_t = tbw - (ptrdiff_t)lane * NW;
     double* vfin_t = vfin - 3 * lane;                   // interleaved: vfin[3 c + {0, 1, 2}] = I, M, D of column c
-    const uint32_t store_flag = ALIGNED ? (uint32_t)(lane == ln) : 0u;
+    const uint32_t store_flag = (uint32_t)(lane == ln);
     uint32_t w_t = s_base - (uint32_t)lane * 80u;       // + 80 t  -> w10[c]
     uint32_t e_t[RPL];                                  // + 16 t  -> e2[sym_j][c]
 #pragma unroll
     for (int j = 0; j < RPL; ++j) { e_t[j] = eaddr[j] - (uint32_t)lane * 16u; asm volatile("" : "+r"(e_t[j])); }
+    // lane 0 owns the first read position, whose I and M values come from the first-row table v1: its "emission"
+    // address of row 0 points there, so the step loads {vI, vM} of row 1 with the load every lane issues anyway
+    if (lane == 0) e_t[0] += v1_delta;
     asm volatile("" : "+l"(tbw_t), "+l"(vfin_t), "+r"(w_t));
 
     // One column step.  GUARD: some lanes are outside the column range (ramp-up / ramp-down of the
@@ -181,7 +184,7 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
         const uint32_t cb = (uint32_t)t * 16u;
 
         // M and D slots depend only on values of the previous column / previous step
-        double nM[RPL], nD[RPL], eIr[RPL];
+        double nM[RPL], nD[RPL], eIr[RPL], eM0 = 0.0;
         uint32_t word[NW];
 #pragma unroll
         for (int k = 0; k < NW; ++k) word[k] = 0;
@@ -195,17 +198,14 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
 #endif
         static_for<0, RPL>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
-            const double2 e = lds128(e_t[j] + cb);             // {eI, eM}
+            const double2 e = lds128(e_t[j] + cb);             // {eI, eM}; lane 0, row 0: {vI, vM} of the first row
             eIr[j] = e.x;
+            if (j == 0) eM0 = e.y;
             const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
             nM[j] = ADV_MAX3(6 * (j % 5) + 2, (oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, j / 5);
             nD[j] = ADV_MAX3(6 * (j % 5) + 4, cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, j / 5);
         });
-        if (lane == 0) {                                       // first read position: from row 0
-            const double2 f = lds128(e_t[0] + v1_delta + cb);
-            nM[0] = f.y;
-            eIr[0] = f.x;                                      // (carries vI of row 1, see below)
-        }
+        if (lane == 0) nM[0] = eM0;                            // first read position: from the row-0 table (e_t[0] above)
         // collector (end_repeating_pattern_match): D of its column is the best unit_end so far.
         // Both cases are rare per lane (1 and `copies` columns of NC), hence real branches.
         if (ACC && c == acc_col) {
@@ -252,12 +252,17 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
                          "@p st.global.f64 [%0], %1;\n\t@p st.global.f64 [%0+8], %2;\n\t@p st.global.f64 [%0+16], %3;\n\t}"
                          :: "l"(vfin_t + 3 * t), "d"(cI[RPL - 1]), "d"(cM[RPL - 1]), "d"(cD[RPL - 1]), "r"(store_flag) : "memory");
-        } else if (lane == ln) {
-            double fI = cI[0], fM = cM[0], fD = cD[0];
-#pragma unroll
-            for (int j = 1; j < RPL; ++j)
-                if (j == jn) { fI = cI[j]; fM = cM[j]; fD = cD[j]; }
-            vfin_t[3 * t] = fI; vfin_t[3 * t + 1] = fM; vfin_t[3 * t + 2] = fD;
+        } else {
+            // the last read position sits in row jn of lane ln; jn is warp-uniform, so this is a uniform jump to
+            // three predicated stores from fixed registers (a runtime select of the row cost 25 instructions per step)
+            double* const dst = vfin_t + 3 * t;
+            static_for<0, RPL - 1>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                if (jn == j)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
+                                 "@p st.global.f64 [%0], %1;\n\t@p st.global.f64 [%0+8], %2;\n\t@p st.global.f64 [%0+16], %3;\n\t}"
+                                 :: "l"(dst), "d"(cI[j]), "d"(cM[j]), "d"(cD[j]), "r"(store_flag) : "memory");
+            });
         }
     };
     // Lanes >= nl have no read positions: in the steady phase they run along (results land in their

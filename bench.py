@@ -897,7 +897,7 @@ class ShardRunner(object):
                 destroy_models(*prev)
             self.calls, _ = engine.genotypes_from_summaries(
                 goff, calls[0], calls[1], None, self.h_logp.numpy(), self.h_summ.numpy().view(engine.SUMMARY_DTYPE).reshape(-1),
-                self.h_plen.numpy(), off)
+                self.h_plen.numpy(), off, threads=compile_threads())          # this rank's share of the host cores
             return self.e0.elapsed_time(self.e1), compile_ms
         if R:
             self.d_res[:R, 0] = self.d_logp[:R].view(torch.int64)
