@@ -312,10 +312,21 @@ class Dist(object):
             raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback of the hot path")
         torch.cuda.set_device(self.local)
         if self.world > 1:
-            # whatever NCCL_DEBUG level the launcher asks for (its version banner included) goes to stderr:
-            # the contract is ONE JSON line on stdout
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            # the contract is ONE JSON line on stdout, and NCCL writes its version banner (and whatever NCCL_DEBUG
+            # level the launcher asks for) to file descriptor 1 when the communicator is made: descriptor 1 points
+            # at stderr until the communicator exists (device_id makes the initialisation eager, the barrier makes
+            # sure of it)
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
     def barrier(self):
         if self.world > 1:
