@@ -17,7 +17,10 @@
 //                            read positions, columns sweep as a register wavefront (skew 1
 //                            column per lane, 3 shuffles per step); model tables staged into
 //                            shared memory with one TMA bulk copy per CTA; 6-bit traceback per
-//                            (position, column) packed into one word per lane and step.
+//                            (position, column) packed into one word per lane and step.  The column
+//                            loop is phased (ramp-up / steady / the 32 steps around the collector's
+//                            column / steady / ramp-down) with warp-uniform bounds, so the steady
+//                            phase carries neither range tests nor the collector select.
 //   banded_fill_f32_kernel   the same schedule in float (optional ADVHMM_FP32 mode)
 //   banded_long_kernel<T,FWD> long reads / models larger than shared memory: 160-position
 //                            stripes dealt to 1..8 warps per read, carry through HBM with

@@ -85,50 +85,6 @@ __device__ __forceinline__ double max3_first(double a0, double a1, double a2, ui
     return m;
 }
 
-#ifdef ADV_TB_FADD
-// Measured variant (profiles/r2_variants.md): the traceback bits are summed as powers of two in two fp32
-// accumulators (bits 0..14, 15..29) by predicated FADDs -- the FMA pipe -- instead of predicated integer adds
-// on the ALU pipe, which already carries the 64-bit selects.
-struct TbAcc { float lo, hi; };
-template <int SH>
-__device__ __forceinline__ double max3_first_fa(double a0, double a1, double a2, TbAcc& acc)
-{
-    double m;
-    constexpr int S1 = SH, S2 = SH + 1;
-    const float c1 = __int_as_float((127 + (S1 % 15)) << 23), c2 = __int_as_float((127 + (S2 % 15)) << 23);
-    float& t1 = (S1 < 15) ? acc.lo : acc.hi;
-    float& t2 = (S2 < 15) ? acc.lo : acc.hi;
-    if constexpr ((S1 < 15) == (S2 < 15)) {
-        asm("{\n\t"
-            ".reg .pred p1, p2;\n\t"
-            ".reg .f64 t;\n\t"
-            "setp.gt.f64 p2, %4, %3;\n\t"
-            "selp.f64 t, %4, %3, p2;\n\t"
-            "@p2 add.f32 %1, %1, %6;\n\t"
-            "setp.gt.f64 p1, t, %2;\n\t"
-            "selp.f64 %0, t, %2, p1;\n\t"
-            "@p1 add.f32 %1, %1, %5;\n\t"
-            "}"
-            : "=d"(m), "+f"(t1)
-            : "d"(a0), "d"(a1), "d"(a2), "f"(c1), "f"(c2));
-    } else {
-        asm("{\n\t"
-            ".reg .pred p1, p2;\n\t"
-            ".reg .f64 t;\n\t"
-            "setp.gt.f64 p2, %5, %4;\n\t"
-            "selp.f64 t, %5, %4, p2;\n\t"
-            "@p2 add.f32 %2, %2, %7;\n\t"
-            "setp.gt.f64 p1, t, %3;\n\t"
-            "selp.f64 %0, t, %3, p1;\n\t"
-            "@p1 add.f32 %1, %1, %6;\n\t"
-            "}"
-            : "=d"(m), "+f"(t1), "+f"(t2)
-            : "d"(a0), "d"(a1), "d"(a2), "f"(c1), "f"(c2));
-    }
-    return m;
-}
-#endif
-
 // ALIGNED: the read length is a multiple of RPL, so the last read position is the last row of a
 // lane and its values can be stored from fixed registers.
 template <int RPL, bool ALIGNED>
@@ -188,22 +144,14 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
         uint32_t word[NW];
 #pragma unroll
         for (int k = 0; k < NW; ++k) word[k] = 0;
-#ifdef ADV_TB_FADD
-        TbAcc tacc[NW];
-#pragma unroll
-        for (int k = 0; k < NW; ++k) tacc[k].lo = tacc[k].hi = 0.0f;
-#define ADV_MAX3(SH, A0, A1, A2, K) max3_first_fa<SH>(A0, A1, A2, tacc[K])
-#else
-#define ADV_MAX3(SH, A0, A1, A2, K) max3_first<SH>(A0, A1, A2, word[K])
-#endif
         static_for<0, RPL>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             const double2 e = lds128(e_t[j] + cb);             // {eI, eM}; lane 0, row 0: {vI, vM} of the first row
             eIr[j] = e.x;
             if (j == 0) eM0 = e.y;
             const double oI = j ? cI[j ? j - 1 : 0] : bI, oM = j ? cM[j ? j - 1 : 0] : bM, oD = j ? cD[j ? j - 1 : 0] : bD;
-            nM[j] = ADV_MAX3(6 * (j % 5) + 2, (oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, j / 5);
-            nD[j] = ADV_MAX3(6 * (j % 5) + 4, cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, j / 5);
+            nM[j] = max3_first<6 * (j % 5) + 2>((oI + wMI) + e.y, (oM + wMM) + e.y, (oD + wMD) + e.y, word[j / 5]);
+            nD[j] = max3_first<6 * (j % 5) + 4>(cI[j] + wDI, cM[j] + wDM, cD[j] + wDD, word[j / 5]);
         });
         if (lane == 0) nM[0] = eM0;                            // first read position: from the row-0 table (e_t[0] above)
         // collector (end_repeating_pattern_match): D of its column is the best unit_end so far.
@@ -212,11 +160,7 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
 #pragma unroll
             for (int j = 0; j < RPL; ++j) nD[j] = acc[j];
         }
-#ifdef ADV_AW_INT
-        if (__double2hiint(aw) != (int)0xfff00000) {           // -inf has no other pattern: the test leaves the fp64 pipe
-#else
         if (aw > kNegInf) {                                    // a unit_end column
-#endif
 #pragma unroll
             for (int j = 0; j < RPL; ++j) {
                 const double cand = nD[j] + aw;
@@ -229,24 +173,14 @@ __device__ __forceinline__ void banded_sweep(const int NC, const int P, const in
         double uI = uI0, uM = uM0, uD = uD0;
         static_for<0, RPL>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
-            double vI = ADV_MAX3(6 * (j % 5), (uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], j / 5);
+            double vI = max3_first<6 * (j % 5)>((uI + wII) + eIr[j], (uM + wIM) + eIr[j], (uD + wID) + eIr[j], word[j / 5]);
             if (j == 0 && lane == 0) vI = eIr[0];
             uI = vI; uM = nM[j]; uD = nD[j];
             cI[j] = vI; cM[j] = nM[j]; cD[j] = nD[j];
         });
-#undef ADV_MAX3
-#ifdef ADV_TB_FADD
-#pragma unroll
-        for (int k = 0; k < NW; ++k) word[k] = __float2uint_rz(tacc[k].lo) | (__float2uint_rz(tacc[k].hi) << 15);
-#endif
         bI = uI0; bM = uM0; bD = uD0;
-#ifdef ADV_TB_STCS
-        if (NW == 1) __stcs(&tbw_t[t], word[0]);
-        else __stcs(&reinterpret_cast<uint2*>(tbw_t)[t], make_uint2(word[0], word[NW - 1]));
-#else
         if (NW == 1) tbw_t[t] = word[0];
         else reinterpret_cast<uint2*>(tbw_t)[t] = make_uint2(word[0], word[NW - 1]);
-#endif
         if (ALIGNED) {
             // predicated stores, no branch: the step stays one basic block up to the collector
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
