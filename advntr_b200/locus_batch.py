@@ -216,12 +216,12 @@ def dominant_copy_numbers_from_spanning_reads(left_flank, right_flank, repeat_se
     max_copies = int(round(longest / float(len(pattern))))
     model = fast_compile.build_vntr_matcher_hmm(left_flank, right_flank, list(repeat_segments), max_copies,
                                                 flank_size=100, error_rate=error_rate)
-    res = model.viterbi_batch([r.upper() for r in spanning_reads])
-    states = model.states
-    observed = []
-    for i in range(len(spanning_reads)):
-        p = res.path(i)
-        observed.append(path_utils.get_number_of_repeats_in_vpath([(int(k), states[k]) for k in p]))
+    # the repeat count of every read comes from the on-device path reducer (get_number_of_repeats_in_vpath on the
+    # device): the 10-20 k state paths of PacBio reads stay there
+    res = model.viterbi_batch([r.upper() for r in spanning_reads], want_path=False, want_summary=True)
+    if (res.path_len < 0).any():                     # the reference subscripts the None path of an impossible read
+        raise TypeError("'NoneType' object is not subscriptable")
+    observed = [int(x) for x in res.summaries["repeats"]]
     copy_numbers, max_prob = genotype.dominant_copy_numbers(observed, accuracy_filter, is_haploid)
     return copy_numbers, max_prob, observed
 
