@@ -2025,8 +2025,13 @@ int advhmm_frameshift_candidates(int64_t n_loci, const int64_t* group_off, const
                     ++c.selected;
                     c.repeat_bp += summaries[i].repeat_bp;
                     const int32_t* p = path + path_off[i];
-                    for (int32_t k = 0; k < path_len[i]; ++k)
+                    int64_t emitted = 0;                               // a path must be one of ITS read on ITS model
+                    for (int32_t k = 0; k < path_len[i]; ++k) {
                         if (p[k] < 0 || p[k] >= n_states) { bad.store(i); return; }
+                        const int kind = state_class[state_off[g] + p[k]] & 7;
+                        emitted += (k > 0 && k + 1 < path_len[i]) && (kind == 1 || kind == 2);
+                    }
+                    if (emitted != seq_off[i + 1] - seq_off[i]) { bad.store(i); return; }
                     calls::frameshift_mutations_of_read(
                         calls::PathView{p, path_len[i], state_class + state_off[g], state_label + state_off[g], seqs + seq_off[i]},
                         pattern_len[g], mut, lengths, first_visit);
@@ -2042,7 +2047,7 @@ int advhmm_frameshift_candidates(int64_t n_loci, const int64_t* group_off, const
     } catch (const std::exception& e) {
         return set_error(ADVHMM_EINVAL, "%s", e.what());
     }
-    if (bad.load() >= 0) return set_error(ADVHMM_EINVAL, "read %lld: a path entry is not a state of its locus's model", (long long)bad.load());
+    if (bad.load() >= 0) return set_error(ADVHMM_EINVAL, "read %lld: its path is not a path of this read on its locus's model (state index or emitted length)", (long long)bad.load());
     return ADVHMM_OK;
 }
 

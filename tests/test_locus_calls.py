@@ -206,3 +206,20 @@ def test_frameshift_candidate_of_the_reference_callsite_golden():
     assert (path_utils.frameshift_label(got), int(got["count"])) == (case["frameshift_candidate"], case["frameshift_count"])
     assert int(got["selected"]) == len(case["selected_sequences"])
     assert float(got["repeat_bp"]) / (30 * len(segs)) / 2 == case["avg_bp_coverage"]
+
+
+def test_frameshift_candidates_refuse_foreign_paths():
+    """A path that is not a path of its read on its model (state index out of range, emitted length) is an error,
+    not a silent walk over someone else's memory."""
+    S = np.zeros(1, engine.SUMMARY_DTYPE)
+    S["n_match"], S["left_bp"], S["left_hits"], S["right_bp"], S["right_hits"] = 1, 1, 1, 1, 1
+    cls = np.array([0, 1 | (3 << 3), 0], np.uint8)                 # start, a repeat-unit match state, end
+    tables = [(cls, np.full(3, -1, np.int32))]
+    ok = dict(group_off=[0, 1], pattern_len=[5], min_score=[-100.0], state_tables=tables, logp=[-1.0], summaries=S,
+              path_len=[3], path_off=[0], paths=[0, 1, 2], seqs=[2, 0], seq_off=[0, 1])
+    rec = engine.frameshift_candidates(**ok)
+    assert int(rec[0]["selected"]) == 1 and int(rec[0]["kind"]) == 0
+    with pytest.raises(engine.EngineError):
+        engine.frameshift_candidates(**dict(ok, paths=[0, 7, 2]))
+    with pytest.raises(engine.EngineError):
+        engine.frameshift_candidates(**dict(ok, seq_off=[0, 2]))
