@@ -255,6 +255,9 @@ def cpu_reference_pass(n_sample_loci, coverage, decoys, procs):
             "procs": len(slices), "reads_per_s": reads / busy, "gcups": cells / busy / 1e9}
 
 
+ONE_PROCESS_SAMPLE_LOCI = 4        # the single-process figure of the CPU baseline: ~600 reads, a few seconds
+
+
 def auto_sample_loci(procs):
     # ~155 reads/locus at ~200 reads/s/core: one locus per worker is ~0.8 s of decoding; aim at
     # roughly 15 s of CPU work per pass
@@ -274,6 +277,9 @@ def run_reference_arm(args):
             times.append(last)
     reads_s = sum(t["reads"] for t in times) / sum(t["seconds"] for t in times)
     gcups = sum(t["cells"] for t in times) / sum(t["seconds"] for t in times) / 1e9
+    one = cpu_reference_pass(ONE_PROCESS_SAMPLE_LOCI, args.coverage, args.decoys, 1)
+    one_process = {"value": one["reads_per_s"], "unit": "reads/s", "gcups": one["gcups"],
+                   "sample": "%d reads of the first %d config-2 loci, %.1f s" % (one["reads"], ONE_PROCESS_SAMPLE_LOCI, one["seconds"])}
     sample = "the first %d of the %d config-2 loci (%d reads) per step, %d processes" % (
         n_loci, args.loci, last["reads"], last["procs"])
     line = {"impl": "reference", "metric": "viterbi_reads_per_s", "value": reads_s, "unit": "reads/s",
@@ -284,7 +290,7 @@ def run_reference_arm(args):
             "config": workload_config(args, args.loci),
             "cpu_sample_loci": n_loci,
             "cpu_baseline": {"value": reads_s, "unit": "reads/s", "cores": last["procs"], "kind": last["kind"],
-                             "sample": sample},
+                             "sample": sample, "one_process": one_process},
             "e2e": {"value": reads_s, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -777,10 +783,14 @@ def run_ours(args):
             procs = host_cores()
             n_cpu = args.cpu_sample_loci or auto_sample_loci(procs)
             cb = cpu_reference_pass(n_cpu, args.coverage, args.decoys, procs)
+            one = cpu_reference_pass(ONE_PROCESS_SAMPLE_LOCI, args.coverage, args.decoys, 1)
             line["cpu_baseline"] = {"value": cb["reads_per_s"], "unit": "reads/s", "gcups": cb["gcups"],
                                     "cores": cb["procs"], "kind": cb["kind"],
                                     "sample": "%d reads of the first %d config-2 loci, %.1f s" %
-                                              (cb["reads"], n_cpu, cb["seconds"])}
+                                              (cb["reads"], n_cpu, cb["seconds"]),
+                                    "one_process": {"value": one["reads_per_s"], "unit": "reads/s", "gcups": one["gcups"],
+                                                    "sample": "%d reads of the first %d config-2 loci, %.1f s" %
+                                                              (one["reads"], ONE_PROCESS_SAMPLE_LOCI, one["seconds"])}}
         print(json.dumps(line))
     for m in models:
         m.close()
