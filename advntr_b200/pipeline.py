@@ -24,7 +24,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import bam_ingest, engine, fast_compile, genotype, keyword_filter
+from . import bam_ingest, engine, fast_compile, genotype, keyword_filter, path_utils
 from .locus_batch import LocusDecoder, reverse_complement
 
 
@@ -141,7 +141,6 @@ class GenotypingRun(object):
         (``identify_frameshift``, scipy).  ``reads_by_locus``: {locus id: the reads ``find_frameshift_from_alignment_file``
         would select from (mapped reads of the region)}.  -> {locus id: the frame-shifting state label, e.g.
         ``'I7A'`` / ``'D12'``, or None}; ``self.frameshift_records`` keeps the per-locus records."""
-        from . import path_utils
         batch, goff = [], [0]
         for dec in self.decoders:
             batch += [r.upper() for r in reads_by_locus.get(dec.id, ()) if "N" not in r.upper()]
