@@ -124,3 +124,40 @@ def test_two_rank_gloo_gather_of_result_rows(tmp_path):
     mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     ok, n_rows, ranks_used = np.load(os.path.join(str(tmp_path), "ok.npy"))
     assert ok == 1 and n_rows > 40000 and ranks_used == 2
+
+
+def _calls_worker(rank, world, port, out_dir):
+    import sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import test_locus_calls as T
+    from advntr_b200 import engine
+    # the same per-read results on every rank (seeded); each rank calls only the loci it owns
+    logp, S, plen, off, goff, layout, scores = T._random_results(np.random.default_rng(77), 240, 0.9)
+    reads = np.diff(goff)
+    owner, _ = sharding.lpt_assign(reads.tolist(), world)
+    score = np.array([np.nan if s is None else s for s in scores])
+    local = {}
+    for g in sharding.my_units(owner, rank):
+        a, b = int(goff[g]), int(goff[g + 1])
+        rec, _ = engine.genotypes_from_summaries([0, b - a], [layout[g][0]], [layout[g][1]], score[g:g + 1], logp[a:b], S[a:b],
+                                                 plen[a:b], off[a:b + 1], threads=1)
+        local[g] = rec.tobytes()
+    full = sharding.gather_results(local, owner, rank, world)
+    whole, _ = engine.genotypes_from_summaries(goff, [m for m, _ in layout], [u for _, u in layout], score, logp, S, plen, off)
+    ok = b"".join(full) == whole.tobytes() and int(whole["has_call"].sum()) > 100 and len(set(owner)) == world
+    open(os.path.join(out_dir, "calls%d.ok" % rank), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_locus_calls_gather(tmp_path):
+    """The step after the decode shards like the decode: every rank calls its own loci with the native stage,
+    the gathered records equal one call over all loci."""
+    port = _free_port()
+    mp.spawn(_calls_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(os.path.join(str(tmp_path), "calls%d.ok" % r)).read() == "1"
